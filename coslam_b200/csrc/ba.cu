@@ -1,0 +1,950 @@
+// ba.cu -- host side of the bundle-adjustment solver + its C-ABI (see include/coslam_b200.h).
+// Replaces bundleAdjustRobust (LibVisualSLAM, call app/SL_CoSLAMRobustBA.cpp:174) and
+// sba_motstr_levmar_x (sba-1.6, call app/SL_CoSLAMBA.cpp:360-363).  The LM control flow mirrors
+// oracle/ba_oracle.cpp:levmar line by line; every arithmetic step runs in the kernels of
+// ba_kernels.cuh.  Multi-GPU: points (with all their observations) are sharded over the ranks,
+// cameras are replicated; per LM trial one NCCL all-reduce (sum) of the packed buffer
+// [S | rhs] and one of a handful of scalars; per linearisation one of [U | ea] and one max-reduce.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "ba_kernels.cuh"
+#include "common.cuh"
+
+using namespace coslam;
+
+/* ---------------------------------------------------------------- NCCL through dlopen */
+namespace {
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSum = 0, ncclMax = 2, ncclFloat64 = 8 };
+
+struct NcclApi {
+  void* handle = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool ok = false;
+};
+
+NcclApi& nccl() {
+  static NcclApi api;
+  if (api.handle) return api;
+  // an already-loaded libnccl (e.g. the one torch bundles) wins: same SONAME
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* n : names) {
+    api.handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    if (api.handle) break;
+  }
+  if (!api.handle) return api;
+  api.GetUniqueId = (int (*)(ncclUniqueId*))dlsym(api.handle, "ncclGetUniqueId");
+  api.CommInitRank =
+      (int (*)(ncclComm_t*, int, ncclUniqueId, int))dlsym(api.handle, "ncclCommInitRank");
+  api.CommDestroy = (int (*)(ncclComm_t))dlsym(api.handle, "ncclCommDestroy");
+  api.AllReduce = (int (*)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t))dlsym(
+      api.handle, "ncclAllReduce");
+  api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
+  api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllReduce;
+  return api;
+}
+
+}  // namespace
+
+struct cosl_ba_comm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, nranks = 1, device = 0;
+};
+
+/* ---------------------------------------------------------------- solver state */
+struct cosl_ba_solver {
+  cosl_ba_options opt;
+  cosl_ba_comm* comm = nullptr;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  BaDev d;
+  // host copies needed for write-back
+  int m = 0, n = 0, mcon = 0, ncon = 0, mf = 0, ns = 0;
+  long long N = 0, Nc = 0;
+  std::vector<double> q0;  // m x 4
+  // device buffers
+  double *d_camK = nullptr, *d_camR0 = nullptr;
+  double *d_pa = nullptr, *d_na = nullptr, *d_dpa = nullptr;
+  double *d_pb = nullptr, *d_nb = nullptr, *d_dpb = nullptr;
+  int *d_cam = nullptr, *d_pt = nullptr, *d_cobs = nullptr, *d_ccam = nullptr;
+  double *d_xy = nullptr, *d_wgt = nullptr;
+  long long* d_ptr = nullptr;
+  double *d_W = nullptr, *d_V = nullptr, *d_eb = nullptr;
+  double* d_Uea = nullptr;   // [U (m x 21) | ea (m x 6)] contiguous for one all-reduce
+  double* d_Srhs = nullptr;  // [S (ns x ns) | rhs (ns)] contiguous for one all-reduce
+  double *d_y = nullptr, *d_x = nullptr;
+  double* d_sc = nullptr;
+  unsigned char* d_outlier = nullptr;
+  BaPairItem* d_items = nullptr;
+  int2* d_entries = nullptr;
+  int nItems = 0;
+  long long nEntries = 0;
+  double* h_sc = nullptr;  // pinned
+  bool smallSolve = true;
+  SectionTimer timer;
+  int secLin = 0, secSchur = 0, secSolve = 0, secBack = 0, secCost = 0, secComm = 0;
+  // statistics
+  int nfev = 0, njev = 0, nlss = 0;
+};
+
+namespace {
+
+void quat2mat(const double q[4], double R[9]) {
+  const double w = q[0], x = q[1], y = q[2], z = q[3];
+  R[0] = w * w + x * x - y * y - z * z;
+  R[1] = 2 * (x * y - w * z);
+  R[2] = 2 * (x * z + w * y);
+  R[3] = 2 * (x * y + w * z);
+  R[4] = w * w - x * x + y * y - z * z;
+  R[5] = 2 * (y * z - w * x);
+  R[6] = 2 * (x * z - w * y);
+  R[7] = 2 * (y * z + w * x);
+  R[8] = w * w - x * x - y * y + z * z;
+}
+
+// mat2quat of LibVisualSLAM geometry/SL_Quaternion.h is not in the tree; Shepperd's method,
+// normalised, w >= 0 (same as the oracle)
+void mat2quat(const double R[9], double q[4]) {
+  const double tr = R[0] + R[4] + R[8];
+  double w, x, y, z;
+  if (tr > 0) {
+    double s = std::sqrt(tr + 1.0) * 2;
+    w = 0.25 * s;
+    x = (R[7] - R[5]) / s;
+    y = (R[2] - R[6]) / s;
+    z = (R[3] - R[1]) / s;
+  } else if (R[0] > R[4] && R[0] > R[8]) {
+    double s = std::sqrt(1.0 + R[0] - R[4] - R[8]) * 2;
+    w = (R[7] - R[5]) / s;
+    x = 0.25 * s;
+    y = (R[1] + R[3]) / s;
+    z = (R[2] + R[6]) / s;
+  } else if (R[4] > R[8]) {
+    double s = std::sqrt(1.0 + R[4] - R[0] - R[8]) * 2;
+    w = (R[2] - R[6]) / s;
+    x = (R[1] + R[3]) / s;
+    y = 0.25 * s;
+    z = (R[5] + R[7]) / s;
+  } else {
+    double s = std::sqrt(1.0 + R[8] - R[0] - R[4]) * 2;
+    w = (R[3] - R[1]) / s;
+    x = (R[2] + R[6]) / s;
+    y = (R[5] + R[7]) / s;
+    z = 0.25 * s;
+  }
+  double nrm = std::sqrt(w * w + x * x + y * y + z * z);
+  if (w < 0) nrm = -nrm;
+  q[0] = w / nrm;
+  q[1] = x / nrm;
+  q[2] = y / nrm;
+  q[3] = z / nrm;
+}
+
+void quat_mul(const double a[4], const double b[4], double p[4]) {
+  p[0] = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  p[1] = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  p[2] = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  p[3] = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+}
+
+template <typename T>
+int dev_alloc(T** p, size_t count) {
+  COSL_CUDA(cudaMalloc((void**)p, sizeof(T) * (count ? count : 1)));
+  return COSL_OK;
+}
+
+int upload_params(cosl_ba_solver* s, const cosl_ba_problem* p) {
+  const int m = s->m;
+  std::vector<double> R0((size_t)m * 9), pa((size_t)m * 6, 0.0);
+  s->q0.resize((size_t)m * 4);
+  for (int j = 0; j < m; ++j) {
+    mat2quat(p->R + 9 * j, &s->q0[4 * j]);
+    quat2mat(&s->q0[4 * j], &R0[9 * j]);
+    for (int k = 0; k < 3; ++k) pa[6 * j + 3 + k] = p->t[3 * j + k];
+  }
+  COSL_CUDA(cudaMemcpyAsync(s->d_camR0, R0.data(), sizeof(double) * 9 * m, cudaMemcpyHostToDevice,
+                            s->stream));
+  COSL_CUDA(cudaMemcpyAsync(s->d_pa, pa.data(), sizeof(double) * 6 * m, cudaMemcpyHostToDevice,
+                            s->stream));
+  COSL_CUDA(cudaMemcpyAsync(s->d_pb, p->X, sizeof(double) * 3 * (size_t)s->n,
+                            cudaMemcpyHostToDevice, s->stream));
+  COSL_CUDA(cudaStreamSynchronize(s->stream));
+  return COSL_OK;
+}
+
+void free_solver(cosl_ba_solver* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  s->timer.destroy();
+  void* bufs[] = {s->d_camK, s->d_camR0, s->d_pa, s->d_na, s->d_dpa, s->d_pb, s->d_nb, s->d_dpb,
+                  s->d_cam, s->d_pt, s->d_cobs, s->d_ccam, s->d_xy, s->d_wgt, s->d_ptr, s->d_W,
+                  s->d_V, s->d_eb, s->d_Uea, s->d_Srhs, s->d_y, s->d_x, s->d_sc, s->d_outlier,
+                  s->d_items, s->d_entries};
+  for (void* b : bufs) cudaFree(b);
+  if (s->h_sc) cudaFreeHost(s->h_sc);
+  if (s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+}
+
+int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
+  const int m = p->m, n = p->n, mcon = p->m_con, ncon = p->n_con;
+  const long long N = p->nobs;
+  s->m = m;
+  s->n = n;
+  s->mcon = mcon;
+  s->ncon = ncon;
+  s->mf = m - mcon;
+  s->ns = 6 * s->mf;
+  s->N = N;
+  // host-side index structures
+  std::vector<int> pt((size_t)N), cam((size_t)N);
+  for (int i = 0; i < n; ++i) {
+    if (p->ptr[i + 1] < p->ptr[i]) return set_error(COSL_E_INVALID, "ptr not monotone at %d", i);
+    for (long long o = p->ptr[i]; o < p->ptr[i + 1]; ++o) pt[o] = i;
+  }
+  for (long long o = 0; o < N; ++o) {
+    cam[o] = p->cam[o];
+    if (cam[o] < 0 || cam[o] >= m) return set_error(COSL_E_INVALID, "camera index out of range");
+  }
+  // camera-major list of the free-camera observations
+  std::vector<long long> cptr(m + 1, 0);
+  for (long long o = 0; o < N; ++o)
+    if (cam[o] >= mcon) cptr[cam[o] + 1]++;
+  for (int j = 0; j < m; ++j) cptr[j + 1] += cptr[j];
+  const long long Nc = cptr[m];
+  s->Nc = Nc;
+  std::vector<int> cobs((size_t)Nc), ccam((size_t)Nc);
+  {
+    std::vector<long long> fill(cptr.begin(), cptr.end() - 1);
+    for (long long o = 0; o < N; ++o)
+      if (cam[o] >= mcon) {
+        const long long q = fill[cam[o]]++;
+        cobs[q] = (int)o;
+        ccam[q] = cam[o];
+      }
+  }
+  // pair lists of the Schur contraction: for every free point, every pair (a <= b) of its
+  // free-camera observations, bucketed by camera pair (counting sort)
+  const int mf = s->mf;
+  std::vector<long long> pcount((size_t)mf * mf + 1, 0);
+  for (int i = ncon; i < n; ++i) {
+    for (long long a = p->ptr[i]; a < p->ptr[i + 1]; ++a) {
+      if (cam[a] < mcon) continue;
+      for (long long b = a; b < p->ptr[i + 1]; ++b) {
+        if (cam[b] < mcon) continue;
+        int ja = cam[a] - mcon, jb = cam[b] - mcon;
+        if (ja > jb) std::swap(ja, jb);
+        pcount[(size_t)ja * mf + jb + 1]++;
+      }
+    }
+  }
+  for (size_t k = 0; k < (size_t)mf * mf; ++k) pcount[k + 1] += pcount[k];
+  const long long nEntries = pcount[(size_t)mf * mf];
+  s->nEntries = nEntries;
+  std::vector<int2> entries((size_t)nEntries);
+  {
+    std::vector<long long> fill(pcount.begin(), pcount.end() - 1);
+    for (int i = ncon; i < n; ++i)
+      for (long long a = p->ptr[i]; a < p->ptr[i + 1]; ++a) {
+        if (cam[a] < mcon) continue;
+        for (long long b = a; b < p->ptr[i + 1]; ++b) {
+          if (cam[b] < mcon) continue;
+          int ja = cam[a] - mcon, jb = cam[b] - mcon;
+          long long oa = a, ob = b;
+          if (ja > jb) {
+            std::swap(ja, jb);
+            std::swap(oa, ob);
+          }
+          entries[fill[(size_t)ja * mf + jb]++] = make_int2((int)oa, (int)ob);
+        }
+      }
+  }
+  std::vector<BaPairItem> items;
+  const int chunk = 512;
+  for (int ja = 0; ja < mf; ++ja)
+    for (int jb = ja; jb < mf; ++jb) {
+      const long long b0 = pcount[(size_t)ja * mf + jb], b1 = pcount[(size_t)ja * mf + jb + 1];
+      for (long long b = b0; b < b1; b += chunk) {
+        BaPairItem it;
+        it.rowCam = ja;
+        it.colCam = jb;
+        it.begin = (int)b;
+        it.end = (int)std::min(b1, b + chunk);
+        items.push_back(it);
+      }
+    }
+  s->nItems = (int)items.size();
+  // intrinsics: only K0,K1,K2,K4,K5 are used (as BundleRTS packs them, app/SL_CoSLAMBA.cpp:337-343)
+  std::vector<double> camK((size_t)m * 5);
+  for (int j = 0; j < m; ++j) {
+    const double* K = p->K + 9 * j;
+    camK[5 * j] = K[0];
+    camK[5 * j + 1] = K[1];
+    camK[5 * j + 2] = K[2];
+    camK[5 * j + 3] = K[4];
+    camK[5 * j + 4] = K[5];
+  }
+  // device allocations
+  COSL_TRY(dev_alloc(&s->d_camK, (size_t)m * 5));
+  COSL_TRY(dev_alloc(&s->d_camR0, (size_t)m * 9));
+  COSL_TRY(dev_alloc(&s->d_pa, (size_t)m * 6));
+  COSL_TRY(dev_alloc(&s->d_na, (size_t)m * 6));
+  COSL_TRY(dev_alloc(&s->d_dpa, (size_t)m * 6));
+  COSL_TRY(dev_alloc(&s->d_pb, (size_t)n * 3));
+  COSL_TRY(dev_alloc(&s->d_nb, (size_t)n * 3));
+  COSL_TRY(dev_alloc(&s->d_dpb, (size_t)n * 3));
+  COSL_TRY(dev_alloc(&s->d_cam, (size_t)N));
+  COSL_TRY(dev_alloc(&s->d_pt, (size_t)N));
+  COSL_TRY(dev_alloc(&s->d_cobs, (size_t)Nc));
+  COSL_TRY(dev_alloc(&s->d_ccam, (size_t)Nc));
+  COSL_TRY(dev_alloc(&s->d_xy, (size_t)N * 2));
+  COSL_TRY(dev_alloc(&s->d_wgt, (size_t)N));
+  COSL_TRY(dev_alloc(&s->d_ptr, (size_t)n + 1));
+  COSL_TRY(dev_alloc(&s->d_W, (size_t)N * 18));
+  COSL_TRY(dev_alloc(&s->d_V, (size_t)n * 6));
+  COSL_TRY(dev_alloc(&s->d_eb, (size_t)n * 3));
+  COSL_TRY(dev_alloc(&s->d_Uea, (size_t)m * 27));
+  COSL_TRY(dev_alloc(&s->d_Srhs, (size_t)s->ns * s->ns + s->ns));
+  COSL_TRY(dev_alloc(&s->d_y, (size_t)s->ns));
+  COSL_TRY(dev_alloc(&s->d_x, (size_t)s->ns));
+  COSL_TRY(dev_alloc(&s->d_sc, (size_t)SC_NTOT));
+  COSL_TRY(dev_alloc(&s->d_outlier, (size_t)N));
+  COSL_TRY(dev_alloc(&s->d_items, items.size()));
+  COSL_TRY(dev_alloc(&s->d_entries, (size_t)nEntries));
+  COSL_CUDA(cudaMallocHost(&s->h_sc, sizeof(double) * SC_NTOT));
+#define UP(dst, src, bytes) \
+  COSL_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s->stream))
+  UP(s->d_camK, camK.data(), sizeof(double) * 5 * m);
+  UP(s->d_cam, cam.data(), sizeof(int) * (size_t)N);
+  UP(s->d_pt, pt.data(), sizeof(int) * (size_t)N);
+  if (Nc) {
+    UP(s->d_cobs, cobs.data(), sizeof(int) * (size_t)Nc);
+    UP(s->d_ccam, ccam.data(), sizeof(int) * (size_t)Nc);
+  }
+  UP(s->d_xy, p->xy, sizeof(double) * 2 * (size_t)N);
+  UP(s->d_ptr, p->ptr, sizeof(long long) * ((size_t)n + 1));
+  if (!items.empty()) UP(s->d_items, items.data(), sizeof(BaPairItem) * items.size());
+  if (nEntries) UP(s->d_entries, entries.data(), sizeof(int2) * (size_t)nEntries);
+#undef UP
+  COSL_CUDA(cudaStreamSynchronize(s->stream));
+  BaDev& d = s->d;
+  d.m = m;
+  d.n = n;
+  d.mcon = mcon;
+  d.ncon = ncon;
+  d.mf = s->mf;
+  d.ns = s->ns;
+  d.N = N;
+  d.Nc = Nc;
+  d.camK = s->d_camK;
+  d.camR0 = s->d_camR0;
+  d.cam = s->d_cam;
+  d.pt = s->d_pt;
+  d.xy = s->d_xy;
+  d.wgt = s->d_wgt;
+  d.ptr = s->d_ptr;
+  d.cobs = s->d_cobs;
+  d.ccam = s->d_ccam;
+  d.W = s->d_W;
+  d.V = s->d_V;
+  d.eb = s->d_eb;
+  d.U = s->d_Uea;
+  d.ea = s->d_Uea + (size_t)m * 21;
+  d.S = s->d_Srhs;
+  d.rhs = s->d_Srhs + (size_t)s->ns * s->ns;
+  d.sc = s->d_sc;
+  // small systems are factored inside one CTA (ns*ns doubles of shared memory)
+  const size_t smallBytes = sizeof(double) * (size_t)s->ns * s->ns;
+  s->smallSolve = (smallBytes <= 200 * 1024) && s->ns <= 1024;
+  if (s->smallSolve && smallBytes > 48 * 1024)
+    COSL_CUDA(cudaFuncSetAttribute(ba_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smallBytes));
+  s->secLin = s->timer.section("ba_linearize");
+  s->secSchur = s->timer.section("ba_schur");
+  s->secSolve = s->timer.section("ba_solve");
+  s->secBack = s->timer.section("ba_backsub");
+  s->secCost = s->timer.section("ba_cost");
+  s->secComm = s->timer.section("ba_allreduce");
+  return upload_params(s, p);
+}
+
+/* ---------------------------------------------------------------- device steps */
+inline bool multi(const cosl_ba_solver* s) { return s->comm && s->comm->nranks > 1; }
+inline int rank_of(const cosl_ba_solver* s) { return s->comm ? s->comm->rank : 0; }
+
+int allreduce(cosl_ba_solver* s, double* buf, size_t count, int op) {
+  if (!multi(s)) return COSL_OK;
+  s->timer.begin(s->secComm, s->stream);
+  const int rc = nccl().AllReduce(buf, buf, count, ncclFloat64, op, s->comm->comm, s->stream);
+  s->timer.end(s->stream);
+  if (rc != 0)
+    return set_error(COSL_E_NCCL, "ncclAllReduce: %s",
+                     nccl().GetErrorString ? nccl().GetErrorString(rc) : "?");
+  return COSL_OK;
+}
+
+int zero_sc(cosl_ba_solver* s, int first, int count) {
+  COSL_CUDA(cudaMemsetAsync(s->d_sc + first, 0, sizeof(double) * count, s->stream));
+  return COSL_OK;
+}
+
+int read_sc(cosl_ba_solver* s) {
+  COSL_CUDA(cudaMemcpyAsync(s->h_sc, s->d_sc, sizeof(double) * SC_NTOT, cudaMemcpyDeviceToHost,
+                            s->stream));
+  COSL_CUDA(cudaStreamSynchronize(s->stream));
+  return COSL_OK;
+}
+
+// weighted cost of a parameter set -> *out (all ranks)
+int eval_cost(cosl_ba_solver* s, const double* pa, const double* pb, double* out, bool* finite) {
+  ++s->nfev;
+  COSL_TRY(zero_sc(s, SC_COST, 1));
+  COSL_TRY(zero_sc(s, SC_NONFINITE, 1));
+  s->timer.begin(s->secCost, s->stream);
+  if (s->N)
+    COSL_LAUNCH(ba_residual_kernel, (unsigned)div_up64(s->N, 256), 256, 0, s->stream, s->d, pa, pb,
+                0, 0.0, nullptr);
+  s->timer.end(s->stream);
+  COSL_TRY(allreduce(s, s->d_sc, SC_NSUM, ncclSum));
+  COSL_TRY(read_sc(s));
+  *out = s->h_sc[SC_COST];
+  *finite = std::isfinite(*out) && s->h_sc[SC_NONFINITE] == 0.0;
+  return COSL_OK;
+}
+
+int compute_weights(cosl_ba_solver* s) {
+  if (s->opt.max_err > 0) {
+    if (s->N)
+      COSL_LAUNCH(ba_residual_kernel, (unsigned)div_up64(s->N, 256), 256, 0, s->stream, s->d,
+                  s->d_pa, s->d_pb, 1, s->opt.max_err, nullptr);
+  } else {
+    std::vector<double> ones((size_t)s->N, 1.0);
+    COSL_CUDA(cudaMemcpyAsync(s->d_wgt, ones.data(), sizeof(double) * (size_t)s->N,
+                              cudaMemcpyHostToDevice, s->stream));
+    COSL_CUDA(cudaStreamSynchronize(s->stream));
+  }
+  return COSL_OK;
+}
+
+// Jacobians, U, V, W, ea, eb at (pa, pb); ginf / maxdiag land in h_sc
+int linearize(cosl_ba_solver* s) {
+  ++s->njev;
+  s->timer.begin(s->secLin, s->stream);
+  COSL_CUDA(cudaMemsetAsync(s->d_V, 0, sizeof(double) * 6 * (size_t)s->n, s->stream));
+  COSL_CUDA(cudaMemsetAsync(s->d_eb, 0, sizeof(double) * 3 * (size_t)s->n, s->stream));
+  COSL_CUDA(cudaMemsetAsync(s->d_Uea, 0, sizeof(double) * 27 * (size_t)s->m, s->stream));
+  if (s->N)
+    COSL_LAUNCH(ba_linearize_points, (unsigned)div_up64(s->N, 256), 256, 0, s->stream, s->d,
+                s->d_pa, s->d_pb);
+  if (s->Nc)
+    COSL_LAUNCH(ba_linearize_cams, (unsigned)div_up64(s->Nc, 128), 128, 0, s->stream, s->d,
+                s->d_pa, s->d_pb);
+  s->timer.end(s->stream);
+  COSL_TRY(allreduce(s, s->d_Uea, (size_t)27 * s->m, ncclSum));
+  COSL_TRY(zero_sc(s, SC_GINF, 2));
+  COSL_LAUNCH(ba_stats_kernel, (unsigned)div_up64((long long)s->n + s->m, 256), 256, 0, s->stream,
+              s->d);
+  COSL_TRY(allreduce(s, s->d_sc + SC_NSUM, 2, ncclMax));
+  COSL_CUDA(cudaGetLastError());
+  return COSL_OK;
+}
+
+int dense_solve(cosl_ba_solver* s) {
+  const int ns = s->ns;
+  if (ns == 0) return COSL_OK;
+  s->timer.begin(s->secSolve, s->stream);
+  if (s->smallSolve) {
+    COSL_LAUNCH(ba_chol_small, 1, 256, sizeof(double) * (size_t)ns * ns, s->stream, s->d.S,
+                s->d.rhs, ns, s->d_sc);
+    // solution is left in rhs
+    COSL_CUDA(cudaMemcpyAsync(s->d_x, s->d.rhs, sizeof(double) * ns, cudaMemcpyDeviceToDevice,
+                              s->stream));
+  } else {
+    for (int k0 = 0; k0 < ns; k0 += CB) {
+      const int bs = std::min(CB, ns - k0);
+      COSL_LAUNCH(ba_chol_potf2, 1, 256, 0, s->stream, s->d.S, ns, k0, bs, s->d_sc);
+      const int rem = ns - k0 - bs;
+      if (rem > 0) {
+        COSL_LAUNCH(ba_chol_trsm, div_up(rem, 128), 128, 0, s->stream, s->d.S, ns, k0, bs);
+        const int nt = div_up(rem, CB);
+        COSL_LAUNCH(ba_chol_syrk, dim3(nt, nt), 256, 0, s->stream, s->d.S, ns, k0, bs);
+      }
+    }
+    for (int k0 = 0; k0 < ns; k0 += CB) {
+      const int bs = std::min(CB, ns - k0);
+      const int rem = ns - k0 - bs;
+      COSL_LAUNCH(ba_trsv_fwd_step, std::max(1, div_up(rem, 128)), 128, 0, s->stream, s->d.S,
+                  s->d.rhs, s->d_y, ns, k0, bs);
+    }
+    const int last = ((ns - 1) / CB) * CB;
+    for (int k0 = last; k0 >= 0; k0 -= CB) {
+      const int bs = std::min(CB, ns - k0);
+      COSL_LAUNCH(ba_trsv_bwd_step, std::max(1, div_up(k0, 128)), 128, 0, s->stream, s->d.S,
+                  s->d_y, s->d_x, ns, k0, bs);
+    }
+  }
+  s->timer.end(s->stream);
+  COSL_CUDA(cudaGetLastError());
+  return COSL_OK;
+}
+
+// Schur complement + dense solve + back substitution for damping mu; trial parameters -> na, nb;
+// scalars (dp_L2, dL, p_L2, fail) -> h_sc
+int solve_trial(cosl_ba_solver* s, double mu, bool* solved) {
+  ++s->nlss;
+  const bool r0 = rank_of(s) == 0;
+  COSL_TRY(zero_sc(s, SC_DP_L2, 3));
+  COSL_TRY(zero_sc(s, SC_FAIL, 1));
+  s->timer.begin(s->secSchur, s->stream);
+  const long long ns = s->ns;
+  if (ns) {
+    COSL_LAUNCH(ba_init_S, (unsigned)div_up64(ns * ns + ns, 256), 256, 0, s->stream, s->d, mu,
+                r0 ? 1 : 0);
+    if (s->nItems)
+      COSL_LAUNCH(ba_schur_pairs, div_up(s->nItems, 4), 128, 0, s->stream, s->d, s->d_items,
+                  s->nItems, s->d_entries, mu);
+  }
+  s->timer.end(s->stream);
+  if (ns) COSL_TRY(allreduce(s, s->d_Srhs, (size_t)(ns * ns + ns), ncclSum));
+  COSL_TRY(dense_solve(s));
+  s->timer.begin(s->secBack, s->stream);
+  COSL_LAUNCH(ba_cam_update, div_up(6 * s->m, 256), 256, 0, s->stream, s->d, s->d_pa, s->d_x,
+              s->d_dpa, s->d_na, mu, r0 ? 1 : 0);
+  COSL_CUDA(cudaMemsetAsync(s->d_nb, 0, sizeof(double) * 3 * (size_t)s->n, s->stream));
+  if (s->N)
+    COSL_LAUNCH(ba_back_subst, (unsigned)div_up64(s->N, 256), 256, 0, s->stream, s->d, s->d_dpa,
+                s->d_nb);
+  if (s->n)
+    COSL_LAUNCH(ba_back_finish, (unsigned)div_up64(s->n, 256), 256, 0, s->stream, s->d, s->d_pb,
+                s->d_nb, s->d_dpb, mu);
+  s->timer.end(s->stream);
+  COSL_CUDA(cudaGetLastError());
+  // the scalar all-reduce of this trial is merged with the cost evaluation by the caller
+  *solved = true;
+  return COSL_OK;
+}
+
+/* Weighted SBA LM, control flow identical to oracle/ba_oracle.cpp:levmar */
+int levmar(cosl_ba_solver* s, int itmax, const double opts[5], double info[10], int fixed_trials) {
+  const double tau = opts[0], eps1 = opts[1], eps2 = opts[2], eps2_sq = opts[2] * opts[2],
+               eps3 = opts[3], eps4 = opts[4];
+  const double EPS_SQ = 1e-24;
+  double mu = 0, nu = 2;
+  int stop = 0, itno = 0;
+  s->nfev = s->njev = s->nlss = 0;
+  double p_eL2 = 0;
+  bool finite = true;
+  COSL_TRY(eval_cost(s, s->d_pa, s->d_pb, &p_eL2, &finite));
+  const double init_eL2 = p_eL2;
+  double ginf = 0, maxdiag = 0, dp_L2 = 0;
+  if (!finite) stop = 7;
+  for (itno = 0; itno < itmax && !stop; ++itno) {
+    COSL_TRY(linearize(s));
+    if (itno == 0 || !fixed_trials) {
+      // ginf/maxdiag are needed on the host only for mu0 and the eps1 test
+      COSL_TRY(read_sc(s));
+      ginf = s->h_sc[SC_GINF];
+      maxdiag = s->h_sc[SC_MAXDIAG];
+    }
+    if (!fixed_trials && ginf <= eps1) {
+      stop = 1;
+      break;
+    }
+    if (itno == 0) mu = tau * maxdiag;
+    while (true) {
+      bool solved = false, accepted = false;
+      COSL_TRY(solve_trial(s, mu, &solved));
+      // trial cost, merged scalar all-reduce
+      ++s->nfev;
+      COSL_TRY(zero_sc(s, SC_COST, 1));
+      COSL_TRY(zero_sc(s, SC_NONFINITE, 1));
+      s->timer.begin(s->secCost, s->stream);
+      if (s->N)
+        COSL_LAUNCH(ba_residual_kernel, (unsigned)div_up64(s->N, 256), 256, 0, s->stream, s->d,
+                    s->d_na, s->d_nb, 0, 0.0, nullptr);
+      s->timer.end(s->stream);
+      COSL_TRY(allreduce(s, s->d_sc, SC_NSUM, ncclSum));
+      COSL_TRY(read_sc(s));
+      solved = (s->h_sc[SC_FAIL] == 0.0);
+      if (solved) {
+        dp_L2 = s->h_sc[SC_DP_L2];
+        const double dL = s->h_sc[SC_DL], p_L2 = s->h_sc[SC_P_L2];
+        if (!fixed_trials) {
+          if (dp_L2 <= eps2_sq * p_L2) {
+            stop = 2;
+            break;
+          }
+          if (dp_L2 >= (p_L2 + eps2) / EPS_SQ) {
+            stop = 4;
+            break;
+          }
+        }
+        const double pdp_eL2 = s->h_sc[SC_COST];
+        if (!std::isfinite(pdp_eL2) || s->h_sc[SC_NONFINITE] != 0.0) {
+          stop = 7;
+          break;
+        }
+        const double dF = p_eL2 - pdp_eL2;
+        if (s->opt.verbose && rank_of(s) == 0)
+          std::printf("  [gpu LM %d] mu %.3e cost %.9g -> %.9g dL %.3e\n", itno, mu, p_eL2, pdp_eL2,
+                      dL);
+        if (dF > 0 && dL > 0) {
+          double tmp = 2 * dF / dL - 1;
+          tmp = 1 - tmp * tmp * tmp;
+          mu = mu * std::max(tmp, 1.0 / 3.0);
+          nu = 2;
+          if (!fixed_trials && (std::sqrt(p_eL2) - std::sqrt(pdp_eL2)) < eps4 * std::sqrt(p_eL2))
+            stop = 6;
+          std::swap(s->d_pa, s->d_na);
+          std::swap(s->d_pb, s->d_nb);
+          p_eL2 = pdp_eL2;
+          accepted = true;
+        }
+      }
+      if (fixed_trials && s->nlss >= fixed_trials) {
+        stop = 3;
+        break;
+      }
+      if (accepted) break;
+      mu *= nu;
+      const double nu2 = nu * 2;
+      if (!(nu2 > nu) || !std::isfinite(mu)) {
+        stop = 5;
+        break;
+      }
+      nu = nu2;
+    }
+    if (!fixed_trials && p_eL2 <= eps3) stop = 3;
+  }
+  if (itno >= itmax && !stop) stop = 3;
+  if (info) {
+    info[0] = init_eL2;
+    info[1] = p_eL2;
+    info[2] = ginf;
+    info[3] = dp_L2;
+    info[4] = maxdiag > 0 ? mu / maxdiag : 0;
+    info[5] = itno;
+    info[6] = stop;
+    info[7] = s->nfev;
+    info[8] = s->njev;
+    info[9] = s->nlss;
+  }
+  return COSL_OK;
+}
+
+int run_robust(cosl_ba_solver* s, int fixed_trials, double info[COSL_BA_INFOSZ]) {
+  double sinfo[10] = {0};
+  double first_e0 = -1;
+  int total_trials = 0;
+  COSL_CUDA(cudaStreamSynchronize(s->stream));
+  const auto t0 = std::chrono::steady_clock::now();
+  const int rounds = fixed_trials ? 1 : std::max(1, s->opt.outer_iters);
+  for (int r = 0; r < rounds; ++r) {
+    COSL_TRY(compute_weights(s));
+    COSL_TRY(levmar(s, fixed_trials ? (1 << 30) : s->opt.inner_iters, s->opt.opts, sinfo,
+                    fixed_trials));
+    if (first_e0 < 0) first_e0 = sinfo[0];
+    total_trials += (int)sinfo[9];
+  }
+  int nout = 0;
+  if (s->opt.max_err > 0 && s->N) {
+    COSL_LAUNCH(ba_residual_kernel, (unsigned)div_up64(s->N, 256), 256, 0, s->stream, s->d, s->d_pa,
+                s->d_pb, 2, s->opt.max_err, s->d_outlier);
+  } else {
+    COSL_CUDA(cudaMemsetAsync(s->d_outlier, 0, (size_t)s->N ? (size_t)s->N : 1, s->stream));
+  }
+  COSL_CUDA(cudaStreamSynchronize(s->stream));
+  const auto t1 = std::chrono::steady_clock::now();
+  if (info) {
+    for (int k = 0; k < COSL_BA_INFOSZ; ++k) info[k] = 0;
+    for (int k = 0; k < 10; ++k) info[k] = sinfo[k];
+    info[0] = first_e0;
+    info[10] = total_trials;
+    info[11] = std::chrono::duration<double>(t1 - t0).count();
+    info[12] = sinfo[1];
+    info[13] = nout;
+  }
+  return COSL_OK;
+}
+
+int download(cosl_ba_solver* s, cosl_ba_problem* p) {
+  const int m = s->m;
+  std::vector<double> pa((size_t)m * 6);
+  COSL_CUDA(cudaMemcpyAsync(pa.data(), s->d_pa, sizeof(double) * 6 * m, cudaMemcpyDeviceToHost,
+                            s->stream));
+  std::vector<double> X((size_t)s->n * 3);
+  COSL_CUDA(cudaMemcpyAsync(X.data(), s->d_pb, sizeof(double) * 3 * (size_t)s->n,
+                            cudaMemcpyDeviceToHost, s->stream));
+  if (p->outlier && s->N)
+    COSL_CUDA(cudaMemcpyAsync(p->outlier, s->d_outlier, (size_t)s->N, cudaMemcpyDeviceToHost,
+                              s->stream));
+  COSL_CUDA(cudaStreamSynchronize(s->stream));
+  for (int j = s->mcon; j < m; ++j) {
+    const double* v = &pa[6 * j];
+    const double dq[4] = {std::sqrt(1.0 - (v[0] * v[0] + v[1] * v[1] + v[2] * v[2])), v[0], v[1],
+                          v[2]};
+    double q[4];
+    quat_mul(dq, &s->q0[4 * j], q);
+    const double nr = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+    for (int k = 0; k < 4; ++k) q[k] /= nr;
+    quat2mat(q, p->R + 9 * j);
+    for (int k = 0; k < 3; ++k) p->t[3 * j + k] = pa[6 * j + 3 + k];
+  }
+  for (int i = s->ncon; i < s->n; ++i)
+    for (int k = 0; k < 3; ++k) p->X[3 * (size_t)i + k] = X[3 * (size_t)i + k];
+  return COSL_OK;
+}
+
+}  // namespace
+
+/* ================================================================ C-ABI */
+extern "C" {
+
+void cosl_ba_options_default(cosl_ba_options* o) {
+  if (!o) return;
+  o->max_err = 6.0;  // RobustBundleRTSParameter defaults (app/SL_CoSLAMRobustBA.h:33-38)
+  o->outer_iters = 5;
+  o->inner_iters = 10;
+  o->opts[0] = 1e-3 * 1e-4;  // app/SL_CoSLAMBA.cpp:323-328
+  o->opts[1] = 1e-12;
+  o->opts[2] = 1e-12;
+  o->opts[3] = 0;
+  o->opts[4] = 1e-16;
+  o->device = 0;
+  o->verbose = 0;
+}
+
+int cosl_nccl_unique_id(uint8_t id[128]) {
+  if (!id) return set_error(COSL_E_INVALID, "null id");
+  if (!nccl().ok) return set_error(COSL_E_NCCL, "libnccl.so.2 could not be loaded");
+  ncclUniqueId u;
+  const int rc = nccl().GetUniqueId(&u);
+  if (rc != 0) return set_error(COSL_E_NCCL, "ncclGetUniqueId failed (%d)", rc);
+  std::memcpy(id, u.internal, 128);
+  return COSL_OK;
+}
+
+int cosl_ba_comm_create(const uint8_t id[128], int rank, int nranks, int device,
+                        cosl_ba_comm** out) {
+  if (!id || !out || rank < 0 || rank >= nranks)
+    return set_error(COSL_E_INVALID, "cosl_ba_comm_create: bad argument");
+  *out = nullptr;
+  if (!nccl().ok) return set_error(COSL_E_NCCL, "libnccl.so.2 could not be loaded");
+  COSL_CUDA(cudaSetDevice(device));
+  cosl_ba_comm* c = new (std::nothrow) cosl_ba_comm();
+  if (!c) return set_error(COSL_E_NOMEM, "host allocation failed");
+  ncclUniqueId u;
+  std::memcpy(u.internal, id, 128);
+  const int rc = nccl().CommInitRank(&c->comm, nranks, u, rank);
+  if (rc != 0) {
+    delete c;
+    return set_error(COSL_E_NCCL, "ncclCommInitRank: %s",
+                     nccl().GetErrorString ? nccl().GetErrorString(rc) : "?");
+  }
+  c->rank = rank;
+  c->nranks = nranks;
+  c->device = device;
+  *out = c;
+  return COSL_OK;
+}
+
+int cosl_ba_comm_destroy(cosl_ba_comm* c) {
+  if (!c) return COSL_OK;
+  if (c->comm) nccl().CommDestroy(c->comm);
+  delete c;
+  return COSL_OK;
+}
+
+int cosl_ba_solver_create(const cosl_ba_problem* prob, const cosl_ba_options* opt,
+                          cosl_ba_comm* comm, cosl_ba_solver** out) {
+  if (!prob || !opt || !out) return set_error(COSL_E_INVALID, "null argument");
+  *out = nullptr;
+  if (prob->m < 1 || prob->n < 0 || prob->nobs < 0 || prob->m_con < 0 || prob->m_con > prob->m ||
+      prob->n_con < 0 || prob->n_con > prob->n || !prob->K || !prob->R || !prob->t ||
+      (prob->n && (!prob->X || !prob->ptr)) || (prob->nobs && (!prob->cam || !prob->xy)) ||
+      prob->nobs >= (1ll << 31))
+    return set_error(COSL_E_INVALID, "cosl_ba_solver_create: bad problem");
+  if (prob->n && prob->ptr[prob->n] != prob->nobs)
+    return set_error(COSL_E_INVALID, "ptr[n] != nobs");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || opt->device < 0 || opt->device >= ndev)
+    return set_error(COSL_E_CUDA, "CUDA device %d not available", opt->device);
+  COSL_CUDA(cudaSetDevice(opt->device));
+  cosl_ba_solver* s = new (std::nothrow) cosl_ba_solver();
+  if (!s) return set_error(COSL_E_NOMEM, "host allocation failed");
+  s->opt = *opt;
+  s->comm = comm;
+  s->device = opt->device;
+  cudaError_t e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete s;
+    return set_error(COSL_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+  }
+  const int rc = build_solver(s, prob);
+  if (rc != COSL_OK) {
+    free_solver(s);
+    return rc;
+  }
+  *out = s;
+  return COSL_OK;
+}
+
+#define BA_ENTER(s)                                               \
+  if (!(s)) return set_error(COSL_E_INVALID, "null solver handle"); \
+  COSL_CUDA(cudaSetDevice((s)->device));
+
+int cosl_ba_solver_reset(cosl_ba_solver* s, const cosl_ba_problem* prob) {
+  BA_ENTER(s)
+  if (!prob || prob->m != s->m || prob->n != s->n)
+    return set_error(COSL_E_INVALID, "cosl_ba_solver_reset: problem shape changed");
+  s->timer.reset();
+  return upload_params(s, prob);
+}
+
+int cosl_ba_solver_run(cosl_ba_solver* s, double info[COSL_BA_INFOSZ]) {
+  BA_ENTER(s)
+  return run_robust(s, 0, info);
+}
+
+int cosl_ba_solver_run_fixed(cosl_ba_solver* s, int trials, double info[COSL_BA_INFOSZ]) {
+  BA_ENTER(s)
+  return run_robust(s, trials < 1 ? 1 : trials, info);
+}
+
+int cosl_ba_solver_download(cosl_ba_solver* s, cosl_ba_problem* prob) {
+  BA_ENTER(s)
+  if (!prob || prob->m != s->m || prob->n != s->n)
+    return set_error(COSL_E_INVALID, "cosl_ba_solver_download: problem shape changed");
+  return download(s, prob);
+}
+
+int cosl_ba_solver_destroy(cosl_ba_solver* s) {
+  free_solver(s);
+  return COSL_OK;
+}
+
+void* cosl_ba_solver_stream(cosl_ba_solver* s) { return s ? (void*)s->stream : nullptr; }
+
+int cosl_ba_solver_profile_enable(cosl_ba_solver* s, int on) {
+  BA_ENTER(s)
+  COSL_CUDA(cudaStreamSynchronize(s->stream));
+  s->timer.reset();
+  s->timer.enabled = on != 0;
+  return COSL_OK;
+}
+
+const char* cosl_ba_solver_timer(cosl_ba_solver* s, int idx, double* ms, int* calls) {
+  if (!s || idx < 0 || idx >= s->timer.nsec) return nullptr;
+  cudaSetDevice(s->device);
+  cudaStreamSynchronize(s->stream);
+  s->timer.flush();
+  if (ms) *ms = s->timer.ms[idx];
+  if (calls) *calls = s->timer.calls[idx];
+  return s->timer.names[idx];
+}
+
+int cosl_ba_solve(cosl_ba_problem* prob, const cosl_ba_options* opt,
+                  double info[COSL_BA_INFOSZ]) {
+  cosl_ba_solver* s = nullptr;
+  COSL_TRY(cosl_ba_solver_create(prob, opt, nullptr, &s));
+  int rc = run_robust(s, 0, info);
+  if (rc == COSL_OK) rc = download(s, prob);
+  if (rc == COSL_OK && info && prob->outlier) {
+    long long c = 0;
+    for (long long o = 0; o < prob->nobs; ++o) c += prob->outlier[o] ? 1 : 0;
+    info[13] = (double)c;
+  }
+  free_solver(s);
+  return rc;
+}
+
+int cosl_sba_motstr_levmar_x(int n, int ncon, int m, int mcon, const char* vmask, double* p,
+                             int cnp, int pnp, const double* x, int mnp,
+                             const double* rot0params, int itmax, int verbose,
+                             const double opts[5], double info[10], int device) {
+  if (cnp != 11 || pnp != 3 || mnp != 2 || !vmask || !p || !x || !rot0params || !opts)
+    return set_error(COSL_E_INVALID, "cosl_sba_motstr_levmar_x: only cnp=11, pnp=3, mnp=2");
+  std::vector<double> K((size_t)m * 9, 0.0), R((size_t)m * 9), t((size_t)m * 3), X((size_t)n * 3);
+  for (int j = 0; j < m; ++j) {
+    const double* c = p + (size_t)cnp * j;
+    double* k = &K[9 * j];
+    k[0] = c[0];
+    k[1] = c[4];
+    k[2] = c[1];
+    k[4] = c[3] * c[0];
+    k[5] = c[2];
+    k[8] = 1.0;
+    const double dq[4] = {std::sqrt(1.0 - (c[5] * c[5] + c[6] * c[6] + c[7] * c[7])), c[5], c[6],
+                          c[7]};
+    double q[4];
+    quat_mul(dq, rot0params + 4 * j, q);
+    quat2mat(q, &R[9 * j]);
+    for (int a = 0; a < 3; ++a) t[3 * j + a] = c[8 + a];
+  }
+  std::memcpy(X.data(), p + (size_t)cnp * m, sizeof(double) * 3 * n);
+  std::vector<int64_t> ptr(n + 1, 0);
+  std::vector<int32_t> cam;
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j < m; ++j)
+      if (vmask[(size_t)i * m + j]) cam.push_back(j);
+    ptr[i + 1] = (int64_t)cam.size();
+  }
+  cosl_ba_problem pr;
+  std::memset(&pr, 0, sizeof(pr));
+  pr.m = m;
+  pr.n = n;
+  pr.nobs = (int64_t)cam.size();
+  pr.m_con = mcon;
+  pr.n_con = ncon;
+  pr.K = K.data();
+  pr.R = R.data();
+  pr.t = t.data();
+  pr.X = X.data();
+  pr.ptr = ptr.data();
+  pr.cam = cam.data();
+  pr.xy = x;
+  cosl_ba_options o;
+  cosl_ba_options_default(&o);
+  o.max_err = 0;
+  o.outer_iters = 1;
+  o.inner_iters = itmax;
+  for (int k = 0; k < 5; ++k) o.opts[k] = opts[k];
+  o.verbose = verbose;
+  o.device = device;
+  double inf[COSL_BA_INFOSZ];
+  COSL_TRY(cosl_ba_solve(&pr, &o, inf));
+  if (info)
+    for (int k = 0; k < 10; ++k) info[k] = inf[k];
+  for (int j = mcon; j < m; ++j) {
+    double q[4], qn[4];
+    const double q0c[4] = {rot0params[4 * j], -rot0params[4 * j + 1], -rot0params[4 * j + 2],
+                           -rot0params[4 * j + 3]};
+    mat2quat(&R[9 * j], q);
+    quat_mul(q, q0c, qn);
+    if (qn[0] < 0)
+      for (int a = 0; a < 4; ++a) qn[a] = -qn[a];
+    double* c = p + (size_t)cnp * j;
+    c[5] = qn[1];
+    c[6] = qn[2];
+    c[7] = qn[3];
+    for (int a = 0; a < 3; ++a) c[8 + a] = t[3 * j + a];
+  }
+  std::memcpy(p + (size_t)cnp * m + 3 * (size_t)ncon, X.data() + 3 * (size_t)ncon,
+              sizeof(double) * 3 * (size_t)(n - ncon));
+  return (int)inf[5];
+}
+
+}  // extern "C"

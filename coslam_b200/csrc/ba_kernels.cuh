@@ -1,0 +1,803 @@
+// ba_kernels.cuh -- device code of the Schur-complement Levenberg-Marquardt bundle adjustment
+// (sm_100a, fp64).  Algorithm: sba_motstr_levmar_x of Lourakis & Argyros with the KRTS camera
+// parameterisation of app/SL_CoSLAMBA.cpp:290-378.
+//
+// Data layout in HBM (per solver / per rank):
+//   cameras (replicated): camK[m][5] (K0,K1,K2,K4,K5), camR0[m][9] (rotation of q0), pa[m][6] (v,t)
+//   points  (this rank's shard): pb[n][3]
+//   observations, point-major CSR: cam[N], pt[N], xy[N][2], wgt[N]
+//   camera-major permutation of the free-camera observations: cobs[Nc], ccam[Nc]
+//   W[N][18]   W_ij = A_ij^T B_ij (6x3 row-major) of the current linearisation
+//   V[n][6], eb[n][3], U[m][21] (packed upper), ea[m][6]
+//   pair work list for the Schur contraction: items {rowCam, colCam, begin, end} over entry pairs
+//   (obsA, obsB) sorted by camera pair
+//   S[ns*ns] row-major, only blocks (j <= k) are formed (== lower triangle in column-major); rhs[ns]
+//
+// One-observation-per-thread kernels evaluate residuals and the 2x6 / 2x3 Jacobian blocks; per-point
+// (resp. per-camera) sums are collapsed with segmented warp shuffles and only segment heads touch
+// memory with atomics.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace coslam {
+
+struct BaDev {
+  int m, n, mcon, ncon, mf, ns;
+  long long N, Nc;
+  const double* camK;
+  const double* camR0;
+  const int* cam;
+  const int* pt;
+  const double* xy;
+  double* wgt;
+  const long long* ptr;
+  const int* cobs;
+  const int* ccam;
+  double* W;
+  double* V;
+  double* eb;
+  double* U;
+  double* ea;
+  double* S;
+  double* rhs;
+  double* sc;  // scalars, see BaScalar
+};
+
+enum BaScalar {
+  SC_COST = 0,     // sum w |e|^2 of the evaluated parameter set
+  SC_DP_L2 = 1,    // |dp|^2
+  SC_DL = 2,       // dp . (mu dp + g)
+  SC_P_L2 = 3,     // |p|^2 over free parameters
+  SC_NONFINITE = 4,
+  SC_NSUM = 8,     // [0, SC_NSUM) are sums (all-reduce sum)
+  SC_GINF = 8,     // |g|_inf                 (all-reduce max)
+  SC_MAXDIAG = 9,  // max diag(U, V)
+  SC_FAIL = 10,    // Cholesky break-down flag
+  SC_NTOT = 16
+};
+
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
+  // valid for non-negative doubles: the bit pattern is monotone
+  atomicMax(reinterpret_cast<unsigned long long*>(addr),
+            static_cast<unsigned long long>(__double_as_longlong(v)));
+}
+
+__device__ __forceinline__ void cross3(const double a[3], const double b[3], double c[3]) {
+  c[0] = a[1] * b[2] - a[2] * b[1];
+  c[1] = a[2] * b[0] - a[0] * b[2];
+  c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// x = pi(K (R(dq(v)) R0 X + t)); optionally A = dx/d(v,t) (2x6), B = dx/dX (2x3).
+// Same formulas as oracle/ba_oracle.cpp:orc_ba_project.
+template <bool WANT_A, bool WANT_B>
+__device__ __forceinline__ void ba_project(const double* __restrict__ Kc,
+                                           const double* __restrict__ R0,
+                                           const double* __restrict__ p6, const double X[3],
+                                           double xy[2], double A[12], double B[6]) {
+  const double v[3] = {p6[0], p6[1], p6[2]};
+  const double Y[3] = {R0[0] * X[0] + R0[1] * X[1] + R0[2] * X[2],
+                       R0[3] * X[0] + R0[4] * X[1] + R0[5] * X[2],
+                       R0[6] * X[0] + R0[7] * X[1] + R0[8] * X[2]};
+  const double w = sqrt(1.0 - (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]));
+  double vxY[3], vxvxY[3];
+  cross3(v, Y, vxY);
+  cross3(v, vxY, vxvxY);
+  const double P[3] = {Y[0] + 2 * w * vxY[0] + 2 * vxvxY[0] + p6[3],
+                       Y[1] + 2 * w * vxY[1] + 2 * vxvxY[1] + p6[4],
+                       Y[2] + 2 * w * vxY[2] + 2 * vxvxY[2] + p6[5]};
+  const double iz = 1.0 / P[2];
+  const double un = Kc[0] * P[0] + Kc[1] * P[1];
+  xy[0] = un * iz + Kc[2];
+  xy[1] = Kc[3] * P[1] * iz + Kc[4];
+  if (!WANT_A && !WANT_B) return;
+  const double Jp[6] = {Kc[0] * iz, Kc[1] * iz, -un * iz * iz, 0.0, Kc[3] * iz,
+                        -Kc[3] * P[1] * iz * iz};
+  if (WANT_A) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double e[3] = {0, 0, 0};
+      e[k] = 1.0;
+      double exY[3], exvxY[3], vxexY[3];
+      cross3(e, Y, exY);
+      cross3(e, vxY, exvxY);
+      cross3(v, exY, vxexY);
+      const double dw = -v[k] / w;
+      double dP[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+        dP[c] = 2 * dw * vxY[c] + 2 * w * exY[c] + 2 * exvxY[c] + 2 * vxexY[c];
+      A[k] = Jp[0] * dP[0] + Jp[1] * dP[1] + Jp[2] * dP[2];
+      A[6 + k] = Jp[3] * dP[0] + Jp[4] * dP[1] + Jp[5] * dP[2];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      A[3 + k] = Jp[k];
+      A[9 + k] = Jp[3 + k];
+    }
+  }
+  if (WANT_B) {
+    // R(dq) from the unit quaternion (w, v), then Rf = R(dq) R0
+    const double x = v[0], y = v[1], z = v[2];
+    const double Rd[9] = {w * w + x * x - y * y - z * z, 2 * (x * y - w * z), 2 * (x * z + w * y),
+                          2 * (x * y + w * z), w * w - x * x + y * y - z * z, 2 * (y * z - w * x),
+                          2 * (x * z - w * y), 2 * (y * z + w * x), w * w - x * x - y * y + z * z};
+    double Rf[9];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        Rf[3 * i + j] = Rd[3 * i] * R0[j] + Rd[3 * i + 1] * R0[3 + j] + Rd[3 * i + 2] * R0[6 + j];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      B[k] = Jp[0] * Rf[k] + Jp[1] * Rf[3 + k] + Jp[2] * Rf[6 + k];
+      B[3 + k] = Jp[3] * Rf[k] + Jp[4] * Rf[3 + k] + Jp[5] * Rf[6 + k];
+    }
+  }
+}
+
+// Segmented warp reduction by key for contiguous segments: after the call the FIRST lane of every
+// run of equal keys holds the run's sum.
+template <int NV>
+__device__ __forceinline__ void seg_reduce(double* v, int key, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int ko = __shfl_down_sync(0xffffffffu, key, o);
+    const bool take = (lane + o < 32) && (ko == key);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const double t = __shfl_down_sync(0xffffffffu, v[k], o);
+      if (take) v[k] += t;
+    }
+  }
+}
+
+__device__ __forceinline__ double block_sum_1(double v, double* s_red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) s_red[wid] = v;
+  __syncthreads();
+  double t = 0;
+  if (wid == 0) {
+    t = (lane < (int)(blockDim.x >> 5)) ? s_red[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  }
+  return t;  // valid in warp 0
+}
+
+__device__ __forceinline__ double tukey_w(double e, double s) {
+  if (e >= s) return 0;
+  e /= s;
+  e = 1 - e * e;
+  return e * e;
+}
+
+// ------------------------------------------------------------------------------------------
+// cost / weights / outliers: one observation per thread
+// mode 0: sc[SC_COST] += w |e|^2 ; mode 1: wgt = tukey(|e|, maxErr) ; mode 2: outlier = |e|>=maxErr
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ba_residual_kernel(BaDev d, const double* __restrict__ pa, const double* __restrict__ pb, int mode,
+                   double maxErr, unsigned char* __restrict__ outlier) {
+  __shared__ double s_red[8];
+  const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double c = 0;
+  if (o < d.N) {
+    const int j = d.cam[o], i = d.pt[o];
+    const double X[3] = {pb[3 * (size_t)i], pb[3 * (size_t)i + 1], pb[3 * (size_t)i + 2]};
+    double h[2];
+    ba_project<false, false>(d.camK + 5 * j, d.camR0 + 9 * j, pa + 6 * j, X, h, nullptr, nullptr);
+    const double dx = d.xy[2 * o] - h[0], dy = d.xy[2 * o + 1] - h[1];
+    const double e2 = dx * dx + dy * dy;
+    if (mode == 0) {
+      c = d.wgt[o] * e2;
+    } else if (mode == 1) {
+      d.wgt[o] = tukey_w(sqrt(e2), maxErr);
+    } else {
+      outlier[o] = (sqrt(e2) >= maxErr) ? 1 : 0;
+    }
+  }
+  if (mode == 0) {
+    const double t = block_sum_1(c, s_red);
+    if (threadIdx.x == 0) {
+      if (isfinite(t))
+        atomicAdd(&d.sc[SC_COST], t);
+      else
+        d.sc[SC_NONFINITE] = 1.0;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Linearisation, point-major: per observation e, A (2x6), B (2x3) (scaled by sqrt(w)); stores
+// W_ij = A^T B; collapses V_i = sum B^T B and eb_i = sum B^T e per point with segmented shuffles.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ba_linearize_points(BaDev d, const double* __restrict__ pa, const double* __restrict__ pb) {
+  const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  double acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = 0;
+  int key = -1 - lane;  // inactive lanes never merge
+  if (o < d.N) {
+    const int j = d.cam[o], i = d.pt[o];
+    key = i;
+    const double X[3] = {pb[3 * (size_t)i], pb[3 * (size_t)i + 1], pb[3 * (size_t)i + 2]};
+    double h[2], A[12], B[6];
+    ba_project<true, true>(d.camK + 5 * j, d.camR0 + 9 * j, pa + 6 * j, X, h, A, B);
+    const double sw = sqrt(d.wgt[o]);
+    const double e0 = (d.xy[2 * o] - h[0]) * sw, e1 = (d.xy[2 * o + 1] - h[1]) * sw;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) B[k] *= sw;
+    if (i >= d.ncon) {
+      acc[0] = B[0] * B[0] + B[3] * B[3];
+      acc[1] = B[0] * B[1] + B[3] * B[4];
+      acc[2] = B[0] * B[2] + B[3] * B[5];
+      acc[3] = B[1] * B[1] + B[4] * B[4];
+      acc[4] = B[1] * B[2] + B[4] * B[5];
+      acc[5] = B[2] * B[2] + B[5] * B[5];
+      acc[6] = B[0] * e0 + B[3] * e1;
+      acc[7] = B[1] * e0 + B[4] * e1;
+      acc[8] = B[2] * e0 + B[5] * e1;
+      if (j >= d.mcon) {
+#pragma unroll
+        for (int k = 0; k < 12; ++k) A[k] *= sw;
+        double* Wp = d.W + 18 * (size_t)o;
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) Wp[3 * r + c] = A[r] * B[c] + A[6 + r] * B[3 + c];
+      }
+    }
+  }
+  seg_reduce<9>(acc, key, lane);
+  const int kprev = __shfl_up_sync(0xffffffffu, key, 1);
+  const bool head = (lane == 0) || (kprev != key);
+  if (head && key >= d.ncon) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) atomicAdd(&d.V[6 * (size_t)key + k], acc[k]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) atomicAdd(&d.eb[3 * (size_t)key + k], acc[6 + k]);
+  }
+}
+
+// Linearisation, camera-major over the free-camera observations: U_j = sum A^T A (packed upper,
+// 21) and ea_j = sum A^T e (6), collapsed per camera with segmented shuffles.
+__global__ void __launch_bounds__(128)
+ba_linearize_cams(BaDev d, const double* __restrict__ pa, const double* __restrict__ pb) {
+  const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  double acc[27];
+#pragma unroll
+  for (int k = 0; k < 27; ++k) acc[k] = 0;
+  int key = -1 - lane;
+  if (q < d.Nc) {
+    const int o = d.cobs[q], j = d.ccam[q], i = d.pt[o];
+    key = j;
+    const double X[3] = {pb[3 * (size_t)i], pb[3 * (size_t)i + 1], pb[3 * (size_t)i + 2]};
+    double h[2], A[12];
+    ba_project<true, false>(d.camK + 5 * j, d.camR0 + 9 * j, pa + 6 * j, X, h, A, nullptr);
+    const double sw = sqrt(d.wgt[o]);
+    const double e0 = (d.xy[2 * (size_t)o] - h[0]) * sw, e1 = (d.xy[2 * (size_t)o + 1] - h[1]) * sw;
+#pragma unroll
+    for (int k = 0; k < 12; ++k) A[k] *= sw;
+    int t = 0;
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int c = r; c < 6; ++c) acc[t++] = A[r] * A[c] + A[6 + r] * A[6 + c];
+#pragma unroll
+    for (int r = 0; r < 6; ++r) acc[21 + r] = A[r] * e0 + A[6 + r] * e1;
+  }
+  seg_reduce<27>(acc, key, lane);
+  const int kprev = __shfl_up_sync(0xffffffffu, key, 1);
+  const bool head = (lane == 0) || (kprev != key);
+  if (head && key >= 0) {
+#pragma unroll
+    for (int k = 0; k < 21; ++k) atomicAdd(&d.U[21 * (size_t)key + k], acc[k]);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) atomicAdd(&d.ea[6 * (size_t)key + k], acc[21 + k]);
+  }
+}
+
+// |g|_inf and max diag over (U, ea) of the free cameras [global after all-reduce] and (V, eb) of
+// this rank's free points.
+__global__ void __launch_bounds__(256) ba_stats_kernel(BaDev d) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double g = 0, dg = 0;
+  if (t < d.n) {
+    if (t >= d.ncon) {
+      const double* V = d.V + 6 * t;
+      const double* e = d.eb + 3 * t;
+      g = fmax(fabs(e[0]), fmax(fabs(e[1]), fabs(e[2])));
+      dg = fmax(V[0], fmax(V[3], V[5]));
+    }
+  } else if (t < (long long)d.n + d.m) {
+    const int j = (int)(t - d.n);
+    if (j >= d.mcon) {
+      const double* U = d.U + 21 * (size_t)j;
+      const double* e = d.ea + 6 * (size_t)j;
+      // packed upper: diagonal entries at offsets 0, 6, 11, 15, 18, 20
+      dg = fmax(fmax(U[0], U[6]), fmax(fmax(U[11], U[15]), fmax(U[18], U[20])));
+#pragma unroll
+      for (int k = 0; k < 6; ++k) g = fmax(g, fabs(e[k]));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    g = fmax(g, __shfl_xor_sync(0xffffffffu, g, o));
+    dg = fmax(dg, __shfl_xor_sync(0xffffffffu, dg, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (g > 0) atomic_max_nonneg(&d.sc[SC_GINF], g);
+    if (dg > 0) atomic_max_nonneg(&d.sc[SC_MAXDIAG], dg);
+  }
+}
+
+// S <- 0 with the damped camera blocks U*_j on the diagonal, rhs <- ea.  addU: this rank
+// contributes U/ea/mu (rank 0 only in the multi-GPU case, where U/ea are already all-reduced).
+__global__ void __launch_bounds__(256) ba_init_S(BaDev d, double mu, int addU) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long ns = d.ns;
+  if (t < ns * ns) {
+    const int r = (int)(t / ns), c = (int)(t - (long long)r * ns);
+    double v = 0;
+    const int jb = r / 6, kb = c / 6;
+    if (addU && jb == kb && c >= r) {
+      const int a = r - 6 * jb, b = c - 6 * kb;
+      const int idx = a * 6 - (a * (a - 1)) / 2 + (b - a);  // packed upper index of (a, b), a<=b
+      v = d.U[21 * (size_t)(jb + d.mcon) + idx];
+      if (a == b) v += mu;
+    }
+    d.S[t] = v;
+  } else if (t < ns * ns + ns) {
+    const int r = (int)(t - ns * ns);
+    d.rhs[r] = addU ? d.ea[6 * (size_t)d.mcon + r] : 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Schur contraction over camera pairs.  Work item = a run of (obsA, obsB) entries that belong to
+// one camera pair (j <= k): block(j,k) -= sum_i W_ij V*_i^-1 W_ik^T (and, for j == k,
+// rhs_j -= sum_i W_ij V*_i^-1 eb_i).  One warp per item; two lanes share an entry (3 block columns
+// each), 18 accumulators per lane, butterfly reduction, 18 atomics per lane-parity per item.
+// ------------------------------------------------------------------------------------------
+struct BaPairItem {
+  int rowCam, colCam;  // free-camera indices (0-based in the reduced system)
+  int begin, end;      // entry range
+};
+
+__device__ __forceinline__ void inv3sym_mu(const double* __restrict__ V, double mu, double I[6]) {
+  const double a = V[0] + mu, b = V[1], c = V[2], d = V[3] + mu, e = V[4], f = V[5] + mu;
+  const double A = d * f - e * e, B = c * e - b * f, C = b * e - c * d;
+  const double r = 1.0 / (a * A + b * B + c * C);
+  I[0] = A * r;
+  I[1] = B * r;
+  I[2] = C * r;
+  I[3] = (a * f - c * c) * r;
+  I[4] = (b * c - a * e) * r;
+  I[5] = (a * d - b * b) * r;
+}
+
+__global__ void __launch_bounds__(128)
+ba_schur_pairs(BaDev d, const BaPairItem* __restrict__ items, int nItems,
+               const int2* __restrict__ entries, double mu) {
+  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (item >= nItems) return;
+  const int lane = threadIdx.x & 31;
+  const int half = lane & 1;  // which 3 columns of the 6x6 block
+  const BaPairItem it = items[item];
+  double acc[18];
+#pragma unroll
+  for (int k = 0; k < 18; ++k) acc[k] = 0;
+  double racc[3] = {0, 0, 0};
+  const bool diag = (it.rowCam == it.colCam);
+  for (int e = it.begin + (lane >> 1); e < it.end; e += 16) {
+    const int2 ob = entries[e];
+    const double* Wa = d.W + 18 * (size_t)ob.x;
+    const double* Wb = d.W + 18 * (size_t)ob.y;
+    const int i = d.pt[ob.x];
+    double Iv[6];
+    inv3sym_mu(d.V + 6 * (size_t)i, mu, Iv);
+    double wa[18];
+#pragma unroll
+    for (int k = 0; k < 18; ++k) wa[k] = Wa[k];
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) {
+      const int c = 3 * half + cc;
+      const double b0 = Wb[3 * c], b1 = Wb[3 * c + 1], b2 = Wb[3 * c + 2];
+      const double t0 = Iv[0] * b0 + Iv[1] * b1 + Iv[2] * b2;
+      const double t1 = Iv[1] * b0 + Iv[3] * b1 + Iv[4] * b2;
+      const double t2 = Iv[2] * b0 + Iv[4] * b1 + Iv[5] * b2;
+#pragma unroll
+      for (int r = 0; r < 6; ++r)
+        acc[3 * r + cc] += wa[3 * r] * t0 + wa[3 * r + 1] * t1 + wa[3 * r + 2] * t2;
+    }
+    if (diag) {
+      const double* eb = d.eb + 3 * (size_t)i;
+      const double t0 = Iv[0] * eb[0] + Iv[1] * eb[1] + Iv[2] * eb[2];
+      const double t1 = Iv[1] * eb[0] + Iv[3] * eb[1] + Iv[4] * eb[2];
+      const double t2 = Iv[2] * eb[0] + Iv[4] * eb[1] + Iv[5] * eb[2];
+#pragma unroll
+      for (int rr = 0; rr < 3; ++rr) {
+        const double* wr = Wa + 3 * (3 * half + rr);  // row (3*half + rr) of W_a
+        racc[rr] += wr[0] * t0 + wr[1] * t1 + wr[2] * t2;
+      }
+    }
+  }
+  // butterfly over lanes of equal parity
+#pragma unroll
+  for (int o = 2; o < 32; o <<= 1) {
+#pragma unroll
+    for (int k = 0; k < 18; ++k) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) racc[k] += __shfl_xor_sync(0xffffffffu, racc[k], o);
+  }
+  if (lane < 2) {
+    const long long ns = d.ns;
+    const int r0 = 6 * it.rowCam, c0 = 6 * it.colCam + 3 * half;
+#pragma unroll
+    for (int r = 0; r < 6; ++r)
+#pragma unroll
+      for (int cc = 0; cc < 3; ++cc) {
+        // only the upper part (col >= row) of diagonal blocks is kept
+        if (!diag || (c0 + cc >= r0 + r))
+          atomicAdd(&d.S[(long long)(r0 + r) * ns + c0 + cc], -acc[3 * r + cc]);
+      }
+    if (diag) {
+#pragma unroll
+      for (int rr = 0; rr < 3; ++rr) atomicAdd(&d.rhs[r0 + 3 * half + rr], -racc[rr]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Back substitution, step 1, point-major, one observation per thread: t_i = sum_j W_ij^T da_j,
+// collapsed per point with segmented shuffles; run heads add into acc3[n][3] (zeroed before).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ba_back_subst(BaDev d, const double* __restrict__ dpa, double* __restrict__ acc3) {
+  const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  double acc[3] = {0, 0, 0};
+  int key = -1 - lane;
+  if (o < d.N) {
+    const int j = d.cam[o], i = d.pt[o];
+    key = i;
+    if (i >= d.ncon && j >= d.mcon) {
+      const double* Wp = d.W + 18 * (size_t)o;
+      const double* da = dpa + 6 * (size_t)j;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        double s = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) s += Wp[3 * r + c] * da[r];
+        acc[c] = s;
+      }
+    }
+  }
+  seg_reduce<3>(acc, key, lane);
+  const int kprev = __shfl_up_sync(0xffffffffu, key, 1);
+  const bool head = (lane == 0) || (kprev != key);
+  if (head && key >= d.ncon) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) atomicAdd(&acc3[3 * (size_t)key + c], acc[c]);
+  }
+}
+
+// Back substitution, step 2, one point per thread: nb holds t_i on entry; db_i = V*_i^-1 (eb_i - t_i),
+// nb <- pb + db, plus the point-side parts of |dp|^2, dL, |p|^2.
+__global__ void __launch_bounds__(256)
+ba_back_finish(BaDev d, const double* __restrict__ pb, double* __restrict__ nb,
+               double* __restrict__ dpb, double mu) {
+  __shared__ double s_red[8];
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double dp2 = 0, dl = 0, p2 = 0;
+  if (i < d.n) {
+    double x[3] = {pb[3 * i], pb[3 * i + 1], pb[3 * i + 2]};
+    double db[3] = {0, 0, 0};
+    if (i >= d.ncon) {
+      double Iv[6];
+      inv3sym_mu(d.V + 6 * i, mu, Iv);
+      const double* eb = d.eb + 3 * i;
+      const double t0 = eb[0] - nb[3 * i], t1 = eb[1] - nb[3 * i + 1], t2 = eb[2] - nb[3 * i + 2];
+      db[0] = Iv[0] * t0 + Iv[1] * t1 + Iv[2] * t2;
+      db[1] = Iv[1] * t0 + Iv[3] * t1 + Iv[4] * t2;
+      db[2] = Iv[2] * t0 + Iv[4] * t1 + Iv[5] * t2;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        dp2 += db[c] * db[c];
+        dl += db[c] * (mu * db[c] + eb[c]);
+        p2 += x[c] * x[c];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      dpb[3 * i + c] = db[c];
+      nb[3 * i + c] = x[c] + db[c];
+    }
+  }
+  double t = block_sum_1(dp2, s_red);
+  if (threadIdx.x == 0 && t != 0) atomicAdd(&d.sc[SC_DP_L2], t);
+  t = block_sum_1(dl, s_red);
+  if (threadIdx.x == 0 && t != 0) atomicAdd(&d.sc[SC_DL], t);
+  t = block_sum_1(p2, s_red);
+  if (threadIdx.x == 0 && t != 0) atomicAdd(&d.sc[SC_P_L2], t);
+}
+
+// Trial camera parameters na = pa + dpa and the camera-side parts of |dp|^2, dL, |p|^2.
+// addSums: only one rank contributes the (replicated) camera-side sums.
+__global__ void __launch_bounds__(256)
+ba_cam_update(BaDev d, const double* __restrict__ pa, const double* __restrict__ sol,
+              double* __restrict__ dpa, double* __restrict__ na, double mu, int addSums) {
+  __shared__ double s_red[8];
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  double dp2 = 0, dl = 0, p2 = 0;
+  if (t < 6 * d.m) {
+    const int j = t / 6, r = t - 6 * j;
+    double dlt = 0;
+    if (j >= d.mcon) {
+      dlt = sol[6 * (j - d.mcon) + r];
+      dp2 = dlt * dlt;
+      dl = dlt * (mu * dlt + d.ea[t]);
+      p2 = pa[t] * pa[t];
+    }
+    dpa[t] = dlt;
+    na[t] = pa[t] + dlt;
+  }
+  double s = block_sum_1(dp2, s_red);
+  if (threadIdx.x == 0 && addSums && s != 0) atomicAdd(&d.sc[SC_DP_L2], s);
+  s = block_sum_1(dl, s_red);
+  if (threadIdx.x == 0 && addSums && s != 0) atomicAdd(&d.sc[SC_DL], s);
+  s = block_sum_1(p2, s_red);
+  if (threadIdx.x == 0 && addSums && s != 0) atomicAdd(&d.sc[SC_P_L2], s);
+}
+
+// ------------------------------------------------------------------------------------------
+// Dense SPD solve of the reduced camera system.
+// Storage convention: S row-major with the blocks (row <= col) valid == column-major LOWER
+// triangle: element L(i, j), i >= j, lives at S[j * ns + i].
+// ------------------------------------------------------------------------------------------
+
+// Small systems (ns*ns doubles fit in shared memory): factor + both triangular solves in one CTA.
+__global__ void __launch_bounds__(256)
+ba_chol_small(double* __restrict__ S, double* __restrict__ rhs, int ns, double* __restrict__ sc) {
+  extern __shared__ double sL[];  // column-major lower, leading dimension ns
+  __shared__ int s_fail;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int t = tid; t < ns * ns; t += nt) sL[t] = S[t];
+  if (tid == 0) s_fail = 0;
+  __syncthreads();
+  for (int k = 0; k < ns; ++k) {
+    if (tid == 0) {
+      const double dkk = sL[k * ns + k];
+      if (!(dkk > 0) || !isfinite(dkk)) {
+        s_fail = 1;
+        sL[k * ns + k] = 1.0;
+      } else {
+        sL[k * ns + k] = sqrt(dkk);
+      }
+    }
+    __syncthreads();
+    if (s_fail) break;
+    const double rk = 1.0 / sL[k * ns + k];
+    for (int i = k + 1 + tid; i < ns; i += nt) sL[k * ns + i] *= rk;
+    __syncthreads();
+    // trailing update of the lower triangle: L(i, j) -= L(i,k) L(j,k), j in (k, ns), i >= j
+    const int rem = ns - k - 1;
+    for (int t = tid; t < rem * rem; t += nt) {
+      const int jj = t / rem, ii = t - jj * rem;
+      if (ii >= jj) {
+        const int i = k + 1 + ii, j = k + 1 + jj;
+        sL[j * ns + i] -= sL[k * ns + i] * sL[k * ns + j];
+      }
+    }
+    __syncthreads();
+  }
+  if (s_fail) {
+    if (tid == 0) sc[SC_FAIL] = 1.0;
+    return;
+  }
+  // forward L y = b, backward L^T x = y by one warp (columns striped over lanes)
+  if (tid < 32) {
+    __shared__ double sx[1024];
+    for (int i = tid; i < ns; i += 32) sx[i] = rhs[i];
+    __syncwarp();
+    for (int k = 0; k < ns; ++k) {
+      const double xk = sx[k] / sL[k * ns + k];
+      __syncwarp();
+      if (tid == 0) sx[k] = xk;
+      for (int i = k + 1 + tid; i < ns; i += 32) sx[i] -= sL[k * ns + i] * xk;
+      __syncwarp();
+    }
+    for (int k = ns - 1; k >= 0; --k) {
+      double part = 0;
+      for (int i = k + 1 + tid; i < ns; i += 32) part += sL[k * ns + i] * sx[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      __syncwarp();
+      if (tid == 0) sx[k] = (sx[k] - part) / sL[k * ns + k];
+      __syncwarp();
+    }
+    for (int i = tid; i < ns; i += 32) rhs[i] = sx[i];
+  }
+}
+
+// ---- blocked right-looking Cholesky for large ns (block size CB) ----
+constexpr int CB = 64;
+
+// factor the CB x CB diagonal block k (in place, lower), one CTA
+__global__ void __launch_bounds__(256)
+ba_chol_potf2(double* __restrict__ S, int ns, int k0, int bs, double* __restrict__ sc) {
+  __shared__ double sA[CB][CB + 1];
+  __shared__ int s_fail;
+  const int tid = threadIdx.x;
+  for (int t = tid; t < bs * bs; t += 256) {
+    const int j = t / bs, i = t - j * bs;
+    sA[i][j] = (i >= j) ? S[(size_t)(k0 + j) * ns + k0 + i] : 0.0;
+  }
+  if (tid == 0) s_fail = 0;
+  __syncthreads();
+  for (int k = 0; k < bs; ++k) {
+    if (tid == 0) {
+      const double dkk = sA[k][k];
+      if (!(dkk > 0) || !isfinite(dkk)) {
+        s_fail = 1;
+        sA[k][k] = 1.0;
+      } else
+        sA[k][k] = sqrt(dkk);
+    }
+    __syncthreads();
+    const double rk = 1.0 / sA[k][k];
+    for (int i = k + 1 + tid; i < bs; i += 256) sA[i][k] *= rk;
+    __syncthreads();
+    const int rem = bs - k - 1;
+    for (int t = tid; t < rem * rem; t += 256) {
+      const int jj = t / rem, ii = t - jj * rem;
+      if (ii >= jj) sA[k + 1 + ii][k + 1 + jj] -= sA[k + 1 + ii][k] * sA[k + 1 + jj][k];
+    }
+    __syncthreads();
+  }
+  if (s_fail && tid == 0) sc[SC_FAIL] = 1.0;
+  for (int t = tid; t < bs * bs; t += 256) {
+    const int j = t / bs, i = t - j * bs;
+    if (i >= j) S[(size_t)(k0 + j) * ns + k0 + i] = sA[i][j];
+  }
+}
+
+// panel solve: rows below the diagonal block: X L_kk^T = A  -> each thread owns one row
+__global__ void __launch_bounds__(128)
+ba_chol_trsm(double* __restrict__ S, int ns, int k0, int bs) {
+  __shared__ double sLk[CB][CB + 1];
+  const int tid = threadIdx.x;
+  for (int t = tid; t < bs * bs; t += 128) {
+    const int j = t / bs, i = t - j * bs;
+    sLk[i][j] = (i >= j) ? S[(size_t)(k0 + j) * ns + k0 + i] : 0.0;
+  }
+  __syncthreads();
+  const int row = k0 + bs + blockIdx.x * 128 + tid;
+  if (row >= ns) return;
+  double x[CB];
+#pragma unroll 8
+  for (int j = 0; j < bs; ++j) x[j] = S[(size_t)(k0 + j) * ns + row];
+  for (int j = 0; j < bs; ++j) {
+    double s = x[j];
+    for (int p = 0; p < j; ++p) s -= x[p] * sLk[j][p];
+    x[j] = s / sLk[j][j];
+  }
+  for (int j = 0; j < bs; ++j) S[(size_t)(k0 + j) * ns + row] = x[j];
+}
+
+// trailing update: A(i, j) -= sum_p L(i, k0+p) L(j, k0+p) for i >= j > panel; 64x64 tiles, 256
+// threads, 4x4 micro-tiles, fp64 FMA.
+__global__ void __launch_bounds__(256)
+ba_chol_syrk(double* __restrict__ S, int ns, int k0, int bs) {
+  const int tj = blockIdx.x, ti = blockIdx.y;  // tile coordinates in the trailing matrix
+  if (ti < tj) return;
+  constexpr int KC = 32;  // contraction chunk staged in shared memory
+  __shared__ double sAi[KC][CB + 1];  // [p][row]
+  __shared__ double sAj[KC][CB + 1];
+  const int base = k0 + bs;
+  const int i0 = base + ti * CB, j0 = base + tj * CB;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each 4 x 4
+  double c[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) c[a][b] = 0;
+  for (int p0 = 0; p0 < bs; p0 += KC) {
+    const int pc = min(KC, bs - p0);
+    __syncthreads();
+    for (int t = tid; t < pc * CB; t += 256) {
+      const int p = t / CB, r = t - p * CB;
+      sAi[p][r] = (i0 + r < ns) ? S[(size_t)(k0 + p0 + p) * ns + i0 + r] : 0.0;
+      sAj[p][r] = (j0 + r < ns) ? S[(size_t)(k0 + p0 + p) * ns + j0 + r] : 0.0;
+    }
+    __syncthreads();
+    for (int p = 0; p < pc; ++p) {
+      double ai[4], aj[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) ai[a] = sAi[p][tx + 16 * a];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) aj[b] = sAj[p][ty + 16 * b];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) c[a][b] += ai[a] * aj[b];
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = i0 + tx + 16 * a, j = j0 + ty + 16 * b;
+      if (i < ns && j < ns && i >= j) S[(size_t)j * ns + i] -= c[a][b];
+    }
+}
+
+// Triangular solves for the blocked factor, one kernel per block step (ns/CB steps per direction).
+// forward step k : every CTA redundantly solves L_kk y_k = b_k (b_k is read-only in this step),
+//                  CTA 0 publishes y_k to `y`, all CTAs update their rows b_i -= L_ik y_k (i > k).
+__global__ void __launch_bounds__(128)
+ba_trsv_fwd_step(const double* __restrict__ S, double* __restrict__ b, double* __restrict__ y,
+                 int ns, int k0, int bs) {
+  __shared__ double sx[CB];
+  const int tid = threadIdx.x;
+  if (tid < 32) {
+    for (int i = tid; i < bs; i += 32) sx[i] = b[k0 + i];
+    __syncwarp();
+    for (int k = 0; k < bs; ++k) {
+      const double xk = sx[k] / S[(size_t)(k0 + k) * ns + k0 + k];
+      __syncwarp();
+      if (tid == 0) sx[k] = xk;
+      for (int i = k + 1 + tid; i < bs; i += 32) sx[i] -= S[(size_t)(k0 + k) * ns + k0 + i] * xk;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && tid < bs) y[k0 + tid] = sx[tid];
+  const int row = k0 + bs + blockIdx.x * 128 + tid;
+  if (row < ns) {
+    double s = 0;
+    for (int p = 0; p < bs; ++p) s += S[(size_t)(k0 + p) * ns + row] * sx[p];
+    b[row] -= s;
+  }
+}
+
+// backward step k: every CTA redundantly solves L_kk^T x_k = y_k (read-only), CTA 0 publishes x_k
+//                  to `x`, all CTAs update their columns y_c -= L(k-block, c)^T x_k (c < k0).
+__global__ void __launch_bounds__(128)
+ba_trsv_bwd_step(const double* __restrict__ S, double* __restrict__ y, double* __restrict__ x,
+                 int ns, int k0, int bs) {
+  __shared__ double sx[CB];
+  const int tid = threadIdx.x;
+  if (tid < 32) {
+    for (int i = tid; i < bs; i += 32) sx[i] = y[k0 + i];
+    __syncwarp();
+    for (int k = bs - 1; k >= 0; --k) {
+      // x_k = (y_k - sum_{i>k} L(i,k) x_i) / L(k,k); the subtraction was applied incrementally
+      const double xk = sx[k] / S[(size_t)(k0 + k) * ns + k0 + k];
+      __syncwarp();
+      if (tid == 0) sx[k] = xk;
+      for (int i = tid; i < k; i += 32) sx[i] -= S[(size_t)(k0 + i) * ns + k0 + k] * xk;
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (blockIdx.x == 0 && tid < bs) x[k0 + tid] = sx[tid];
+  const int c = blockIdx.x * 128 + tid;
+  if (c < k0) {
+    const double* col = S + (size_t)c * ns + k0;  // L(k0 + p, c), p contiguous
+    double s = 0;
+    for (int p = 0; p < bs; ++p) s += col[p] * sx[p];
+    y[c] -= s;
+  }
+}
+
+}  // namespace coslam

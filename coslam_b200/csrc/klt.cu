@@ -1,0 +1,671 @@
+// klt.cu -- host side of the KLT tracker group + its C-ABI (see include/coslam_b200.h).
+// Replaces V3D_GPU::KLT_SequenceTracker (tracking/CGKLT/v3d_gpuklt.{h,cpp}) and its GL/Cg runtime.
+// All sequencing (status mapping, top-N selection, slot refill, provide) runs on the device; a
+// frame costs one H2D copy per camera, one D2H copy of the feature table and one synchronise.
+#include <algorithm>
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "common.cuh"
+#include "klt_kernels.cuh"
+
+using namespace coslam;
+
+struct cosl_klt {
+  cosl_klt_config cfg;
+  int C = 1, W = 0, H = 0, L = 0, fw = 0, fh = 0, F = 0, plCap = 0, device = 0;
+  int levelSkip = 1, halfWidth = 3;
+  float trackMargin = 4.f, conv = 0.1f, ssd = 5000.f, detectMargin = 10.f;
+  cudaStream_t stream = nullptr;
+  // geometry
+  int lvW[8], lvH[8];
+  long long lvOff[8];
+  long long pyrStride = 0;  // float4 elements per camera
+  size_t imgPitch = 0, imgStride = 0;
+  int candCap = 0, smemKeys = 0;
+  // device memory
+  uint8_t* d_img = nullptr;
+  float4* d_pyr[2] = {nullptr, nullptr};
+  int cur = 1;  // pyr1 == d_pyr[cur]
+  float* d_corn = nullptr;
+  float4 *d_src = nullptr, *d_dst = nullptr, *d_ping = nullptr, *d_pong = nullptr, *d_res = nullptr;
+  float4* d_present = nullptr;
+  int* d_nbr = nullptr;
+  unsigned long long* d_cand = nullptr;
+  int* d_counters = nullptr;
+  cosl_klt_feature* d_feat = nullptr;
+  float* d_feedpts = nullptr;
+  int* d_feedids = nullptr;
+  int feedCap = 0;
+  // pinned host mirrors
+  cosl_klt_feature* h_feat = nullptr;
+  int* h_counters = nullptr;
+  float4* h_present = nullptr;
+  bool havePrev = false;
+  SectionTimer timer;
+  int secPyr = 0, secTrack = 0, secDetect = 0, secSelect = 0;
+};
+
+namespace {
+
+int alloc_group(cosl_klt* g) {
+  const int C = g->C, W = g->W, H = g->H, F = g->F;
+  long long off = 0;
+  for (int l = 0; l < g->L; ++l) {
+    g->lvW[l] = W >> l;
+    g->lvH[l] = H >> l;
+    g->lvOff[l] = off;
+    off += (long long)g->lvW[l] * g->lvH[l];
+  }
+  g->pyrStride = off;
+  g->imgPitch = ((size_t)W + 15) & ~(size_t)15;
+  g->imgStride = g->imgPitch * H;
+  // candidate capacity: a strict (2r+1)^2 maximum admits at most one survivor per (r+1)^2 pixels
+  const int r = std::max(1, g->cfg.minDistance);
+  long long maxCand = ((long long)(W + r) / (r + 1) + 1) * ((long long)(H + r) / (r + 1) + 1);
+  int cap = 1024;
+  while (cap < maxCand) cap <<= 1;
+  g->candCap = cap;
+  g->smemKeys = std::min(cap, 16384);
+  COSL_CUDA(cudaMalloc(&g->d_img, g->imgStride * C));
+  for (int b = 0; b < 2; ++b) {
+    COSL_CUDA(cudaMalloc(&g->d_pyr[b], sizeof(float4) * g->pyrStride * C));
+    COSL_CUDA(cudaMemsetAsync(g->d_pyr[b], 0, sizeof(float4) * g->pyrStride * C, g->stream));
+  }
+  COSL_CUDA(cudaMalloc(&g->d_corn, sizeof(float) * (size_t)W * H * C));
+  const size_t fbytes = sizeof(float4) * (size_t)F * C;
+  float4** bufs[] = {&g->d_src, &g->d_dst, &g->d_ping, &g->d_pong, &g->d_res, &g->d_present};
+  std::vector<float4> init((size_t)F * C, make_float4(-1.f, -1.f, 1.f, 0.f));
+  for (auto pb : bufs) {
+    COSL_CUDA(cudaMalloc(pb, fbytes));
+    COSL_CUDA(cudaMemcpy(*pb, init.data(), fbytes, cudaMemcpyHostToDevice));
+  }
+  COSL_CUDA(cudaMalloc(&g->d_cand, sizeof(unsigned long long) * (size_t)cap * C));
+  COSL_CUDA(cudaMalloc(&g->d_counters, sizeof(int) * 8 * C));
+  COSL_CUDA(cudaMemset(g->d_counters, 0, sizeof(int) * 8 * C));
+  COSL_CUDA(cudaMalloc(&g->d_feat, sizeof(cosl_klt_feature) * (size_t)F * C));
+  COSL_CUDA(cudaMallocHost(&g->h_feat, sizeof(cosl_klt_feature) * (size_t)F * C));
+  COSL_CUDA(cudaMallocHost(&g->h_counters, sizeof(int) * 8 * C));
+  COSL_CUDA(cudaMallocHost(&g->h_present, fbytes));
+  // neighbour slots of the gain smoothness term (klt_tracker_with_gain.cg:64-75): NEAREST,
+  // CLAMP_TO_EDGE lookups in the featW x featH slot texture at st0 +- ds0; betaN1 adds the SCALAR
+  // ds0.x (resp. ds0.y) to both coordinates.
+  std::vector<int> nbr((size_t)F * 8);
+  const double fw = g->fw, fh = g->fh;
+  for (int sy = 0; sy < g->fh; ++sy)
+    for (int sx = 0; sx < g->fw; ++sx) {
+      const double cx = sx + 0.5, cy = sy + 0.5;
+      const double offs[8][2] = {{+1.0, +fh / fw}, {-1.0, -fh / fw}, {+fw / fh, +1.0},
+                                 {-fw / fh, -1.0}, {+1.0, 0.0},      {-1.0, 0.0},
+                                 {0.0, +1.0},      {0.0, -1.0}};
+      for (int k = 0; k < 8; ++k) {
+        const int nx = std::min(std::max((int)std::floor(cx + offs[k][0]), 0), g->fw - 1);
+        const int ny = std::min(std::max((int)std::floor(cy + offs[k][1]), 0), g->fh - 1);
+        nbr[(size_t)(sy * g->fw + sx) * 8 + k] = ny * g->fw + nx;
+      }
+    }
+  COSL_CUDA(cudaMalloc(&g->d_nbr, sizeof(int) * nbr.size()));
+  COSL_CUDA(cudaMemcpy(g->d_nbr, nbr.data(), sizeof(int) * nbr.size(), cudaMemcpyHostToDevice));
+  // dynamic shared memory opt-ins
+  COSL_CUDA(cudaFuncSetAttribute(klt_select_refill, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 g->smemKeys * (int)sizeof(unsigned long long)));
+  const int TS = NM_T + 2 * r;
+  const int nmBytes = (TS * TS + TS * NM_T) * (int)sizeof(float);
+  if (nmBytes > 48 * 1024)
+    COSL_CUDA(cudaFuncSetAttribute(klt_nonmax_compact, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   nmBytes));
+  g->secPyr = g->timer.section("klt_pyramid");
+  g->secTrack = g->timer.section("klt_track");
+  g->secDetect = g->timer.section("klt_detect");
+  g->secSelect = g->timer.section("klt_select");
+  COSL_CUDA(cudaStreamSynchronize(g->stream));
+  return COSL_OK;
+}
+
+void free_group(cosl_klt* g) {
+  if (!g) return;
+  cudaSetDevice(g->device);
+  if (g->stream) cudaStreamSynchronize(g->stream);
+  g->timer.destroy();
+  cudaFree(g->d_img);
+  cudaFree(g->d_pyr[0]);
+  cudaFree(g->d_pyr[1]);
+  cudaFree(g->d_corn);
+  cudaFree(g->d_src);
+  cudaFree(g->d_dst);
+  cudaFree(g->d_ping);
+  cudaFree(g->d_pong);
+  cudaFree(g->d_res);
+  cudaFree(g->d_present);
+  cudaFree(g->d_nbr);
+  cudaFree(g->d_cand);
+  cudaFree(g->d_counters);
+  cudaFree(g->d_feat);
+  cudaFree(g->d_feedpts);
+  cudaFree(g->d_feedids);
+  cudaFreeHost(g->h_feat);
+  cudaFreeHost(g->h_counters);
+  cudaFreeHost(g->h_present);
+  if (g->stream) cudaStreamDestroy(g->stream);
+  delete g;
+}
+
+// ---- stages (all asynchronous on g->stream) ----
+
+int upload_images(cosl_klt* g, const uint8_t* const* imgs, size_t pitch, cudaMemcpyKind kind) {
+  for (int c = 0; c < g->C; ++c)
+    COSL_CUDA(cudaMemcpy2DAsync(g->d_img + (size_t)c * g->imgStride, g->imgPitch, imgs[c], pitch,
+                                g->W, g->H, kind, g->stream));
+  return COSL_OK;
+}
+
+// PyramidWithDerivativesCreator::buildPyramidForGrayscaleImage (v3d_gpupyramid.cpp:366-429)
+int build_pyramid(cosl_klt* g) {
+  float4* P = g->d_pyr[g->cur];
+  g->timer.begin(g->secPyr, g->stream);
+  dim3 g0(div_up(g->W, P0_TW), div_up(g->H, P0_TH), g->C);
+  COSL_LAUNCH(klt_pyr_level0, g0, 256, 0, g->stream, g->d_img, g->imgPitch, g->imgStride, P,
+              g->pyrStride, g->W, g->H);
+  for (int l = 1; l < g->L; ++l) {
+    dim3 gl(div_up(g->lvW[l], PD_TW), div_up(g->lvH[l], PD_TH), g->C);
+    COSL_LAUNCH(klt_pyr_down, gl, 256, 0, g->stream, P + g->lvOff[l - 1], P + g->lvOff[l],
+                g->pyrStride, g->lvW[l - 1], g->lvH[l - 1], g->lvW[l], g->lvH[l]);
+  }
+  g->timer.end(g->stream);
+  COSL_CUDA(cudaGetLastError());
+  return COSL_OK;
+}
+
+KltTrackParams track_params(const cosl_klt* g, bool strict) {
+  KltTrackParams P;
+  P.W = g->W;
+  P.H = g->H;
+  P.F = g->F;
+  P.halfWidth = g->halfWidth;
+  const float Wf = (float)g->W, Hf = (float)g->H, m = g->trackMargin;
+  if (strict) {
+    P.sqrConv = g->conv * g->conv;
+    P.ssdThr = g->ssd;
+    P.vr0 = m / Wf;
+    P.vr1 = m / Hf;
+    P.vr2 = 1.0f - m / Wf;
+    P.vr3 = 1.0f - m / Hf;
+  } else {  // v3d_gpuklt.cpp:246-248, 266-270
+    P.sqrConv = 1000000.0f;
+    P.ssdThr = 1000000.0f;
+    P.vr0 = -1.0f;
+    P.vr1 = -1.0f;
+    P.vr2 = 2.0f;
+    P.vr3 = 2.0f;
+  }
+  P.lambda = 1.0f;
+  P.delta = 200.0f;
+  return P;
+}
+
+// KLT_TrackerWithGain::trackFeaturesAndGain (v3d_gpuklt.cpp:205-305) /
+// KLT_Tracker::trackFeatures (:99-161); result -> d_res
+int run_tracker(cosl_klt* g) {
+  const float4* P0 = g->d_pyr[1 - g->cur];
+  const float4* P1 = g->d_pyr[g->cur];
+  const int wpb = 8;  // warps per block
+  dim3 grid(div_up(g->F, wpb), g->C);
+  g->timer.begin(g->secTrack, g->stream);
+  if (g->cfg.trackWithGain) {
+    const float4* in = g->d_src;
+    float4* bufs[2] = {g->d_ping, g->d_pong};
+    int which = 0, first = 1;
+    bool strict = false;
+    for (int level = g->L - 1; level >= 0; level -= g->levelSkip) {
+      const int w = g->lvW[level], h = g->lvH[level];
+      const float dsx = 1.0f / (float)w, dsy = 1.0f / (float)h;
+      for (int iter = 1; iter <= g->cfg.nIterations; ++iter) {
+        if (iter == 1)
+          strict = false;
+        else if (iter == g->cfg.nIterations)
+          strict = true;
+        const bool last =
+            (level - g->levelSkip < 0) && (iter == g->cfg.nIterations);
+        float4* out = last ? g->d_res : bufs[which];
+        COSL_LAUNCH(klt_gain_pass, grid, wpb * 32, 0, g->stream, P0, P1, g->pyrStride,
+                    g->lvOff[level], w, h, g->d_src, in, out, g->d_nbr, dsx, dsy,
+                    track_params(g, strict), first);
+        in = out;
+        which ^= 1;
+        first = 0;
+      }
+    }
+  } else {
+    KltLevels LV;
+    LV.n = 0;
+    float mult = (float)(1 << (g->L - 1));
+    for (int level = g->L - 1; level >= 0; level -= g->levelSkip) {
+      LV.level[LV.n] = level;
+      LV.w[LV.n] = g->lvW[level];
+      LV.h[LV.n] = g->lvH[level];
+      LV.off[LV.n] = g->lvOff[level];
+      LV.mult[LV.n] = mult;
+      mult /= (float)(1 << g->levelSkip);
+      ++LV.n;
+    }
+    const int nIter = (g->cfg.compat & COSL_KLT_COMPAT_ITER5) ? 5 : g->cfg.nIterations;
+    COSL_LAUNCH(klt_track_2x2, grid, wpb * 32, 0, g->stream, P0, P1, g->pyrStride, LV, g->d_src,
+                g->d_res, track_params(g, true), nIter);
+  }
+  g->timer.end(g->stream);
+  COSL_CUDA(cudaGetLastError());
+  return COSL_OK;
+}
+
+int zero_counters(cosl_klt* g) {
+  COSL_CUDA(cudaMemsetAsync(g->d_counters, 0, sizeof(int) * 8 * g->C, g->stream));
+  return COSL_OK;
+}
+
+int run_status(cosl_klt* g) {
+  dim3 grid(div_up(g->F, 256), g->C);
+  COSL_LAUNCH(klt_status, grid, 256, 0, g->stream, g->d_res, g->d_feat, g->d_counters, g->F);
+  return COSL_OK;
+}
+
+// KLT_Detector::detectCorners + extractCorners (v3d_gpuklt.cpp:423-588) and the slot logic of
+// detect/redetect (:651-805).  mode 0: detect (present = external points), 1: redetect.
+int run_detector(cosl_klt* g, int mode, int nPresentExt) {
+  const float Wf = (float)g->W, Hf = (float)g->H, mg = g->detectMargin;
+  g->timer.begin(g->secDetect, g->stream);
+  dim3 gc(div_up(g->W, DC_TW), div_up(g->H, DC_TH), g->C);
+  COSL_LAUNCH(klt_cornerness, gc, 256, 0, g->stream, g->d_pyr[g->cur], g->pyrStride, g->d_corn,
+              g->W, g->H, g->cfg.minCornerness, mg / Wf, mg / Hf, 1.0f - mg / Wf, 1.0f - mg / Hf);
+  if (mode == 1) {
+    dim3 gs(div_up(g->F, 256), g->C);
+    COSL_LAUNCH(klt_suppress, gs, 256, 0, g->stream, g->d_res, g->F, g->F, g->d_corn, g->W, g->H);
+  } else if (nPresentExt > 0) {
+    dim3 gs(div_up(nPresentExt, 256), g->C);
+    COSL_LAUNCH(klt_suppress, gs, 256, 0, g->stream, g->d_present, nPresentExt, g->F, g->d_corn,
+                g->W, g->H);
+  }
+  const int r = std::max(1, g->cfg.minDistance);
+  const int TS = NM_T + 2 * r;
+  const int nmBytes = (TS * TS + TS * NM_T) * (int)sizeof(float);
+  dim3 gn(div_up(g->W, NM_T), div_up(g->H, NM_T), g->C);
+  COSL_LAUNCH(klt_nonmax_compact, gn, 256, nmBytes, g->stream, g->d_corn, g->W, g->H, r, g->d_cand,
+              g->candCap, g->d_counters);
+  g->timer.end(g->stream);
+  g->timer.begin(g->secSelect, g->stream);
+  COSL_LAUNCH(klt_select_refill, g->C, 1024, g->smemKeys * sizeof(unsigned long long), g->stream,
+              g->d_cand, g->candCap, g->plCap, g->d_counters, g->d_feat, g->d_dst, g->d_present,
+              nPresentExt, g->F, g->W, g->H, mode, g->cfg.trackWithGain ? 1 : 0, g->smemKeys);
+  g->timer.end(g->stream);
+  COSL_CUDA(cudaGetLastError());
+  return COSL_OK;
+}
+
+int fetch_results(cosl_klt* g) {
+  COSL_CUDA(cudaMemcpyAsync(g->h_feat, g->d_feat, sizeof(cosl_klt_feature) * (size_t)g->F * g->C,
+                            cudaMemcpyDeviceToHost, g->stream));
+  COSL_CUDA(cudaMemcpyAsync(g->h_counters, g->d_counters, sizeof(int) * 8 * g->C,
+                            cudaMemcpyDeviceToHost, g->stream));
+  COSL_CUDA(cudaStreamSynchronize(g->stream));
+  return COSL_OK;
+}
+
+int advance(cosl_klt* g) {
+  // swapFeatureBuffers + swap pyramids (v3d_gpuklt.h:252-259); the feature buffer is copied, not
+  // swapped, so a later feed() still sees the provided set (see DESIGN.md, quirk list)
+  const size_t n = (size_t)g->F * g->C;
+  COSL_LAUNCH(klt_copy_f4, (unsigned)div_up64(n, 256), 256, 0, g->stream, g->d_dst, g->d_src, n);
+  g->cur = 1 - g->cur;
+  return COSL_OK;
+}
+
+int do_track(cosl_klt* g) {
+  COSL_TRY(build_pyramid(g));
+  COSL_TRY(run_tracker(g));
+  COSL_TRY(zero_counters(g));
+  COSL_TRY(run_status(g));
+  return COSL_OK;
+}
+
+int do_redetect(cosl_klt* g) {
+  COSL_TRY(do_track(g));
+  COSL_TRY(run_detector(g, 1, 0));
+  return COSL_OK;
+}
+
+int do_detect(cosl_klt* g, int nPresentExt) {
+  COSL_TRY(build_pyramid(g));
+  COSL_TRY(zero_counters(g));
+  COSL_TRY(run_detector(g, 0, nPresentExt));
+  return COSL_OK;
+}
+
+void copy_out(cosl_klt* g, int cam, cosl_klt_feature* dest) {
+  std::memcpy(dest, g->h_feat + (size_t)cam * g->F, sizeof(cosl_klt_feature) * g->F);
+}
+
+}  // namespace
+
+/* ================================================================ C-ABI */
+extern "C" {
+
+void cosl_klt_config_default(cosl_klt_config* c) {
+  if (!c) return;
+  c->nIterations = 12;
+  c->nLevels = 3;
+  c->levelSkip = 2;
+  c->windowWidth = 5;
+  c->trackBorderMargin = 4.0f;
+  c->convergenceThreshold = 0.1f;
+  c->SSD_Threshold = 5000.0f;
+  c->trackWithGain = 0;
+  c->minDistance = 8;
+  c->minCornerness = 1000.0f;
+  c->detectBorderMargin = 4.0f;
+  c->compat = COSL_KLT_COMPAT_ITER5;
+}
+
+int cosl_klt_group_create(const cosl_klt_config* cfg, int nCams, int width, int height,
+                          int nLevels, int featW, int featH, int plW, int plH, int device,
+                          cosl_klt** out) {
+  if (!cfg || !out) return set_error(COSL_E_INVALID, "null argument");
+  *out = nullptr;
+  if (nCams < 1 || nCams > 64 || width < 16 || height < 16 || width > 65535 || height > 65535 ||
+      nLevels < 1 || nLevels > 8 || featW < 1 || featH < 1 || (width >> (nLevels - 1)) < 2 ||
+      (height >> (nLevels - 1)) < 2)
+    return set_error(COSL_E_INVALID, "bad tracker geometry %dx%d L=%d feat=%dx%d C=%d", width,
+                     height, nLevels, featW, featH, nCams);
+  if (cfg->windowWidth < 1 || cfg->windowWidth > 31 || cfg->minDistance < 1 ||
+      cfg->minDistance > 32 || cfg->nIterations < 1)
+    return set_error(COSL_E_INVALID, "bad tracker config");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev)
+    return set_error(COSL_E_CUDA, "CUDA device %d not available (%d devices)", device, ndev);
+  COSL_CUDA(cudaSetDevice(device));
+  cosl_klt* g = new (std::nothrow) cosl_klt();
+  if (!g) return set_error(COSL_E_NOMEM, "host allocation failed");
+  g->cfg = *cfg;
+  g->cfg.nLevels = nLevels;
+  g->C = nCams;
+  g->W = width;
+  g->H = height;
+  g->L = nLevels;
+  g->fw = featW;
+  g->fh = featH;
+  g->F = featW * featH;
+  if (plW <= 0) plW = 2 * featW;
+  if (plH <= 0) plH = 2 * featH;
+  g->plCap = plW * plH;
+  g->device = device;
+  g->levelSkip = cfg->levelSkip > 0 ? cfg->levelSkip : (nLevels - 1);
+  if (g->levelSkip < 1) g->levelSkip = 1;
+  g->halfWidth = cfg->windowWidth / 2;
+  g->trackMargin = cfg->trackBorderMargin;
+  g->conv = cfg->convergenceThreshold;
+  g->ssd = cfg->SSD_Threshold;
+  g->detectMargin = 10.0f;  // KLT_Detector::_margin default (v3d_gpuklt.h:113-114)
+  cudaError_t e = cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete g;
+    return set_error(COSL_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+  }
+  int rc = alloc_group(g);
+  if (rc != COSL_OK) {
+    free_group(g);
+    return rc;
+  }
+  *out = g;
+  return COSL_OK;
+}
+
+int cosl_klt_create(const cosl_klt_config* cfg, int width, int height, int nLevels, int featW,
+                    int featH, int plW, int plH, int device, cosl_klt** out) {
+  return cosl_klt_group_create(cfg, 1, width, height, nLevels, featW, featH, plW, plH, device, out);
+}
+
+int cosl_klt_destroy(cosl_klt* h) {
+  free_group(h);
+  return COSL_OK;
+}
+
+#define KLT_ENTER(h)                                              \
+  if (!(h)) return set_error(COSL_E_INVALID, "null tracker handle"); \
+  COSL_CUDA(cudaSetDevice((h)->device));
+
+#define KLT_SINGLE(h) \
+  KLT_ENTER(h)        \
+  if ((h)->C != 1) return set_error(COSL_E_STATE, "single-camera call on a %d-camera group", (h)->C);
+
+int cosl_klt_detect(cosl_klt* h, const uint8_t* img, size_t pitch, int nPresent,
+                    const float* present3, cosl_klt_feature* dest, int* nDetected) {
+  KLT_SINGLE(h)
+  if (!img || !dest || !nDetected || nPresent < 0 || nPresent > h->F || (nPresent && !present3) ||
+      pitch < (size_t)h->W)
+    return set_error(COSL_E_INVALID, "cosl_klt_detect: bad argument");
+  for (int i = 0; i < nPresent; ++i)
+    h->h_present[i] = make_float4(present3[3 * i], present3[3 * i + 1], 0.f, 0.f);
+  if (nPresent)
+    COSL_CUDA(cudaMemcpyAsync(h->d_present, h->h_present, sizeof(float4) * nPresent,
+                              cudaMemcpyHostToDevice, h->stream));
+  const uint8_t* imgs[1] = {img};
+  COSL_TRY(upload_images(h, imgs, pitch, cudaMemcpyHostToDevice));
+  COSL_TRY(do_detect(h, nPresent));
+  COSL_TRY(fetch_results(h));
+  copy_out(h, 0, dest);
+  *nDetected = h->h_counters[2];
+  return COSL_OK;
+}
+
+int cosl_klt_redetect(cosl_klt* h, const uint8_t* img, size_t pitch, cosl_klt_feature* dest,
+                      int* nNewFeatures) {
+  KLT_SINGLE(h)
+  if (!img || !dest || !nNewFeatures || pitch < (size_t)h->W)
+    return set_error(COSL_E_INVALID, "cosl_klt_redetect: bad argument");
+  const uint8_t* imgs[1] = {img};
+  COSL_TRY(upload_images(h, imgs, pitch, cudaMemcpyHostToDevice));
+  COSL_TRY(do_redetect(h));
+  COSL_TRY(fetch_results(h));
+  copy_out(h, 0, dest);
+  *nNewFeatures = h->h_counters[2];
+  return COSL_OK;
+}
+
+int cosl_klt_track(cosl_klt* h, const uint8_t* img, size_t pitch, cosl_klt_feature* dest,
+                   int* nPresent) {
+  KLT_SINGLE(h)
+  if (!img || !dest || !nPresent || pitch < (size_t)h->W)
+    return set_error(COSL_E_INVALID, "cosl_klt_track: bad argument");
+  const uint8_t* imgs[1] = {img};
+  COSL_TRY(upload_images(h, imgs, pitch, cudaMemcpyHostToDevice));
+  COSL_TRY(do_track(h));
+  // provide: the tracked set becomes the feature table of the next frame
+  const size_t n = (size_t)h->F;
+  COSL_LAUNCH(klt_copy_f4, (unsigned)div_up64(n, 256), 256, 0, h->stream, h->d_res, h->d_dst, n);
+  COSL_TRY(fetch_results(h));
+  copy_out(h, 0, dest);
+  *nPresent = h->h_counters[0];
+  return COSL_OK;
+}
+
+int cosl_klt_feed(cosl_klt* h, int npts, const float* pts3, int* trackIds, int* nFed) {
+  KLT_SINGLE(h)
+  if (npts < 0 || (npts && (!pts3 || !trackIds)) || !nFed)
+    return set_error(COSL_E_INVALID, "cosl_klt_feed: bad argument");
+  *nFed = 0;
+  if (npts == 0) return COSL_OK;
+  if (npts > h->feedCap) {
+    cudaFree(h->d_feedpts);
+    cudaFree(h->d_feedids);
+    h->d_feedpts = nullptr;
+    h->d_feedids = nullptr;
+    h->feedCap = 0;
+    COSL_CUDA(cudaMalloc(&h->d_feedpts, sizeof(float) * 3 * npts));
+    COSL_CUDA(cudaMalloc(&h->d_feedids, sizeof(int) * (npts + 1)));
+    h->feedCap = npts;
+  }
+  COSL_CUDA(cudaMemcpyAsync(h->d_feedpts, pts3, sizeof(float) * 3 * npts, cudaMemcpyHostToDevice,
+                            h->stream));
+  COSL_CUDA(cudaMemsetAsync(h->d_feedids, 0xff, sizeof(int) * (npts + 1), h->stream));
+  COSL_LAUNCH(klt_feed_kill, div_up(h->F, 256), 256, 0, h->stream, h->d_dst, h->F, h->d_feedpts,
+              npts);
+  COSL_LAUNCH(klt_feed_place, 1, 32, 0, h->stream, h->d_dst, h->F, h->d_feedpts, npts,
+              h->d_feedids, h->d_feedids + npts);
+  std::vector<int> ids(npts + 1);
+  COSL_CUDA(cudaMemcpyAsync(ids.data(), h->d_feedids, sizeof(int) * (npts + 1),
+                            cudaMemcpyDeviceToHost, h->stream));
+  COSL_CUDA(cudaStreamSynchronize(h->stream));
+  std::memcpy(trackIds, ids.data(), sizeof(int) * npts);
+  *nFed = ids[npts];
+  return COSL_OK;
+}
+
+int cosl_klt_advance(cosl_klt* h) {
+  KLT_ENTER(h)
+  COSL_TRY(advance(h));
+  COSL_CUDA(cudaGetLastError());
+  return COSL_OK;
+}
+
+int cosl_klt_set_margin(cosl_klt* h, float m) {  // tracker AND detector (v3d_gpuklt.h:217-224)
+  KLT_ENTER(h)
+  h->trackMargin = m;
+  h->detectMargin = m;
+  return COSL_OK;
+}
+int cosl_klt_set_conv(cosl_klt* h, float t) {
+  KLT_ENTER(h)
+  h->conv = t;
+  return COSL_OK;
+}
+int cosl_klt_set_ssd(cosl_klt* h, float t) {
+  KLT_ENTER(h)
+  h->ssd = t;
+  return COSL_OK;
+}
+
+int cosl_klt_group_first(cosl_klt* h, const uint8_t* const* imgs, size_t pitch,
+                         cosl_klt_feature* const* dest, int* nDetected) {
+  KLT_ENTER(h)
+  if (!imgs || pitch < (size_t)h->W) return set_error(COSL_E_INVALID, "group_first: bad argument");
+  COSL_TRY(upload_images(h, imgs, pitch, cudaMemcpyHostToDevice));
+  COSL_TRY(do_detect(h, 0));
+  COSL_TRY(advance(h));
+  COSL_TRY(fetch_results(h));
+  for (int c = 0; c < h->C; ++c) {
+    if (dest && dest[c]) copy_out(h, c, dest[c]);
+    if (nDetected) nDetected[c] = h->h_counters[8 * c + 2];
+  }
+  return COSL_OK;
+}
+
+int cosl_klt_group_next(cosl_klt* h, const uint8_t* const* imgs, size_t pitch,
+                        cosl_klt_feature* const* dest, int* nNew) {
+  KLT_ENTER(h)
+  if (!imgs || pitch < (size_t)h->W) return set_error(COSL_E_INVALID, "group_next: bad argument");
+  COSL_TRY(upload_images(h, imgs, pitch, cudaMemcpyHostToDevice));
+  COSL_TRY(do_redetect(h));
+  COSL_TRY(advance(h));
+  COSL_TRY(fetch_results(h));
+  for (int c = 0; c < h->C; ++c) {
+    if (dest && dest[c]) copy_out(h, c, dest[c]);
+    if (nNew) nNew[c] = h->h_counters[8 * c + 2];
+  }
+  return COSL_OK;
+}
+
+int cosl_klt_group_next_dev(cosl_klt* h, const uint8_t* const* dimgs, size_t pitch) {
+  KLT_ENTER(h)
+  if (!dimgs || pitch < (size_t)h->W)
+    return set_error(COSL_E_INVALID, "group_next_dev: bad argument");
+  COSL_TRY(upload_images(h, dimgs, pitch, cudaMemcpyDeviceToDevice));
+  COSL_TRY(do_redetect(h));
+  COSL_TRY(advance(h));
+  return COSL_OK;
+}
+
+int cosl_klt_group_fetch(cosl_klt* h, cosl_klt_feature* const* dest, int* nNew) {
+  KLT_ENTER(h)
+  COSL_TRY(fetch_results(h));
+  for (int c = 0; c < h->C; ++c) {
+    if (dest && dest[c]) copy_out(h, c, dest[c]);
+    if (nNew) nNew[c] = h->h_counters[8 * c + 2];
+  }
+  return COSL_OK;
+}
+
+int cosl_klt_group_sync(cosl_klt* h) {
+  KLT_ENTER(h)
+  COSL_CUDA(cudaStreamSynchronize(h->stream));
+  return COSL_OK;
+}
+
+void* cosl_klt_stream(cosl_klt* h) { return h ? (void*)h->stream : nullptr; }
+
+int cosl_klt_debug_pyramid(cosl_klt* h, int cam, int which, int level, float* out3, int* w,
+                           int* ht) {
+  KLT_ENTER(h)
+  if (cam < 0 || cam >= h->C || level < 0 || level >= h->L)
+    return set_error(COSL_E_INVALID, "debug_pyramid: bad argument");
+  const int lw = h->lvW[level], lh = h->lvH[level];
+  if (w) *w = lw;
+  if (ht) *ht = lh;
+  if (!out3) return COSL_OK;
+  std::vector<float4> tmp((size_t)lw * lh);
+  const float4* src =
+      h->d_pyr[which ? h->cur : 1 - h->cur] + (size_t)cam * h->pyrStride + h->lvOff[level];
+  COSL_CUDA(cudaStreamSynchronize(h->stream));
+  COSL_CUDA(cudaMemcpy(tmp.data(), src, sizeof(float4) * tmp.size(), cudaMemcpyDeviceToHost));
+  for (size_t i = 0; i < tmp.size(); ++i) {
+    out3[3 * i] = tmp[i].x;
+    out3[3 * i + 1] = tmp[i].y;
+    out3[3 * i + 2] = tmp[i].z;
+  }
+  return COSL_OK;
+}
+
+int cosl_klt_debug_cornerness(cosl_klt* h, int cam, float* out) {
+  KLT_ENTER(h)
+  if (cam < 0 || cam >= h->C || !out) return set_error(COSL_E_INVALID, "debug_cornerness");
+  COSL_CUDA(cudaStreamSynchronize(h->stream));
+  COSL_CUDA(cudaMemcpy(out, h->d_corn + (size_t)cam * h->W * h->H,
+                       sizeof(float) * (size_t)h->W * h->H, cudaMemcpyDeviceToHost));
+  return COSL_OK;
+}
+
+int cosl_klt_debug_num_candidates(cosl_klt* h, int cam) {
+  if (!h || cam < 0 || cam >= h->C) return -1;
+  return h->h_counters[8 * cam + 3];
+}
+
+double cosl_klt_algorithmic_bytes(cosl_klt* h) {
+  if (!h) return 0;
+  // B_frame = C * (25 W H + 4640 F); the 4640 B/feature generalise to
+  // n_lvl * 2 * (w+1)^2 * 12 + 32 for other window sizes / level sets
+  int nlv = 0;
+  for (int level = h->L - 1; level >= 0; level -= h->levelSkip) ++nlv;
+  const double w1 = 2 * h->halfWidth + 2;
+  double pyr = 1.0;
+  for (int l = 0; l < h->L; ++l) pyr += 12.0 / (double)(1 << (2 * l));
+  const double perFeat = nlv * 2.0 * w1 * w1 * 12.0 + 32.0;
+  return (double)h->C * ((pyr + 8.0) * h->W * h->H + perFeat * h->F);
+}
+
+int cosl_klt_profile_enable(cosl_klt* h, int on) {
+  KLT_ENTER(h)
+  COSL_CUDA(cudaStreamSynchronize(h->stream));
+  h->timer.reset();
+  h->timer.enabled = on != 0;
+  return COSL_OK;
+}
+
+const char* cosl_klt_profile_get(cosl_klt* h, int idx, double* ms, int* calls) {
+  if (!h || idx < 0 || idx >= h->timer.nsec) return nullptr;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  h->timer.flush();
+  if (ms) *ms = h->timer.ms[idx];
+  if (calls) *calls = h->timer.calls[idx];
+  return h->timer.names[idx];
+}
+
+}  // extern "C"

@@ -139,6 +139,13 @@ int cosl_klt_debug_pyramid(cosl_klt* h, int cam, int which, int level, float* ou
                            int* ht);
 /* Copy the cornerness map after non-max suppression input stage (W*H floats) of camera cam. */
 int cosl_klt_debug_cornerness(cosl_klt* h, int cam, float* out);
+/* Raw number of detector candidates of the last detect/redetect fetched to the host. */
+int cosl_klt_debug_num_candidates(cosl_klt* h, int cam);
+/* Per-kernel-class device time (CUDA events on the group's stream).  enable(1) resets and starts
+ * accumulating; get(idx) returns the class name ("klt_pyramid", "klt_track", "klt_detect",
+ * "klt_select") or NULL past the end. */
+int cosl_klt_profile_enable(cosl_klt* h, int on);
+const char* cosl_klt_profile_get(cosl_klt* h, int idx, double* ms, int* calls);
 /* Algorithmic HBM bytes of one group_next call (SURVEY.md 8d contract): C*(25*W*H + 4640*F). */
 double cosl_klt_algorithmic_bytes(cosl_klt* h);
 
@@ -262,6 +269,8 @@ void* cosl_ba_solver_stream(cosl_ba_solver* s);
 /* Per-kernel accumulated device time in ms since create/reset, by name (NULL-terminated list via
  * index): returns name or NULL when idx is out of range. */
 const char* cosl_ba_solver_timer(cosl_ba_solver* s, int idx, double* ms, int* calls);
+/* enable(1) resets and starts accumulating the per-kernel-class timers above. */
+int cosl_ba_solver_profile_enable(cosl_ba_solver* s, int on);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,35 @@
+"""Shared helpers of the parity tests."""
+import numpy as np
+
+from coslam_b200 import synth
+from coslam_b200.ctypes_defs import KltConfig
+
+
+def live_cfg(gain=True, min_corner=3000.0):
+    c = KltConfig.coslam_live(with_gain=gain)
+    c.minCornerness = min_corner
+    return c
+
+
+def seq(h, w, seed, n=4, **kw):
+    return synth.ImageSequence(h, w, seed, n_frames=n, **kw)
+
+
+def compare_features(fa, fb, W, H, pos_tol_px=2e-3, gain_tol=2e-3, max_flip_frac=0.01):
+    """Compare two cosl_klt_feature tables (oracle vs CUDA).  Returns dict of statistics and raises
+    on violation.  Status flips are allowed for a small fraction of slots (threshold decisions on
+    fp32 sums that are reduced in a different order on the GPU)."""
+    assert len(fa) == len(fb)
+    sa, sb = fa["status"], fb["status"]
+    flips = sa != sb
+    n = len(fa)
+    both = (~flips) & (sa >= 0)
+    d = np.abs(fa["pos"][both] - fb["pos"][both]) * np.array([W, H], np.float32)
+    dmax = float(d.max()) if d.size else 0.0
+    tr = (~flips) & (sa == 0)
+    gmax = float(np.abs(fa["gain"][tr] - fb["gain"][tr]).max()) if tr.any() else 0.0
+    stats = dict(n=n, flips=int(flips.sum()), pos_max_px=dmax, gain_max=gmax)
+    assert flips.sum() <= max(1, int(max_flip_frac * n)), stats
+    assert dmax <= pos_tol_px, stats
+    assert gmax <= gain_tol, stats
+    return stats

@@ -1,0 +1,145 @@
+"""CUDA KLT path vs the CPU oracle, through the C-ABI (needs a GPU)."""
+import numpy as np
+import pytest
+
+from helpers import compare_features, live_cfg, seq
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(api, orc, cfg, W, H, L, fw, fh):
+    return api.KltTracker(cfg, W, H, L, fw, fh), orc.OracleKlt(cfg, W, H, L, fw, fh)
+
+
+@pytest.mark.parametrize("W,H,L", [(640, 480, 6), (328, 250, 4), (1280, 720, 6)])
+def test_pyramid_bit_exact(api, orc, W, H, L):
+    s = seq(H, W, 11, n=1)
+    g, o = _pair(api, orc, live_cfg(), W, H, L, 16, 16)
+    g.detect(s.frames[0])
+    o.detect(s.frames[0])
+    for l in range(L):
+        a, b = g.pyramid(1, l), o.pyramid(1, l)
+        assert a.shape == b.shape
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"level {l} differs"
+
+
+@pytest.mark.parametrize("W,H", [(640, 480), (328, 250)])
+def test_cornerness_and_detection_exact(api, orc, W, H):
+    s = seq(H, W, 5, n=1)
+    g, o = _pair(api, orc, live_cfg(min_corner=1500.0), W, H, 4, 32, 32)
+    fg, ng = g.detect(s.frames[0])
+    fo, no = o.detect(s.frames[0])
+    assert np.array_equal(g.cornerness().view(np.uint32), o.cornerness().view(np.uint32))
+    assert ng == no and g.num_candidates() == o.num_candidates()
+    # same corners in the same (deterministic strongest-first) slot order, bit for bit
+    assert np.array_equal(fg["status"], fo["status"])
+    assert np.array_equal(fg["pos"].view(np.uint32), fo["pos"].view(np.uint32))
+    assert np.array_equal(fg["fed"], fo["fed"])
+
+
+def test_detect_with_present_points(api, orc):
+    W, H = 640, 480
+    s = seq(H, W, 6, n=1)
+    g, o = _pair(api, orc, live_cfg(min_corner=1500.0), W, H, 3, 32, 32)
+    rng = np.random.default_rng(0)
+    pres = np.zeros((40, 3), np.float32)
+    pres[:, 0] = rng.uniform(0.05, 0.95, 40)
+    pres[:, 1] = rng.uniform(0.05, 0.95, 40)
+    fg, ng = g.detect(s.frames[0], pres)
+    fo, no = o.detect(s.frames[0], pres)
+    assert ng == no
+    assert np.array_equal(fg["status"], fo["status"])
+    assert np.array_equal(fg["fed"], fo["fed"])
+    assert np.array_equal(fg["pos"].view(np.uint32), fo["pos"].view(np.uint32))
+
+
+@pytest.mark.parametrize("gain", [True, False])
+@pytest.mark.parametrize("W,H,fw,fh", [(640, 480, 32, 32), (328, 250, 20, 12)])
+def test_sequence_parity(api, orc, gain, W, H, fw, fh):
+    """GPUKLT::first + 3 x GPUKLT::next on a synthetic sequence: slot-for-slot parity."""
+    s = seq(H, W, 21, n=4)
+    cfg = live_cfg(gain=gain, min_corner=1500.0)
+    g, o = _pair(api, orc, cfg, W, H, 6 if W >= 640 else 4, fw, fh)
+    fg, ng = g.first(s.frames[0])
+    fo, no = o.first(s.frames[0])
+    assert ng == no
+    assert np.array_equal(fg["pos"].view(np.uint32), fo["pos"].view(np.uint32))
+    for k in range(1, 4):
+        fg, ng = g.next(s.frames[k])
+        fo, no = o.next(s.frames[k])
+        st = compare_features(fo, fg, W, H)
+        assert abs(ng - no) <= max(2, st["flips"] * 2), (ng, no, st)
+        assert (fo["status"] == 0).sum() > 0.5 * (fo["status"] >= 0).sum()
+
+
+def test_track_only_cadence_and_feed(api, orc):
+    W, H = 640, 480
+    s = seq(H, W, 22, n=3)
+    cfg = live_cfg(gain=True, min_corner=1500.0)
+    g, o = _pair(api, orc, cfg, W, H, 6, 32, 32)
+    g.first(s.frames[0])
+    o.first(s.frames[0])
+    fg, ng = g.track(s.frames[1])
+    fo, no = o.track(s.frames[1])
+    compare_features(fo, fg, W, H)
+    g.advance()
+    o.advance()
+    # feed external points (GPUKLT::feedExternFeatPoints, tracking/GPUKLT.cpp:163-190)
+    pts = np.zeros((7, 3), np.float32)
+    pts[:, 0] = np.linspace(0.2, 0.8, 7)
+    pts[:, 1] = 0.5
+    live = fo[fo["status"] >= 0]
+    pts[0, :2] = live["pos"][0]  # forces one KLT point to be killed and replaced
+    ig, kg = g.feed(pts)
+    io, ko = o.feed(pts)
+    assert kg == ko and np.array_equal(ig[:kg], io[:ko])
+    g.advance()
+    o.advance()
+    fg, ng = g.track(s.frames[2])
+    fo, no = o.track(s.frames[2])
+    compare_features(fo, fg, W, H, max_flip_frac=0.02)
+
+
+def test_group_matches_single(api):
+    W, H = 640, 480
+    cfg = live_cfg(min_corner=1500.0)
+    seqs = [seq(H, W, 30 + c, n=3) for c in range(3)]
+    grp = api.KltGroup(cfg, 3, W, H, 6, 32, 32)
+    singles = [api.KltTracker(cfg, W, H, 6, 32, 32) for _ in range(3)]
+    f, n = grp.first([s.frames[0] for s in seqs])
+    for c in range(3):
+        fs, ns = singles[c].first(seqs[c].frames[0])
+        assert ns == n[c] and np.array_equal(fs["pos"], f[c]["pos"])
+    for k in (1, 2):
+        f, n = grp.next([s.frames[k] for s in seqs])
+        for c in range(3):
+            fs, ns = singles[c].next(seqs[c].frames[k])
+            assert ns == n[c]
+            assert np.array_equal(fs["status"], f[c]["status"])
+            assert np.array_equal(fs["pos"].view(np.uint32), f[c]["pos"].view(np.uint32))
+
+
+def test_full_size_known_answer_flow(api):
+    """BASELINE c3 shape (4 x 1280x720, F=2000): tracked features follow the known synthetic flow."""
+    W, H, F = 1280, 720, (50, 40)
+    cfg = live_cfg(min_corner=1500.0)
+    seqs = [seq(H, W, 40 + c, n=3) for c in range(4)]
+    grp = api.KltGroup(cfg, 4, W, H, 6, *F)
+    f0, n0 = grp.first([s.frames[0] for s in seqs])
+    f0 = f0.copy()
+    assert (n0 >= 1500).all(), n0
+    f1, n1 = grp.next([s.frames[1] for s in seqs])
+    for c in range(4):
+        tr = f1[c]["status"] == 0
+        assert tr.sum() > 0.8 * n0[c]
+        x0 = f0[c]["pos"][tr] * [W, H]
+        x1 = f1[c]["pos"][tr] * [W, H]
+        gx, gy = seqs[c].flow_truth(0, 1, x0[:, 0], x0[:, 1])
+        err = np.hypot(x1[:, 0] - gx, x1[:, 1] - gy)
+        assert np.median(err) < 0.15, np.median(err)
+        # min-distance property of the refilled set: new corners keep > minDistance from live tracks
+        new = f1[c]["status"] == 1
+        if new.any() and tr.any():
+            pn = f1[c]["pos"][new] * [W, H]
+            d = np.abs(pn[:, None, :] - x1[None, :, :]).max(-1).min(1)
+            assert d.min() > cfg.minDistance - 1.0
