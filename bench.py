@@ -1,0 +1,459 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of coslam_b200 (contract: see DESIGN.md "Measurement").
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle) timed
+                                                           # on the host cores, rank 0 only
+
+Primary line  : KLT features/s on BASELINE config c3 (4 cameras 1280x720, 2000 feature slots per
+                camera, CoSLAM's live tracker settings: 3x3 gain tracker, levels 5/3/1 x 12
+                iterations, re-detection every frame).  One step = GPUKLT::next for all 4 cameras.
+                N GPUs = N independent replicas (the path does not shard) -> "weak".
+Nested "ba"   : BA LM-iterations/s on BASELINE config c4 (4 cams x 200 key frames x 50 k points),
+                points sharded over the N GPUs, one NCCL all-reduce of the reduced camera system
+                per LM trial -> "strong".
+One JSON line on stdout (rank 0)."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+KLT_W, KLT_H, KLT_C, KLT_FW, KLT_FH, KLT_L = 1280, 720, 4, 50, 40, 6
+KLT_FRAMES = 8
+BA_CAMS, BA_KF, BA_PTS = 4, 200, 50000
+FP64_NOMINAL_TFLOPS = 40.0  # B200 FP64 (nominal; MEASURED_PEAKS.json has no fp64 entry)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
+                 "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip().split(", "))
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for k, nm in enumerate(names):
+                    if r[5 + k].strip().lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def make_sequences(rank):
+    from coslam_b200 import synth
+    return [synth.ImageSequence(KLT_H, KLT_W, synth.BASE_SEED + 2 + 17 * rank + c,
+                                n_frames=KLT_FRAMES) for c in range(KLT_C)]
+
+
+def klt_cfg():
+    from coslam_b200.ctypes_defs import KltConfig
+    return KltConfig.coslam_live(with_gain=True)
+
+
+# =================================================================== reference arm (CPU oracle)
+def run_reference(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    from coslam_b200 import synth
+    from coslam_b200.ctypes_defs import BaOptions
+    from oracle import orc
+    cores = orc.max_threads()
+    orc.set_threads(cores)
+    cfg = klt_cfg()
+    seqs = make_sequences(0)
+    trk = [orc.OracleKlt(cfg, KLT_W, KLT_H, KLT_L, KLT_FW, KLT_FH) for _ in range(KLT_C)]
+    for c in range(KLT_C):
+        trk[c].first(seqs[c].frame(0))
+    steps = max(1, min(args.steps, 12))
+    warm = max(1, min(args.warmup, 2))
+    i = 1
+    for _ in range(warm):
+        for c in range(KLT_C):
+            trk[c].next(seqs[c].frame(i))
+        i += 1
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        for c in range(KLT_C):
+            trk[c].next(seqs[c].frame(i))
+        i += 1
+    dt = time.perf_counter() - t0
+    val = KLT_C * KLT_FW * KLT_FH * steps / dt
+    # BA c4 on the host cores: a bounded number of LM trials
+    prob, _ = synth.make_ba_scene(BA_CAMS, BA_KF, BA_PTS, KLT_W, KLT_H, seed=synth.BASE_SEED + 4,
+                                  m_con=BA_CAMS, n_con=0)
+    opt = BaOptions.defaults()
+    ntr = 3
+    p = prob.copy()
+    tb = time.perf_counter()
+    info = orc.ba_run_fixed(p, opt, ntr)
+    ba_dt = time.perf_counter() - tb
+    ba_val = info[9] / info[11] if info[11] > 0 else 0.0
+    sample = f"{steps} frames x {KLT_C} cameras of the c3 sequence"
+    line = {
+        "impl": "reference", "metric": "klt_features_per_s", "value": val, "unit": "features/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": 1e3 * dt / steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": "c3: 4 cams 1280x720, 2000 feature slots/cam, KLT next() "
+                               "(pyramid + 3x3 gain LK levels 5/3/1 x 12 it + re-detect)"},
+        "cpu_baseline": {"value": val, "unit": "features/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": val, "unit": "features/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "ba": {"metric": "ba_lm_iters_per_s", "value": ba_val, "unit": "LM-iter/s",
+               "config": {"workload": f"c4: {prob.m} poses, {prob.n} points, {prob.nobs} obs"},
+               "cpu_baseline": {"value": ba_val, "unit": "LM-iter/s", "cores": cores,
+                                "kind": "port", "sample": f"{int(info[9])} LM trials, "
+                                f"{ba_dt:.1f} s incl. setup"},
+               "e2e": {"value": info[9] / ba_dt, "unit": "LM-iter/s", "h2d_bytes_per_step": 0,
+                       "d2h_bytes_per_step": 0}},
+    }
+    print(json.dumps(line))
+
+
+# =================================================================== CUDA arm
+def run_cuda(args):
+    import torch
+    rank, world, local = dist_env()
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from coslam_b200 import api, synth
+    from coslam_b200.ctypes_defs import BaOptions
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    hbm_peak, peak_src = peaks()
+    cfg = klt_cfg()
+    F = KLT_FW * KLT_FH
+    # ------------------------------------------------------------------ KLT (c3), one replica/rank
+    seqs = make_sequences(rank)
+    grp = api.KltGroup(cfg, KLT_C, KLT_W, KLT_H, KLT_L, KLT_FW, KLT_FH, device=local)
+    stream = torch.cuda.ExternalStream(grp.stream(), device=local)
+    host = [[torch.from_numpy(seqs[c].frames[k]).pin_memory() for c in range(KLT_C)]
+            for k in range(KLT_FRAMES)]
+    dev = [[h.cuda() for h in row] for row in host]
+    torch.cuda.synchronize()
+
+    def fidx(i):
+        return seqs[0].frame_index(i)
+
+    feats, n0 = grp.first([host[0][c].numpy() for c in range(KLT_C)])
+    n_detected = [int(v) for v in n0]
+    K, Wm = args.steps, max(3, args.warmup)
+    i = 1
+    for _ in range(Wm):
+        grp.next_dev([t.data_ptr() for t in dev[fidx(i)]], KLT_W)
+        i += 1
+    grp.sync()
+    # ---- value: frames resident in HBM, no host transfer, device-timed on the launching stream
+    clocks = ClockSampler(local)
+    clocks.start()
+    barrier()
+    launches0 = api.kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        grp.next_dev([t.data_ptr() for t in dev[fidx(i)]], KLT_W)
+        i += 1
+    e1.record(stream)
+    grp.sync()
+    barrier()
+    gpu_launches = api.kernel_launch_count() - launches0
+    ms_val = max_over_ranks(e0.elapsed_time(e1))
+    clk = clocks.stop()
+    feats, cnt = grp.fetch()
+    tracked_frac = float(np.mean([(feats[c]["status"] == 0).mean() for c in range(KLT_C)]))
+    # ---- roofline: second pass of the same region with per-kernel-class CUDA events
+    grp.profile_enable(True)
+    for _ in range(K):
+        grp.next_dev([t.data_ptr() for t in dev[fidx(i)]], KLT_W)
+        i += 1
+    grp.sync()
+    prof = grp.profile()
+    grp.profile_enable(False)
+    px = KLT_C * KLT_W * KLT_H
+    alg = {"klt_pyramid": 17.0 * px, "klt_track": 4640.0 * KLT_C * F,
+           "klt_detect": 8.0 * px + 48.0 * KLT_C * F, "klt_select": 48.0 * KLT_C * F}
+    top = max(prof, key=lambda k: prof[k][0])
+    top_ms = prof[top][0] / max(1, prof[top][1])
+    achieved = alg[top] / (top_ms * 1e-3) / 1e9
+    roof = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_step": alg[top], "avg_ms_per_step": top_ms,
+            "share_of_step": {k: v[0] / max(1e-9, sum(x[0] for x in prof.values()))
+                              for k, v in prof.items()},
+            "frame_total": {"algorithmic_bytes": grp.algorithmic_bytes(),
+                            "achieved": grp.algorithmic_bytes() / (ms_val / K * 1e-3) / 1e9,
+                            "frac": grp.algorithmic_bytes() / (ms_val / K * 1e-3) / 1e9 / hbm_peak}}
+    # ---- e2e: host buffers through the public C-ABI call, H2D + D2H inside the timed region
+    for _ in range(3):
+        grp.next([h.numpy() for h in host[fidx(i)]])
+        i += 1
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall = time.perf_counter()
+    e2.record(stream)
+    for _ in range(K):
+        grp.next([h.numpy() for h in host[fidx(i)]])
+        i += 1
+    e3.record(stream)
+    grp.sync()
+    wall = time.perf_counter() - t_wall
+    ms_e2e = max_over_ranks(max(e2.elapsed_time(e3), wall * 1e3))
+    barrier()
+    klt_value = world * KLT_C * F * K / (ms_val * 1e-3)
+    klt_e2e = world * KLT_C * F * K / (ms_e2e * 1e-3)
+
+    # ------------------------------------------------------------------ BA (c4), sharded
+    ba = run_ba(args, api, synth, BaOptions, torch, dist, rank, world, local, barrier,
+                max_over_ranks)
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = cpu_baseline_klt(cfg, seqs)
+    if rank == 0:
+        line = {
+            "metric": "klt_features_per_s", "value": klt_value, "unit": "features/s",
+            "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": ms_val / K,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "c3: 4 cams 1280x720, 2000 feature slots/cam, KLT next() "
+                                   "(pyramid + 3x3 gain LK levels 5/3/1 x 12 it + re-detect)",
+                       "replicas": world, "frames": f"{KLT_FRAMES}-frame ping-pong sequence/cam",
+                       "l2": "working set (2 pyramids + cornerness + images, ~190 MB/replica) "
+                             "exceeds the 126 MB L2; no explicit flush",
+                       "detected_at_frame0": n_detected, "tracked_fraction": tracked_frac},
+            "e2e": {"value": klt_e2e, "unit": "features/s",
+                    "h2d_bytes_per_step": KLT_C * KLT_W * KLT_H,
+                    "d2h_bytes_per_step": KLT_C * F * 20 + KLT_C * 32,
+                    "ms_per_step": ms_e2e / K},
+            "gpu_launches": int(gpu_launches),
+            "clocks": clk, "roofline": roof,
+            "fps_4cam": K / (ms_e2e * 1e-3),
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        if ba is not None:
+            line["ba"] = ba
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline_klt(cfg, seqs):
+    from oracle import orc
+    cores = orc.max_threads()
+    orc.set_threads(cores)
+    trk = [orc.OracleKlt(cfg, KLT_W, KLT_H, KLT_L, KLT_FW, KLT_FH) for _ in range(KLT_C)]
+    for c in range(KLT_C):
+        trk[c].first(seqs[c].frame(0))
+    nfr = 6
+    t0 = time.perf_counter()
+    for k in range(1, 1 + nfr):
+        for c in range(KLT_C):
+            trk[c].next(seqs[c].frame(k))
+    dt = time.perf_counter() - t0
+    return {"value": KLT_C * KLT_FW * KLT_FH * nfr / dt, "unit": "features/s", "cores": cores,
+            "kind": "port", "sample": f"{nfr} frames x {KLT_C} cameras of the same c3 sequence",
+            "ms_per_step": 1e3 * dt / nfr}
+
+
+def run_ba(args, api, synth, BaOptions, torch, dist, rank, world, local, barrier, max_over_ranks):
+    prob, truth = synth.make_ba_scene(BA_CAMS, BA_KF, BA_PTS, KLT_W, KLT_H,
+                                      seed=synth.BASE_SEED + 4, m_con=BA_CAMS, n_con=0)
+    opt = BaOptions.defaults()
+    opt.device = local
+    comm = None
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid.copy_(torch.from_numpy(api.nccl_unique_id()))
+        dist.broadcast(uid, 0)
+        comm = api.BaComm(uid.cpu().numpy(), rank, world, local)
+        shard, (lo, hi) = prob.shard(rank, world)
+    else:
+        shard = prob
+    t_setup = time.perf_counter()
+    solver = api.BaSolver(shard, opt, comm)
+    setup_s = time.perf_counter() - t_setup
+    stream = torch.cuda.ExternalStream(solver.stream(), device=local)
+    K = max(4, min(args.steps, 20))
+    Wm = 3
+    solver.run_fixed(Wm)
+    solver.reset()
+    barrier()
+    launches0 = api.kernel_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    t0 = time.perf_counter()
+    info = solver.run_fixed(K)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = max_over_ranks(max(e0.elapsed_time(e1), wall * 1e3))
+    launches = api.kernel_launch_count() - launches0
+    trials = int(info[9])
+    # per-kernel-class shares and the roofline of the dominant one
+    solver.reset()
+    solver.profile_enable(True)
+    solver.run_fixed(K)
+    tm = solver.timers()
+    solver.profile_enable(False)
+    tot = sum(v[0] for v in tm.values())
+    top = max(tm, key=lambda k: tm[k][0])
+    ns = 6 * (prob.m - prob.m_con)
+    top_ms = tm[top][0] / max(1, trials)
+    kk = np.diff(prob.ptr).astype(np.float64)
+    if top == "ba_solve":
+        flops = ns ** 3 / 3.0
+        roof = {"bound": "tensor", "kernel": "ba_solve (blocked fp64 Cholesky + trsv)",
+                "achieved": flops / (top_ms * 1e-3) / 1e12, "peak": FP64_NOMINAL_TFLOPS,
+                "unit": "TFLOP/s", "frac": flops / (top_ms * 1e-3) / 1e12 / FP64_NOMINAL_TFLOPS,
+                "traffic": None, "peak_source": "nominal fp64 (not in MEASURED_PEAKS.json)",
+                "algorithmic_flops_per_trial": flops}
+    else:
+        hbm_peak, src = peaks()
+        byts = {"ba_schur": 216.0 * 0.0 + 8.0 * (ns * (ns + 1) / 2) + 144.0 * prob.nobs,
+                "ba_linearize": 24.0 * prob.nobs + 24.0 * prob.n,
+                "ba_backsub": 8.0 * prob.nobs + 48.0 * prob.n, "ba_cost": 24.0 * prob.nobs,
+                "ba_allreduce": 8.0 * ns * ns}.get(top, 0.0) / world
+        roof = {"bound": "hbm", "kernel": top, "achieved": byts / (top_ms * 1e-3) / 1e9,
+                "peak": hbm_peak, "unit": "GB/s", "frac": byts / (top_ms * 1e-3) / 1e9 / hbm_peak,
+                "traffic": None, "peak_source": src}
+    roof["share_of_trial"] = {k: v[0] / max(tot, 1e-9) for k, v in tm.items()}
+    roof["avg_ms_per_trial"] = top_ms
+    # e2e: the drop-in call with host buffers (upload + index build + solve + download)
+    e2e = None
+    if world == 1:
+        p2 = prob.copy()
+        o2 = BaOptions.defaults()
+        o2.device = local
+        o2.max_err, o2.outer_iters, o2.inner_iters = 6.0, 1, 10
+        t0 = time.perf_counter()
+        inf2 = api.ba_solve(p2, o2)
+        dt = time.perf_counter() - t0
+        h2d = prob.nobs * (8 * 2 + 4 + 4) + prob.n * 24 + prob.m * 8 * 21
+        e2e = {"value": inf2[9] / dt, "unit": "LM-iter/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(prob.n * 24 + prob.m * 48 + prob.nobs),
+               "call": "cosl_ba_solve (1 robust round x 10 LM iterations, host arrays in/out)",
+               "seconds": dt, "lm_trials": int(inf2[9]), "rms_after": p2.rms(~truth["is_outlier"])}
+    out = {"metric": "ba_lm_iters_per_s", "value": trials / (ms * 1e-3), "unit": "LM-iter/s",
+           "scaling": "strong", "ms_per_trial": ms / max(1, trials), "lm_trials": trials,
+           "gpu_launches": int(launches), "setup_s": setup_s,
+           "config": {"workload": f"c4: {prob.m} poses ({prob.m_con} fixed), {prob.n} points, "
+                                  f"{prob.nobs} obs, reduced system {ns}x{ns} fp64",
+                      "sum_k2": float((kk * kk).sum()), "shards": world},
+           "roofline": roof}
+    if e2e is not None:
+        out["e2e"] = e2e
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import orc
+        cores = orc.max_threads()
+        orc.set_threads(cores)
+        p3 = prob.copy()
+        i3 = orc.ba_run_fixed(p3, opt, 3)
+        out["cpu_baseline"] = {"value": i3[9] / i3[11], "unit": "LM-iter/s", "cores": cores,
+                               "kind": "port", "sample": f"{int(i3[9])} LM trials of the same c4 "
+                               "problem (OpenMP + OpenBLAS dpotrf)"}
+        # parity at full size: same trial count -> same cost
+        solver.reset()
+        ig = solver.run_fixed(3)
+        out["parity_rel_cost_diff_3_trials"] = abs(ig[1] - i3[1]) / i3[1]
+    solver.close()
+    if comm is not None:
+        comm.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -369,7 +369,8 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   // small systems are factored inside one CTA (ns*ns doubles of shared memory)
   const size_t smallBytes = sizeof(double) * (size_t)s->ns * s->ns;
   s->smallSolve = (smallBytes <= 200 * 1024) && s->ns <= 1024;
-  if (s->smallSolve && smallBytes > 48 * 1024)
+  // (the kernel also has ~8 KB of static shared memory, so opt in well below the 48 KB default)
+  if (s->smallSolve && smallBytes > 32 * 1024)
     COSL_CUDA(cudaFuncSetAttribute(ba_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smallBytes));
   s->secLin = s->timer.section("ba_linearize");
