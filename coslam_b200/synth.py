@@ -204,7 +204,7 @@ def make_ba_scene(n_cams=4, n_kf=5, n_pts=20000, width=1280, height=720, seed=BA
         m_con = n_cams
     R0 = Rs.copy()
     t0 = ts.copy()
-    base = step * max(1, n_kf - 1)
+    base = step  # inter-key-frame baseline
     for j in range(m_con, m):
         dR = _rodrigues(rng.normal(0, np.deg2rad(pose_rot_deg) / np.sqrt(3), 3))
         Cj = Cs[j] + rng.normal(0, pose_trans_frac * max(base, 1.0) / np.sqrt(3), 3)
