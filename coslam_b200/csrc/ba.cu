@@ -93,6 +93,11 @@ struct cosl_ba_solver {
   long long nEntries = 0;
   double* h_sc = nullptr;  // pinned
   bool smallSolve = true;
+  // block envelope (skyline) of the reduced camera system for the blocked factorisation: block row
+  // I has its first structurally non-zero block column at firstBlk[I]; panel k only touches block
+  // rows (k, lastBlk[k]].  Dense co-visibility gives firstBlk == 0 everywhere (== dense algorithm).
+  std::vector<int> firstBlk, lastBlk;
+  cudaGraphExec_t solveGraph = nullptr;
   SectionTimer timer;
   int secLin = 0, secSchur = 0, secSolve = 0, secBack = 0, secCost = 0, secComm = 0;
   // statistics

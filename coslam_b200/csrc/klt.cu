@@ -43,6 +43,13 @@ struct cosl_klt {
   int* h_counters = nullptr;
   float4* h_present = nullptr;
   bool havePrev = false;
+  // persistent fused gain tracker (klt_gain_fused)
+  float4* d_state = nullptr;  // [2][C*F]
+  int* d_ver = nullptr;       // [2][C*F]
+  int* d_waitset = nullptr;   // [F][16]
+  bool fusedOK = false;
+  int fusedBlocks = 0;
+  int verBase = 0;
   SectionTimer timer;
   int secPyr = 0, secTrack = 0, secDetect = 0, secSelect = 0;
 };
@@ -107,6 +114,42 @@ int alloc_group(cosl_klt* g) {
     }
   COSL_CUDA(cudaMalloc(&g->d_nbr, sizeof(int) * nbr.size()));
   COSL_CUDA(cudaMemcpy(g->d_nbr, nbr.data(), sizeof(int) * nbr.size(), cudaMemcpyHostToDevice));
+  // wait sets of the persistent gain tracker: 8 neighbours + up to 8 reverse neighbours (slots
+  // that read this slot but are not among its neighbours are enough; duplicates are harmless)
+  {
+    std::vector<int> ws((size_t)F * 16, -1);
+    std::vector<int> nrev(F, 0);
+    bool ok = true;
+    for (int i = 0; i < F; ++i)
+      for (int k = 0; k < 8; ++k) ws[(size_t)i * 16 + k] = nbr[(size_t)i * 8 + k];
+    for (int i = 0; i < F && ok; ++i)
+      for (int k = 0; k < 8 && ok; ++k) {
+        const int j = nbr[(size_t)i * 8 + k];  // i reads j  ->  j must wait for i
+        bool have = false;
+        for (int q = 0; q < 8 + nrev[j]; ++q)
+          if (ws[(size_t)j * 16 + q] == i) have = true;
+        if (have) continue;
+        if (nrev[j] >= 8) {
+          ok = false;
+          break;
+        }
+        ws[(size_t)j * 16 + 8 + nrev[j]++] = i;
+      }
+    int dev = 0, coop = 0, nsm = 0, perSM = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, klt_gain_fused, 256, 0);
+    g->fusedOK = ok && coop && perSM > 0 && !(g->cfg.compat & COSL_KLT_PASS_KERNELS);
+    const int T = F * C;
+    g->fusedBlocks = std::max(1, std::min(div_up(T, 8), nsm * perSM));
+    COSL_CUDA(cudaMalloc(&g->d_waitset, sizeof(int) * ws.size()));
+    COSL_CUDA(cudaMemcpy(g->d_waitset, ws.data(), sizeof(int) * ws.size(), cudaMemcpyHostToDevice));
+    COSL_CUDA(cudaMalloc(&g->d_state, sizeof(float4) * 2 * (size_t)T));
+    COSL_CUDA(cudaMalloc(&g->d_ver, sizeof(int) * 2 * (size_t)T));
+    COSL_CUDA(cudaMemset(g->d_ver, 0, sizeof(int) * 2 * (size_t)T));
+    g->verBase = 0;
+  }
   // dynamic shared memory opt-ins
   COSL_CUDA(cudaFuncSetAttribute(klt_select_refill, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  g->smemKeys * (int)sizeof(unsigned long long)));
@@ -144,6 +187,9 @@ void free_group(cosl_klt* g) {
   cudaFree(g->d_feat);
   cudaFree(g->d_feedpts);
   cudaFree(g->d_feedids);
+  cudaFree(g->d_state);
+  cudaFree(g->d_ver);
+  cudaFree(g->d_waitset);
   cudaFreeHost(g->h_feat);
   cudaFreeHost(g->h_counters);
   cudaFreeHost(g->h_present);
@@ -212,7 +258,35 @@ int run_tracker(cosl_klt* g) {
   const int wpb = 8;  // warps per block
   dim3 grid(div_up(g->F, wpb), g->C);
   g->timer.begin(g->secTrack, g->stream);
-  if (g->cfg.trackWithGain) {
+  if (g->cfg.trackWithGain && g->fusedOK) {
+    KltLevels LV;
+    LV.n = 0;
+    for (int level = g->L - 1; level >= 0; level -= g->levelSkip) {
+      LV.level[LV.n] = level;
+      LV.w[LV.n] = g->lvW[level];
+      LV.h[LV.n] = g->lvH[level];
+      LV.off[LV.n] = g->lvOff[level];
+      LV.mult[LV.n] = 1.0f;
+      ++LV.n;
+    }
+    int nIter = g->cfg.nIterations, C = g->C;
+    const int nPass = LV.n * nIter;
+    if (g->verBase > 2000000000 - 2 * nPass) {  // version wrap: restart the counters
+      COSL_CUDA(cudaMemsetAsync(g->d_ver, 0, sizeof(int) * 2 * (size_t)g->F * g->C, g->stream));
+      g->verBase = 0;
+    }
+    long long pyrStride = g->pyrStride;
+    KltTrackParams Plax = track_params(g, false), Pstrict = track_params(g, true);
+    int verBase = g->verBase;
+    void* args[] = {(void*)&P0,          (void*)&P1,     (void*)&pyrStride, (void*)&LV,
+                    (void*)&nIter,       (void*)&g->d_src, (void*)&g->d_state, (void*)&g->d_ver,
+                    (void*)&g->d_waitset, (void*)&g->d_res, (void*)&C,        (void*)&Plax,
+                    (void*)&Pstrict,     (void*)&verBase};
+    COSL_CUDA(cudaLaunchCooperativeKernel((const void*)klt_gain_fused, dim3(g->fusedBlocks),
+                                          dim3(256), args, 0, g->stream));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    g->verBase += nPass;
+  } else if (g->cfg.trackWithGain) {
     const float4* in = g->d_src;
     float4* bufs[2] = {g->d_ping, g->d_pong};
     int which = 0, first = 1;

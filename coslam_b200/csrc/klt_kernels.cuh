@@ -284,10 +284,6 @@ klt_gain_pass(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1, 
   if (lane == 0) out[fb + slot] = res;
 }
 
-// ------------------------------------------------------------------------------------------
-// 2x2 LK (klt_tracker.cg:24-132): all levels and iterations inside one kernel, one warp per
-// feature.  Output (X1.x, X1.y, X0.x) or -1.
-// ------------------------------------------------------------------------------------------
 struct KltLevels {
   int n;             // number of levels visited
   int level[8];
@@ -295,6 +291,105 @@ struct KltLevels {
   long long off[8];
   float mult[8];
 };
+
+// ------------------------------------------------------------------------------------------
+// All passes of the gain tracker in ONE persistent cooperative kernel (replaces the reference's
+// levels x iterations draw calls, v3d_gpuklt.cpp:254-295, without changing the pass-synchronous
+// semantics).  The only coupling between feature slots is the gain-smoothness term, which reads
+// the beta of <= 8 neighbour slots produced by the PREVIOUS pass.  Instead of a grid-wide barrier
+// per pass, every slot publishes (x, y, beta) of pass p into a parity double buffer followed by a
+// version number; a slot starts pass p as soon as the slots it reads from have published p-1.  A
+// slot may overwrite its pass p-1 record (when publishing p+1) only after all slots that read it
+// have consumed it, which is guaranteed because it waits for the pass-p record of its readers too
+// (wait set = neighbours + reverse neighbours, symmetric closure built on the host).
+// Work item = (camera, slot); warp w owns items w, w+G, ... and walks the passes in order, so the
+// globally least advanced item can always run: no deadlock as long as all warps are co-resident
+// (cooperative launch).
+//   state[2][T] float4 (x, y, beta, -), ver[2][T] int (pass number of the record)
+//   waitset[F][16]: first 8 = neighbours (values + versions), last 8 = reverse neighbours or -1
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int ld_volatile_int(const int* p) {
+  int v;
+  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
+               long long pyrStride, KltLevels LV, int nIter, const float4* __restrict__ X0buf,
+               float4* __restrict__ state, int* __restrict__ ver, const int* __restrict__ waitset,
+               float4* __restrict__ out, int C, KltTrackParams Plax, KltTrackParams Pstrict,
+               int verBase) {
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int G = gridDim.x * (blockDim.x >> 5);
+  const int F = Plax.F;
+  const int T = C * F;
+  const int nPass = LV.n * nIter;
+  for (int pass = 1; pass <= nPass; ++pass) {
+    const int li = (pass - 1) / nIter, it = (pass - 1) - li * nIter + 1;
+    const int w = LV.w[li], h = LV.h[li];
+    const float dsx = 1.0f / (float)w, dsy = 1.0f / (float)h;
+    // thresholds are lax except on the last iteration of each level (v3d_gpuklt.cpp:266-279)
+    const bool strict = (it == nIter) && (it != 1);
+    const int rd = (pass - 1) & 1, wr = pass & 1;
+    for (int item = warp; item < T; item += G) {
+      const int cam = item / F, slot = item - cam * F;
+      const float4* L0 = pyr0 + (size_t)cam * pyrStride + LV.off[li];
+      const float4* L1 = pyr1 + (size_t)cam * pyrStride + LV.off[li];
+      const float4 x0 = X0buf[item];
+      float4 cur;
+      float bn = 0.f;
+      if (pass == 1) {
+        cur = make_float4(x0.x, x0.y, 1.0f, 0.f);  // X1 <- X0, gain cleared to 1 (:223-227)
+        if (lane < 8) bn = 1.0f;
+      } else {
+        // wait for the pass-(p-1) records of everything this slot reads or is read by
+        if (lane < 16) {
+          const int nb = waitset[slot * 16 + lane];
+          if (nb >= 0) {
+            const int* vp = ver + (size_t)rd * T + (size_t)cam * F + nb;
+            const int need = verBase + pass - 1;
+            while (ld_volatile_int(vp) < need) __nanosleep(20);
+          }
+        }
+        __syncwarp();
+        __threadfence();
+        cur = __ldcg(&state[(size_t)rd * T + item]);
+        if (lane < 8) {
+          const int nb = waitset[slot * 16 + lane];
+          bn = __ldcg(&state[(size_t)rd * T + (size_t)cam * F + nb]).z;
+        }
+      }
+      const float beta = cur.z;
+      if (lane < 8) bn = (bn < 0.f) ? beta : bn;
+      const float hi = __shfl_sync(0xffffffffu, bn, (lane & 3) + 4);
+      const float s4 = bn + hi - 2.0f * beta;
+      const float s0 = __shfl_sync(0xffffffffu, s4, 0), s1 = __shfl_sync(0xffffffffu, s4, 1);
+      const float s2 = __shfl_sync(0xffffffffu, s4, 2), s3 = __shfl_sync(0xffffffffu, s4, 3);
+      const float nbterm = ((s0 + s1) + s2) + s3;
+      const bool pre_invalid = (cur.x < 0.f) || (x0.x < 0.f);
+      float4 res = make_float4(-1.f, -1.f, -1.f, 0.f);
+      if (!pre_invalid)  // warp-uniform
+        res = klt_gain_iteration(L0, L1, w, h, x0.x, x0.y, cur.x, cur.y, beta, nbterm, dsx, dsy,
+                                 strict ? Pstrict : Plax, lane);
+      if (lane == 0) {
+        if (pass == nPass) out[item] = res;
+        state[(size_t)wr * T + item] = res;
+        __threadfence();
+        asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(ver + (size_t)wr * T + item),
+                     "r"(verBase + pass)
+                     : "memory");
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// 2x2 LK (klt_tracker.cg:24-132): all levels and iterations inside one kernel, one warp per
+// feature.  Output (X1.x, X1.y, X0.x) or -1.
+// ------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256)
 klt_track_2x2(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1, long long pyrStride,

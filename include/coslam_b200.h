@@ -62,7 +62,10 @@ typedef struct cosl_klt_config {
   int compat;                 /* extension, see above; default COSL_KLT_COMPAT_ITER5 */
 } cosl_klt_config;
 
-enum { COSL_KLT_COMPAT_ITER5 = 1 };
+/* bit 1 (COSL_KLT_PASS_KERNELS, diagnostic): run the gain tracker as one kernel launch per
+ * (level, iteration) pass like the reference's draw calls, instead of the single persistent
+ * kernel; results are bit-identical, only slower. */
+enum { COSL_KLT_COMPAT_ITER5 = 1, COSL_KLT_PASS_KERNELS = 2 };
 
 /* Mirrors V3D_GPU::KLT_TrackedFeature (v3d_gpuklt.h:166-176): 20 bytes. */
 typedef struct cosl_klt_feature {

@@ -143,3 +143,25 @@ def test_full_size_known_answer_flow(api):
             pn = f1[c]["pos"][new] * [W, H]
             d = np.abs(pn[:, None, :] - x1[None, :, :]).max(-1).min(1)
             assert d.min() > cfg.minDistance - 1.0
+
+
+@pytest.mark.parametrize("fw,fh", [(32, 32), (50, 40), (32, 16), (10, 15)])
+def test_fused_gain_tracker_equals_pass_kernels(api, fw, fh):
+    """The persistent single-launch gain tracker must reproduce the pass-per-launch execution bit
+    for bit (same arithmetic, only the synchronisation differs) -- also on non-square slot grids
+    where the neighbour relation is not symmetric."""
+    from coslam_b200.ctypes_defs import KltConfig
+    W, H = 640, 480
+    s = seq(H, W, 51, n=4)
+    cfg_f = live_cfg(gain=True, min_corner=1200.0)
+    cfg_p = live_cfg(gain=True, min_corner=1200.0)
+    cfg_p.compat |= 2  # COSL_KLT_PASS_KERNELS
+    a = api.KltTracker(cfg_f, W, H, 6, fw, fh)
+    b = api.KltTracker(cfg_p, W, H, 6, fw, fh)
+    fa, na = a.first(s.frames[0])
+    fb, nb = b.first(s.frames[0])
+    assert fa.tobytes() == fb.tobytes()
+    for k in range(1, 4):
+        fa, na = a.next(s.frames[k])
+        fb, nb = b.next(s.frames[k])
+        assert na == nb and fa.tobytes() == fb.tobytes(), f"frame {k}"
