@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "ba_kernels.cuh"
+#include "ba_chol.cuh"
 #include "common.cuh"
 
 using namespace coslam;
@@ -83,8 +84,11 @@ struct cosl_ba_solver {
   long long* d_ptr = nullptr;
   double *d_W = nullptr, *d_V = nullptr, *d_eb = nullptr;
   double* d_Uea = nullptr;   // [U (m x 21) | ea (m x 6)] contiguous for one all-reduce
-  double* d_Srhs = nullptr;  // [S (ns x ns) | rhs (ns)] contiguous for one all-reduce
+  double* d_Srhs = nullptr;  // (ns+1) x ns trapezoid [S ; rhs^T], leading dimension ld, one all-reduce
+  int ld = 0, nb = 0;
   double *d_y = nullptr, *d_x = nullptr;
+  double* d_Linv = nullptr;   // [nb][64*64] inverses of the diagonal Cholesky blocks
+  int* d_firstBlk = nullptr;
   double* d_sc = nullptr;
   unsigned char* d_outlier = nullptr;
   BaPairItem* d_items = nullptr;
@@ -98,6 +102,7 @@ struct cosl_ba_solver {
   // rows (k, lastBlk[k]].  Dense co-visibility gives firstBlk == 0 everywhere (== dense algorithm).
   std::vector<int> firstBlk, lastBlk;
   cudaGraphExec_t solveGraph = nullptr;
+  int solveGraphNodes = 0;
   SectionTimer timer;
   int secLin = 0, secSchur = 0, secSolve = 0, secBack = 0, secCost = 0, secComm = 0;
   // statistics
@@ -197,7 +202,8 @@ void free_solver(cosl_ba_solver* s) {
   void* bufs[] = {s->d_camK, s->d_camR0, s->d_pa, s->d_na, s->d_dpa, s->d_pb, s->d_nb, s->d_dpb,
                   s->d_cam, s->d_pt, s->d_cobs, s->d_ccam, s->d_xy, s->d_wgt, s->d_ptr, s->d_W,
                   s->d_V, s->d_eb, s->d_Uea, s->d_Srhs, s->d_y, s->d_x, s->d_sc, s->d_outlier,
-                  s->d_items, s->d_entries};
+                  s->d_items, s->d_entries, s->d_Linv, s->d_firstBlk};
+  if (s->solveGraph) cudaGraphExecDestroy(s->solveGraph);
   for (void* b : bufs) cudaFree(b);
   if (s->h_sc) cudaFreeHost(s->h_sc);
   if (s->stream) cudaStreamDestroy(s->stream);
@@ -322,7 +328,34 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   COSL_TRY(dev_alloc(&s->d_V, (size_t)n * 6));
   COSL_TRY(dev_alloc(&s->d_eb, (size_t)n * 3));
   COSL_TRY(dev_alloc(&s->d_Uea, (size_t)m * 27));
-  COSL_TRY(dev_alloc(&s->d_Srhs, (size_t)s->ns * s->ns + s->ns));
+  s->ld = ((s->ns + 1 + 15) / 16) * 16;
+  s->nb = (s->ns + CB - 1) / CB;
+  COSL_TRY(dev_alloc(&s->d_Srhs, (size_t)s->ld * (s->ns ? s->ns : 1)));
+  COSL_TRY(dev_alloc(&s->d_Linv, (size_t)std::max(1, s->nb) * CB * CB));
+  COSL_TRY(dev_alloc(&s->d_firstBlk, (size_t)std::max(1, s->nb)));
+  {
+    // block-row envelope from the camera co-visibility (pair counts): pair (ja <= jb) puts
+    // entries at rows of jb, columns of ja of the lower factor
+    const int nbk = s->nb;
+    s->firstBlk.assign(std::max(1, nbk), 0);
+    for (int I = 0; I < nbk; ++I) s->firstBlk[I] = I;
+    for (int ja = 0; ja < mf; ++ja)
+      for (int jb = ja; jb < mf; ++jb)
+        if (pcount[(size_t)ja * mf + jb + 1] > pcount[(size_t)ja * mf + jb]) {
+          const int cb0 = (6 * ja) / CB;
+          for (int rb = (6 * jb) / CB; rb <= (6 * jb + 5) / CB; ++rb)
+            s->firstBlk[rb] = std::min(s->firstBlk[rb], cb0);
+        }
+    s->lastBlk.assign(std::max(1, nbk), 0);
+    for (int k = 0; k < nbk; ++k) {
+      int last = k;
+      for (int I = k + 1; I < nbk; ++I)
+        if (s->firstBlk[I] <= k) last = I;
+      s->lastBlk[k] = last;
+    }
+    COSL_CUDA(cudaMemcpy(s->d_firstBlk, s->firstBlk.data(), sizeof(int) * std::max(1, nbk),
+                         cudaMemcpyHostToDevice));
+  }
   COSL_TRY(dev_alloc(&s->d_y, (size_t)s->ns));
   COSL_TRY(dev_alloc(&s->d_x, (size_t)s->ns));
   COSL_TRY(dev_alloc(&s->d_sc, (size_t)SC_NTOT));
@@ -352,6 +385,7 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   d.ncon = ncon;
   d.mf = s->mf;
   d.ns = s->ns;
+  d.ld = s->ld;
   d.N = N;
   d.Nc = Nc;
   d.camK = s->d_camK;
@@ -369,7 +403,6 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   d.U = s->d_Uea;
   d.ea = s->d_Uea + (size_t)m * 21;
   d.S = s->d_Srhs;
-  d.rhs = s->d_Srhs + (size_t)s->ns * s->ns;
   d.sc = s->d_sc;
   // small systems are factored inside one CTA (ns*ns doubles of shared memory)
   const size_t smallBytes = sizeof(double) * (size_t)s->ns * s->ns;
@@ -378,6 +411,10 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   if (s->smallSolve && smallBytes > 32 * 1024)
     COSL_CUDA(cudaFuncSetAttribute(ba_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smallBytes));
+  COSL_CUDA(cudaFuncSetAttribute(ba_chol_potf2_inv, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 BA_CHOL_SMEM));
+  COSL_CUDA(cudaFuncSetAttribute(ba_chol_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 BA_CHOL_SMEM));
   s->secLin = s->timer.section("ba_linearize");
   s->secSchur = s->timer.section("ba_schur");
   s->secSolve = s->timer.section("ba_solve");
@@ -468,39 +505,58 @@ int linearize(cosl_ba_solver* s) {
   return COSL_OK;
 }
 
+int launch_blocked_solve(cosl_ba_solver* s, int* nLaunch) {
+  const int ns = s->ns, ld = s->ld, nb = s->nb, nrows = ns + 1;
+  const int extraBlk = ns / CB;  // block row that holds the right-hand-side row ns
+  int count = 0;
+  for (int k = 0; k < nb; ++k) {
+    const int k0 = k * CB, bs = std::min(CB, ns - k0);
+    double* Linv = s->d_Linv + (size_t)k * CB * CB;
+    COSL_LAUNCH(ba_chol_potf2_inv, 1, 1024, BA_CHOL_SMEM, s->stream, s->d.S, ld, k0, bs, Linv, s->d_sc,
+                (int)SC_FAIL);
+    const int nAct = s->lastBlk[k] - k;
+    const bool extra = extraBlk > k + nAct || extraBlk == k;
+    const int nT = nAct + (extra ? 1 : 0);
+    if (nT > 0) {
+      COSL_LAUNCH(ba_chol_trsm, nT, 256, BA_CHOL_SMEM, s->stream, s->d.S, ld, nrows, k0, bs, k, nAct,
+                  extraBlk, Linv);
+      COSL_LAUNCH(ba_chol_syrk, dim3(nT, nT), 256, 0, s->stream, s->d.S, ld, ns, nrows, k0, bs, k,
+                  nAct, extraBlk);
+      count += 2;
+    }
+    ++count;
+  }
+  COSL_LAUNCH(ba_chol_backward, 1, 512, 0, s->stream, s->d.S, ld, ns, nb, s->d_Linv, s->d_firstBlk,
+              s->d_y, s->d_x);
+  *nLaunch = count + 1;
+  return COSL_OK;
+}
+
 int dense_solve(cosl_ba_solver* s) {
   const int ns = s->ns;
   if (ns == 0) return COSL_OK;
   s->timer.begin(s->secSolve, s->stream);
   if (s->smallSolve) {
-    COSL_LAUNCH(ba_chol_small, 1, 256, sizeof(double) * (size_t)ns * ns, s->stream, s->d.S,
-                s->d.rhs, ns, s->d_sc);
-    // solution is left in rhs
-    COSL_CUDA(cudaMemcpyAsync(s->d_x, s->d.rhs, sizeof(double) * ns, cudaMemcpyDeviceToDevice,
-                              s->stream));
+    COSL_LAUNCH(ba_chol_small, 1, 256, sizeof(double) * (size_t)ns * ns, s->stream, s->d.S, s->ld,
+                ns, s->d_x, s->d_sc, (int)SC_FAIL);
   } else {
-    for (int k0 = 0; k0 < ns; k0 += CB) {
-      const int bs = std::min(CB, ns - k0);
-      COSL_LAUNCH(ba_chol_potf2, 1, 256, 0, s->stream, s->d.S, ns, k0, bs, s->d_sc);
-      const int rem = ns - k0 - bs;
-      if (rem > 0) {
-        COSL_LAUNCH(ba_chol_trsm, div_up(rem, 128), 128, 0, s->stream, s->d.S, ns, k0, bs);
-        const int nt = div_up(rem, CB);
-        COSL_LAUNCH(ba_chol_syrk, dim3(nt, nt), 256, 0, s->stream, s->d.S, ns, k0, bs);
-      }
+    // the launch sequence only depends on the (fixed) structure: capture it once, replay after
+    if (!s->solveGraph) {
+      cudaGraph_t graph = nullptr;
+      int nl = 0;
+      const uint64_t before = g_launches.load();
+      COSL_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = launch_blocked_solve(s, &nl);
+      cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
+      g_launches.store(before);
+      if (rc != COSL_OK) return rc;
+      if (e != cudaSuccess) return set_error(COSL_E_CUDA, "graph capture: %s", cudaGetErrorString(e));
+      COSL_CUDA(cudaGraphInstantiate(&s->solveGraph, graph, 0));
+      cudaGraphDestroy(graph);
+      s->solveGraphNodes = nl;
     }
-    for (int k0 = 0; k0 < ns; k0 += CB) {
-      const int bs = std::min(CB, ns - k0);
-      const int rem = ns - k0 - bs;
-      COSL_LAUNCH(ba_trsv_fwd_step, std::max(1, div_up(rem, 128)), 128, 0, s->stream, s->d.S,
-                  s->d.rhs, s->d_y, ns, k0, bs);
-    }
-    const int last = ((ns - 1) / CB) * CB;
-    for (int k0 = last; k0 >= 0; k0 -= CB) {
-      const int bs = std::min(CB, ns - k0);
-      COSL_LAUNCH(ba_trsv_bwd_step, std::max(1, div_up(k0, 128)), 128, 0, s->stream, s->d.S,
-                  s->d_y, s->d_x, ns, k0, bs);
-    }
+    COSL_CUDA(cudaGraphLaunch(s->solveGraph, s->stream));
+    g_launches.fetch_add(s->solveGraphNodes, std::memory_order_relaxed);
   }
   s->timer.end(s->stream);
   COSL_CUDA(cudaGetLastError());
@@ -517,14 +573,14 @@ int solve_trial(cosl_ba_solver* s, double mu, bool* solved) {
   s->timer.begin(s->secSchur, s->stream);
   const long long ns = s->ns;
   if (ns) {
-    COSL_LAUNCH(ba_init_S, (unsigned)div_up64(ns * ns + ns, 256), 256, 0, s->stream, s->d, mu,
+    COSL_LAUNCH(ba_init_S, (unsigned)div_up64((long long)s->ld * ns, 256), 256, 0, s->stream, s->d, mu,
                 r0 ? 1 : 0);
     if (s->nItems)
       COSL_LAUNCH(ba_schur_pairs, div_up(s->nItems, 4), 128, 0, s->stream, s->d, s->d_items,
                   s->nItems, s->d_entries, mu);
   }
   s->timer.end(s->stream);
-  if (ns) COSL_TRY(allreduce(s, s->d_Srhs, (size_t)(ns * ns + ns), ncclSum));
+  if (ns) COSL_TRY(allreduce(s, s->d_Srhs, (size_t)s->ld * (size_t)ns, ncclSum));
   COSL_TRY(dense_solve(s));
   s->timer.begin(s->secBack, s->stream);
   COSL_LAUNCH(ba_cam_update, div_up(6 * s->m, 256), 256, 0, s->stream, s->d, s->d_pa, s->d_x,

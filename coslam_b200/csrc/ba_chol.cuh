@@ -1,0 +1,292 @@
+// ba_chol.cuh -- dense / skyline Cholesky solve of the reduced camera system (fp64, sm_100a).
+//
+// Storage: S is column-major LOWER with leading dimension ld >= ns + 1: L(i, j), i >= j, lives at
+// S[j * ld + i].  Row index ns of every column holds the right-hand side, i.e. the matrix is the
+// (ns+1) x ns lower trapezoid [S ; b^T]: factorising it performs the forward substitution for free
+// (after the last panel, row ns holds y^T = (L^-1 b)^T).
+//
+// Blocked right-looking algorithm with block size CB = 64 and a block-row ENVELOPE: block row I has
+// structural non-zeros only from block column firstBlk[I] on (camera co-visibility is banded for
+// sequential key frames), so panel k touches block rows (k, lastBlk[k]] plus the block that holds
+// the right-hand-side row.  With dense co-visibility the envelope is full and this is the plain
+// dense algorithm.  Per panel:
+//   ba_chol_potf2_inv : factor the 64x64 diagonal block and invert the factor (one CTA, 1024 thr)
+//   ba_chol_trsm      : X = A_panel * Linv_k^T          (a GEMM, no triangular dependency chain)
+//   ba_chol_syrk      : A_IJ -= X_I X_J^T on the active tiles
+// then ba_chol_backward: x = L^-T y, one persistent CTA walking the block columns backwards.
+// The whole sequence is captured once into a CUDA graph per solver (fixed structure).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace coslam {
+
+constexpr int CB = 64;
+constexpr int BA_CHOL_SMEM = 2 * CB * (CB + 1) * (int)sizeof(double);
+
+// ------------------------------------------------------------------------------------------
+// Small systems: ns*ns doubles fit in shared memory -> factor + both substitutions in one CTA.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ba_chol_small(double* __restrict__ S, int ld, int ns, double* __restrict__ xout,
+              double* __restrict__ sc, int scFail) {
+  extern __shared__ double sL[];  // column-major lower, leading dimension ns
+  __shared__ int s_fail;
+  __shared__ double sx[1024];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int t = tid; t < ns * ns; t += nt) {
+    const int j = t / ns, i = t - j * ns;
+    sL[t] = (i >= j) ? S[(size_t)j * ld + i] : 0.0;
+  }
+  if (tid == 0) s_fail = 0;
+  __syncthreads();
+  for (int k = 0; k < ns; ++k) {
+    const double dkk = sL[k * ns + k];
+    if (!(dkk > 0) || !isfinite(dkk)) {
+      if (tid == 0) s_fail = 1;
+      break;  // uniform: every thread reads the same dkk
+    }
+    const double rs = 1.0 / sqrt(dkk);
+    __syncthreads();
+    for (int i = k + tid; i < ns; i += nt) sL[k * ns + i] = (i == k) ? sqrt(dkk) : sL[k * ns + i] * rs;
+    __syncthreads();
+    // trailing update: L(i, j) -= L(i,k) L(j,k), k < j <= i; thread grid 16 (j) x 16 (i)
+    const int tj = tid >> 4, ti = tid & 15;
+    for (int j = k + 1 + tj; j < ns; j += 16) {
+      const double ljk = sL[k * ns + j];
+      for (int i = j + ti; i < ns; i += 16) sL[j * ns + i] -= sL[k * ns + i] * ljk;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (s_fail) {
+    if (tid == 0) sc[scFail] = 1.0;
+    return;
+  }
+  if (tid < 32) {
+    for (int i = tid; i < ns; i += 32) sx[i] = S[(size_t)i * ld + ns];
+    __syncwarp();
+    for (int k = 0; k < ns; ++k) {
+      const double xk = sx[k] / sL[k * ns + k];
+      __syncwarp();
+      if (tid == 0) sx[k] = xk;
+      for (int i = k + 1 + tid; i < ns; i += 32) sx[i] -= sL[k * ns + i] * xk;
+      __syncwarp();
+    }
+    for (int k = ns - 1; k >= 0; --k) {
+      double part = 0;
+      for (int i = k + 1 + tid; i < ns; i += 32) part += sL[k * ns + i] * sx[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      __syncwarp();
+      if (tid == 0) sx[k] = (sx[k] - part) / sL[k * ns + k];
+      __syncwarp();
+    }
+    for (int i = tid; i < ns; i += 32) xout[i] = sx[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Diagonal block: Cholesky factor (written back into S) and its inverse Linv (dense bs x bs,
+// row-major: Linv[r * CB + c], lower triangular).  1024 threads: tx = row, ty = column phase.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+ba_chol_potf2_inv(double* __restrict__ S, int ld, int k0, int bs, double* __restrict__ Linv,
+                  double* __restrict__ sc, int scFail) {
+  // dynamic shared memory: two 64 x 65 matrices (BA_CHOL_SMEM bytes); the inverse X reuses the
+  // working copy A once the factorisation is finished
+  extern __shared__ double s_dyn[];
+  double (*A)[CB + 1] = reinterpret_cast<double (*)[CB + 1]>(s_dyn);
+  double (*Lm)[CB + 1] = reinterpret_cast<double (*)[CB + 1]>(s_dyn + CB * (CB + 1));
+  double (*X)[CB + 1] = A;
+  __shared__ int s_fail;
+  const int tid = threadIdx.x;
+  const int tx = tid & 63, ty = tid >> 6;  // 64 rows x 16 phases
+  for (int t = tid; t < CB * CB; t += 1024) {
+    const int j = t >> 6, i = t & 63;
+    A[i][j] = (i < bs && j < bs && i >= j) ? S[(size_t)(k0 + j) * ld + k0 + i] : ((i == j) ? 1.0 : 0.0);
+    Lm[i][j] = 0.0;
+  }
+  if (tid == 0) s_fail = 0;
+  __syncthreads();
+  for (int k = 0; k < CB; ++k) {
+    double d = A[k][k];
+    if (!(d > 0) || !isfinite(d)) {  // uniform across the CTA
+      if (tid == 0) s_fail = 1;
+      d = 1.0;
+    }
+    const double inv_d = 1.0 / d;
+    const double lik = A[tx][k];
+    if (tx > k)
+      for (int j = k + 1 + ty; j <= tx; j += 16) A[tx][j] -= lik * A[j][k] * inv_d;
+    if (ty == 0 && tx >= k) Lm[tx][k] = (tx == k) ? sqrt(d) : lik / sqrt(d);
+    __syncthreads();
+  }
+  // inverse of the lower triangular factor, column j by 16 cooperating threads (same half-warp)
+  for (int t = tid; t < CB * CB; t += 1024) X[t >> 6][t & 63] = 0.0;
+  __syncthreads();
+  {
+    const int j = tid >> 4, q = tid & 15;  // 64 columns x 16 lanes
+    if (q == 0) X[j][j] = 1.0 / Lm[j][j];
+    __syncwarp();
+    // uniform trip count for the whole warp (two columns per warp), rows i <= j are idle
+    for (int i = 1; i < CB; ++i) {
+      double part = 0;
+      if (i > j)
+        for (int p = j + q; p < i; p += 16) part += Lm[i][p] * X[p][j];
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o, 16);
+      if (q == 0 && i > j) X[i][j] = -part / Lm[i][i];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (s_fail && tid == 0) sc[scFail] = 1.0;
+  for (int t = tid; t < CB * CB; t += 1024) {
+    const int j = t >> 6, i = t & 63;
+    if (i < bs && j < bs && i >= j) S[(size_t)(k0 + j) * ld + k0 + i] = Lm[i][j];
+    Linv[i * CB + j] = (i < bs && j < bs) ? X[i][j] : 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Panel: rows [r0, r0 + 64) of block column k:  X(r, c) = sum_{p <= c} A(r, p) Linv(c, p).
+// blockIdx.x < nAct addresses active block row k + 1 + blockIdx.x, blockIdx.x == nAct the extra
+// block row `extraBlk` (the one holding the right-hand-side row).  nrows = ns + 1.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ba_chol_trsm(double* __restrict__ S, int ld, int nrows, int k0, int bs, int kblk, int nAct,
+             int extraBlk, const double* __restrict__ Linv) {
+  const int rowMin = k0 + bs;  // rows of the diagonal block itself are never touched
+  extern __shared__ double s_dyn[];
+  double (*sA)[CB + 1] = reinterpret_cast<double (*)[CB + 1]>(s_dyn);                  // [p][row]
+  double (*sI)[CB + 1] = reinterpret_cast<double (*)[CB + 1]>(s_dyn + CB * (CB + 1));  // [p][c]
+  const int blk = (blockIdx.x < nAct) ? (kblk + 1 + blockIdx.x) : extraBlk;
+  const int r0 = blk * CB;
+  const int tid = threadIdx.x;
+  for (int t = tid; t < CB * CB; t += 256) {
+    const int p = t >> 6, r = t & 63;
+    sA[p][r] = (p < bs && r0 + r < nrows && r0 + r >= rowMin) ? S[(size_t)(k0 + p) * ld + r0 + r] : 0.0;
+    const int c = t >> 6, pp = t & 63;
+    sI[pp][c] = Linv[c * CB + pp];
+  }
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  double acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b] = 0;
+  for (int p = 0; p < bs; ++p) {
+    double ar[4], ic[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) ar[a] = sA[p][tx + 16 * a];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) ic[b] = sI[p][ty + 16 * b];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) acc[a][b] += ar[a] * ic[b];
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int r = r0 + tx + 16 * a, c = ty + 16 * b;
+      if (r < nrows && r >= rowMin && c < bs) S[(size_t)(k0 + c) * ld + r] = acc[a][b];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Trailing update on the active tiles: A(i, j) -= sum_p X(i, p) X(j, p), i >= j, j < ns.
+// Tile rows/cols index the list {k+1 .. k+nAct, extraBlk}; grid = (nT, nT), lower tiles only.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ba_chol_syrk(double* __restrict__ S, int ld, int ns, int nrows, int k0, int bs, int kblk,
+             int nAct, int extraBlk) {
+  const int tjI = blockIdx.x, tiI = blockIdx.y;
+  if (tiI < tjI) return;
+  const int bi = (tiI < nAct) ? (kblk + 1 + tiI) : extraBlk;
+  const int bj = (tjI < nAct) ? (kblk + 1 + tjI) : extraBlk;
+  constexpr int KC = 32;
+  __shared__ double sAi[KC][CB + 1];
+  __shared__ double sAj[KC][CB + 1];
+  const int i0 = bi * CB, j0 = bj * CB;
+  const int rowMin = k0 + bs;  // only the trailing part (rows/cols beyond the panel) is updated
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  double c[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) c[a][b] = 0;
+  for (int p0 = 0; p0 < bs; p0 += KC) {
+    const int pc = min(KC, bs - p0);
+    __syncthreads();
+    for (int t = tid; t < pc * CB; t += 256) {
+      const int p = t >> 6, r = t & 63;
+      sAi[p][r] = (i0 + r < nrows && i0 + r >= rowMin) ? S[(size_t)(k0 + p0 + p) * ld + i0 + r] : 0.0;
+      sAj[p][r] = (j0 + r < nrows && j0 + r >= rowMin) ? S[(size_t)(k0 + p0 + p) * ld + j0 + r] : 0.0;
+    }
+    __syncthreads();
+    for (int p = 0; p < pc; ++p) {
+      double ai[4], aj[4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) ai[a] = sAi[p][tx + 16 * a];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) aj[b] = sAj[p][ty + 16 * b];
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) c[a][b] += ai[a] * aj[b];
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = i0 + tx + 16 * a, j = j0 + ty + 16 * b;
+      if (i < nrows && j < ns && i >= j && j >= rowMin) S[(size_t)j * ld + i] -= c[a][b];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Backward substitution L^T x = y, one persistent CTA: y is row ns of S (after the factorisation),
+// x_k = Linv_k^T y_k, then y_c -= sum_p L(k0 + p, c) x_k[p] for the columns c of the envelope of
+// block row k.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512)
+ba_chol_backward(const double* __restrict__ S, int ld, int ns, int nb,
+                 const double* __restrict__ Linv, const int* __restrict__ firstBlk,
+                 double* __restrict__ y, double* __restrict__ x) {
+  __shared__ double sx[CB];
+  const int tid = threadIdx.x;
+  for (int c = tid; c < ns; c += 512) y[c] = S[(size_t)c * ld + ns];
+  __syncthreads();
+  for (int k = nb - 1; k >= 0; --k) {
+    const int k0 = k * CB, bs = min(CB, ns - k0);
+    const double* Li = Linv + (size_t)k * CB * CB;
+    // x_k[c] = sum_{r >= c} Linv(r, c) y_k[r]   (8 threads per output)
+    {
+      const int c = tid >> 3, q = tid & 7;
+      double part = 0;
+      if (c < bs)
+        for (int r = c + q; r < bs; r += 8) part += Li[r * CB + c] * y[k0 + r];
+      part += __shfl_xor_sync(0xffffffffu, part, 4, 8);
+      part += __shfl_xor_sync(0xffffffffu, part, 2, 8);
+      part += __shfl_xor_sync(0xffffffffu, part, 1, 8);
+      if (q == 0 && c < bs) sx[c] = part;
+    }
+    __syncthreads();
+    if (tid < bs) x[k0 + tid] = sx[tid];
+    const int c0 = firstBlk[k] * CB;
+    for (int c = c0 + tid; c < k0; c += 512) {
+      const double* col = S + (size_t)c * ld + k0;
+      double s = 0;
+      for (int p = 0; p < bs; ++p) s += col[p] * sx[p];
+      y[c] -= s;
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace coslam

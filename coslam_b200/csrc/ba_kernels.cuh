@@ -24,6 +24,7 @@ namespace coslam {
 
 struct BaDev {
   int m, n, mcon, ncon, mf, ns;
+  int ld;  // leading dimension of S (>= ns + 1): column c starts at S + c*ld, row ns = rhs
   long long N, Nc;
   const double* camK;
   const double* camR0;
@@ -40,7 +41,6 @@ struct BaDev {
   double* U;
   double* ea;
   double* S;
-  double* rhs;
   double* sc;  // scalars, see BaScalar
 };
 
@@ -342,23 +342,26 @@ __global__ void __launch_bounds__(256) ba_stats_kernel(BaDev d) {
 // S <- 0 with the damped camera blocks U*_j on the diagonal, rhs <- ea.  addU: this rank
 // contributes U/ea/mu (rank 0 only in the multi-GPU case, where U/ea are already all-reduced).
 __global__ void __launch_bounds__(256) ba_init_S(BaDev d, double mu, int addU) {
+  // one thread per element of the (ns+1) x ns trapezoid stored with leading dimension ld:
+  // memory index t = c * ld + r  (column c of the column-major lower factor == row c of the
+  // row-major upper Schur complement), r == ns is the right-hand side
   const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long ns = d.ns;
-  if (t < ns * ns) {
-    const int r = (int)(t / ns), c = (int)(t - (long long)r * ns);
-    double v = 0;
-    const int jb = r / 6, kb = c / 6;
-    if (addU && jb == kb && c >= r) {
-      const int a = r - 6 * jb, b = c - 6 * kb;
+  const long long ns = d.ns, ld = d.ld;
+  if (t >= ld * ns) return;
+  const int c = (int)(t / ld), r = (int)(t - (long long)c * ld);
+  double v = 0;
+  if (r < ns) {
+    const int jb = c / 6, kb = r / 6;
+    if (addU && jb == kb && r >= c) {
+      const int a = c - 6 * jb, b = r - 6 * kb;
       const int idx = a * 6 - (a * (a - 1)) / 2 + (b - a);  // packed upper index of (a, b), a<=b
       v = d.U[21 * (size_t)(jb + d.mcon) + idx];
       if (a == b) v += mu;
     }
-    d.S[t] = v;
-  } else if (t < ns * ns + ns) {
-    const int r = (int)(t - ns * ns);
-    d.rhs[r] = addU ? d.ea[6 * (size_t)d.mcon + r] : 0.0;
+  } else if (r == ns) {
+    v = addU ? d.ea[6 * (size_t)d.mcon + c] : 0.0;
   }
+  d.S[t] = v;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -439,7 +442,7 @@ ba_schur_pairs(BaDev d, const BaPairItem* __restrict__ items, int nItems,
     for (int k = 0; k < 3; ++k) racc[k] += __shfl_xor_sync(0xffffffffu, racc[k], o);
   }
   if (lane < 2) {
-    const long long ns = d.ns;
+    const long long ld = d.ld;
     const int r0 = 6 * it.rowCam, c0 = 6 * it.colCam + 3 * half;
 #pragma unroll
     for (int r = 0; r < 6; ++r)
@@ -447,11 +450,12 @@ ba_schur_pairs(BaDev d, const BaPairItem* __restrict__ items, int nItems,
       for (int cc = 0; cc < 3; ++cc) {
         // only the upper part (col >= row) of diagonal blocks is kept
         if (!diag || (c0 + cc >= r0 + r))
-          atomicAdd(&d.S[(long long)(r0 + r) * ns + c0 + cc], -acc[3 * r + cc]);
+          atomicAdd(&d.S[(long long)(r0 + r) * ld + c0 + cc], -acc[3 * r + cc]);
       }
     if (diag) {
 #pragma unroll
-      for (int rr = 0; rr < 3; ++rr) atomicAdd(&d.rhs[r0 + 3 * half + rr], -racc[rr]);
+      for (int rr = 0; rr < 3; ++rr)
+        atomicAdd(&d.S[(long long)(r0 + 3 * half + rr) * ld + d.ns], -racc[rr]);
     }
   }
 }
@@ -556,248 +560,6 @@ ba_cam_update(BaDev d, const double* __restrict__ pa, const double* __restrict__
   if (threadIdx.x == 0 && addSums && s != 0) atomicAdd(&d.sc[SC_DL], s);
   s = block_sum_1(p2, s_red);
   if (threadIdx.x == 0 && addSums && s != 0) atomicAdd(&d.sc[SC_P_L2], s);
-}
-
-// ------------------------------------------------------------------------------------------
-// Dense SPD solve of the reduced camera system.
-// Storage convention: S row-major with the blocks (row <= col) valid == column-major LOWER
-// triangle: element L(i, j), i >= j, lives at S[j * ns + i].
-// ------------------------------------------------------------------------------------------
-
-// Small systems (ns*ns doubles fit in shared memory): factor + both triangular solves in one CTA.
-__global__ void __launch_bounds__(256)
-ba_chol_small(double* __restrict__ S, double* __restrict__ rhs, int ns, double* __restrict__ sc) {
-  extern __shared__ double sL[];  // column-major lower, leading dimension ns
-  __shared__ int s_fail;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  for (int t = tid; t < ns * ns; t += nt) sL[t] = S[t];
-  if (tid == 0) s_fail = 0;
-  __syncthreads();
-  for (int k = 0; k < ns; ++k) {
-    if (tid == 0) {
-      const double dkk = sL[k * ns + k];
-      if (!(dkk > 0) || !isfinite(dkk)) {
-        s_fail = 1;
-        sL[k * ns + k] = 1.0;
-      } else {
-        sL[k * ns + k] = sqrt(dkk);
-      }
-    }
-    __syncthreads();
-    if (s_fail) break;
-    const double rk = 1.0 / sL[k * ns + k];
-    for (int i = k + 1 + tid; i < ns; i += nt) sL[k * ns + i] *= rk;
-    __syncthreads();
-    // trailing update of the lower triangle: L(i, j) -= L(i,k) L(j,k), j in (k, ns), i >= j
-    const int rem = ns - k - 1;
-    for (int t = tid; t < rem * rem; t += nt) {
-      const int jj = t / rem, ii = t - jj * rem;
-      if (ii >= jj) {
-        const int i = k + 1 + ii, j = k + 1 + jj;
-        sL[j * ns + i] -= sL[k * ns + i] * sL[k * ns + j];
-      }
-    }
-    __syncthreads();
-  }
-  if (s_fail) {
-    if (tid == 0) sc[SC_FAIL] = 1.0;
-    return;
-  }
-  // forward L y = b, backward L^T x = y by one warp (columns striped over lanes)
-  if (tid < 32) {
-    __shared__ double sx[1024];
-    for (int i = tid; i < ns; i += 32) sx[i] = rhs[i];
-    __syncwarp();
-    for (int k = 0; k < ns; ++k) {
-      const double xk = sx[k] / sL[k * ns + k];
-      __syncwarp();
-      if (tid == 0) sx[k] = xk;
-      for (int i = k + 1 + tid; i < ns; i += 32) sx[i] -= sL[k * ns + i] * xk;
-      __syncwarp();
-    }
-    for (int k = ns - 1; k >= 0; --k) {
-      double part = 0;
-      for (int i = k + 1 + tid; i < ns; i += 32) part += sL[k * ns + i] * sx[i];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-      __syncwarp();
-      if (tid == 0) sx[k] = (sx[k] - part) / sL[k * ns + k];
-      __syncwarp();
-    }
-    for (int i = tid; i < ns; i += 32) rhs[i] = sx[i];
-  }
-}
-
-// ---- blocked right-looking Cholesky for large ns (block size CB) ----
-constexpr int CB = 64;
-
-// factor the CB x CB diagonal block k (in place, lower), one CTA
-__global__ void __launch_bounds__(256)
-ba_chol_potf2(double* __restrict__ S, int ns, int k0, int bs, double* __restrict__ sc) {
-  __shared__ double sA[CB][CB + 1];
-  __shared__ int s_fail;
-  const int tid = threadIdx.x;
-  for (int t = tid; t < bs * bs; t += 256) {
-    const int j = t / bs, i = t - j * bs;
-    sA[i][j] = (i >= j) ? S[(size_t)(k0 + j) * ns + k0 + i] : 0.0;
-  }
-  if (tid == 0) s_fail = 0;
-  __syncthreads();
-  for (int k = 0; k < bs; ++k) {
-    if (tid == 0) {
-      const double dkk = sA[k][k];
-      if (!(dkk > 0) || !isfinite(dkk)) {
-        s_fail = 1;
-        sA[k][k] = 1.0;
-      } else
-        sA[k][k] = sqrt(dkk);
-    }
-    __syncthreads();
-    const double rk = 1.0 / sA[k][k];
-    for (int i = k + 1 + tid; i < bs; i += 256) sA[i][k] *= rk;
-    __syncthreads();
-    const int rem = bs - k - 1;
-    for (int t = tid; t < rem * rem; t += 256) {
-      const int jj = t / rem, ii = t - jj * rem;
-      if (ii >= jj) sA[k + 1 + ii][k + 1 + jj] -= sA[k + 1 + ii][k] * sA[k + 1 + jj][k];
-    }
-    __syncthreads();
-  }
-  if (s_fail && tid == 0) sc[SC_FAIL] = 1.0;
-  for (int t = tid; t < bs * bs; t += 256) {
-    const int j = t / bs, i = t - j * bs;
-    if (i >= j) S[(size_t)(k0 + j) * ns + k0 + i] = sA[i][j];
-  }
-}
-
-// panel solve: rows below the diagonal block: X L_kk^T = A  -> each thread owns one row
-__global__ void __launch_bounds__(128)
-ba_chol_trsm(double* __restrict__ S, int ns, int k0, int bs) {
-  __shared__ double sLk[CB][CB + 1];
-  const int tid = threadIdx.x;
-  for (int t = tid; t < bs * bs; t += 128) {
-    const int j = t / bs, i = t - j * bs;
-    sLk[i][j] = (i >= j) ? S[(size_t)(k0 + j) * ns + k0 + i] : 0.0;
-  }
-  __syncthreads();
-  const int row = k0 + bs + blockIdx.x * 128 + tid;
-  if (row >= ns) return;
-  double x[CB];
-#pragma unroll 8
-  for (int j = 0; j < bs; ++j) x[j] = S[(size_t)(k0 + j) * ns + row];
-  for (int j = 0; j < bs; ++j) {
-    double s = x[j];
-    for (int p = 0; p < j; ++p) s -= x[p] * sLk[j][p];
-    x[j] = s / sLk[j][j];
-  }
-  for (int j = 0; j < bs; ++j) S[(size_t)(k0 + j) * ns + row] = x[j];
-}
-
-// trailing update: A(i, j) -= sum_p L(i, k0+p) L(j, k0+p) for i >= j > panel; 64x64 tiles, 256
-// threads, 4x4 micro-tiles, fp64 FMA.
-__global__ void __launch_bounds__(256)
-ba_chol_syrk(double* __restrict__ S, int ns, int k0, int bs) {
-  const int tj = blockIdx.x, ti = blockIdx.y;  // tile coordinates in the trailing matrix
-  if (ti < tj) return;
-  constexpr int KC = 32;  // contraction chunk staged in shared memory
-  __shared__ double sAi[KC][CB + 1];  // [p][row]
-  __shared__ double sAj[KC][CB + 1];
-  const int base = k0 + bs;
-  const int i0 = base + ti * CB, j0 = base + tj * CB;
-  const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, each 4 x 4
-  double c[4][4];
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) c[a][b] = 0;
-  for (int p0 = 0; p0 < bs; p0 += KC) {
-    const int pc = min(KC, bs - p0);
-    __syncthreads();
-    for (int t = tid; t < pc * CB; t += 256) {
-      const int p = t / CB, r = t - p * CB;
-      sAi[p][r] = (i0 + r < ns) ? S[(size_t)(k0 + p0 + p) * ns + i0 + r] : 0.0;
-      sAj[p][r] = (j0 + r < ns) ? S[(size_t)(k0 + p0 + p) * ns + j0 + r] : 0.0;
-    }
-    __syncthreads();
-    for (int p = 0; p < pc; ++p) {
-      double ai[4], aj[4];
-#pragma unroll
-      for (int a = 0; a < 4; ++a) ai[a] = sAi[p][tx + 16 * a];
-#pragma unroll
-      for (int b = 0; b < 4; ++b) aj[b] = sAj[p][ty + 16 * b];
-#pragma unroll
-      for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b = 0; b < 4; ++b) c[a][b] += ai[a] * aj[b];
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const int i = i0 + tx + 16 * a, j = j0 + ty + 16 * b;
-      if (i < ns && j < ns && i >= j) S[(size_t)j * ns + i] -= c[a][b];
-    }
-}
-
-// Triangular solves for the blocked factor, one kernel per block step (ns/CB steps per direction).
-// forward step k : every CTA redundantly solves L_kk y_k = b_k (b_k is read-only in this step),
-//                  CTA 0 publishes y_k to `y`, all CTAs update their rows b_i -= L_ik y_k (i > k).
-__global__ void __launch_bounds__(128)
-ba_trsv_fwd_step(const double* __restrict__ S, double* __restrict__ b, double* __restrict__ y,
-                 int ns, int k0, int bs) {
-  __shared__ double sx[CB];
-  const int tid = threadIdx.x;
-  if (tid < 32) {
-    for (int i = tid; i < bs; i += 32) sx[i] = b[k0 + i];
-    __syncwarp();
-    for (int k = 0; k < bs; ++k) {
-      const double xk = sx[k] / S[(size_t)(k0 + k) * ns + k0 + k];
-      __syncwarp();
-      if (tid == 0) sx[k] = xk;
-      for (int i = k + 1 + tid; i < bs; i += 32) sx[i] -= S[(size_t)(k0 + k) * ns + k0 + i] * xk;
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-  if (blockIdx.x == 0 && tid < bs) y[k0 + tid] = sx[tid];
-  const int row = k0 + bs + blockIdx.x * 128 + tid;
-  if (row < ns) {
-    double s = 0;
-    for (int p = 0; p < bs; ++p) s += S[(size_t)(k0 + p) * ns + row] * sx[p];
-    b[row] -= s;
-  }
-}
-
-// backward step k: every CTA redundantly solves L_kk^T x_k = y_k (read-only), CTA 0 publishes x_k
-//                  to `x`, all CTAs update their columns y_c -= L(k-block, c)^T x_k (c < k0).
-__global__ void __launch_bounds__(128)
-ba_trsv_bwd_step(const double* __restrict__ S, double* __restrict__ y, double* __restrict__ x,
-                 int ns, int k0, int bs) {
-  __shared__ double sx[CB];
-  const int tid = threadIdx.x;
-  if (tid < 32) {
-    for (int i = tid; i < bs; i += 32) sx[i] = y[k0 + i];
-    __syncwarp();
-    for (int k = bs - 1; k >= 0; --k) {
-      // x_k = (y_k - sum_{i>k} L(i,k) x_i) / L(k,k); the subtraction was applied incrementally
-      const double xk = sx[k] / S[(size_t)(k0 + k) * ns + k0 + k];
-      __syncwarp();
-      if (tid == 0) sx[k] = xk;
-      for (int i = tid; i < k; i += 32) sx[i] -= S[(size_t)(k0 + i) * ns + k0 + k] * xk;
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-  if (blockIdx.x == 0 && tid < bs) x[k0 + tid] = sx[tid];
-  const int c = blockIdx.x * 128 + tid;
-  if (c < k0) {
-    const double* col = S + (size_t)c * ns + k0;  // L(k0 + p, c), p contiguous
-    double s = 0;
-    for (int p = 0; p < bs; ++p) s += col[p] * sx[p];
-    y[c] -= s;
-  }
 }
 
 }  // namespace coslam

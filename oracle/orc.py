@@ -82,7 +82,21 @@ def set_threads(n):
 
 
 def max_threads():
-    return int(lib().orc_get_max_threads())
+    """Host threads the oracle may use: min(CPU affinity, cgroup CPU quota) -- the GPU boxes
+    expose 128 logical CPUs but cap the container at a fraction of them; oversubscribing the
+    quota makes OpenMP dramatically slower, which would be unfair to the CPU baseline."""
+    n = int(lib().orc_get_max_threads())
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per))))
+    except Exception:
+        pass
+    return max(1, n)
 
 
 def _ptr(a):

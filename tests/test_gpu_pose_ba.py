@@ -136,3 +136,30 @@ def test_sba_signature_wrapper(api, orc):
     assert abs(ig[1] - io[1]) <= 1e-6 * io[1]
     assert np.abs(pg - po).max() < 1e-6
     assert ig[1] < ig[0]
+
+
+def test_ba_dense_covisibility_blocked_path(api, orc):
+    """All cameras see all points -> full envelope: the skyline factorisation degenerates to the
+    plain dense blocked Cholesky (reduced system 174 x 174 > one CTA's shared memory)."""
+    prob, truth = synth.make_ba_scene(30, 1, 600, 640, 480, seed=15, m_con=1, n_con=0, window=0,
+                                      p_vis=0.9, outlier_frac=0.0)
+    assert 6 * (prob.m - prob.m_con) == 174
+    opt = BaOptions.defaults()
+    opt.max_err, opt.outer_iters, opt.inner_iters = 0.0, 1, 8
+    _ba_compare(api, orc, prob, opt)
+
+
+def test_ba_c4_slice_parity(api, orc):
+    """A 40-key-frame slice of the c4 scene (banded co-visibility, reduced system 936 x 936):
+    fixed number of LM trials -> identical cost trajectory as the oracle."""
+    prob, truth = synth.make_ba_scene(4, 40, 6000, 1280, 720, seed=16, m_con=4, n_con=0)
+    opt = BaOptions.defaults()
+    pg, po = prob.copy(), prob.copy()
+    s = api.BaSolver(pg, opt)
+    ig = s.run_fixed(4)
+    s.download()
+    io = orc.ba_run_fixed(po, opt, 4)
+    assert ig[9] == io[9] == 4
+    assert abs(ig[1] - io[1]) <= 1e-9 * io[1], (ig[1], io[1])
+    assert abs(pg.rms() - po.rms()) <= REL_RMS_TOL * po.rms()
+    assert np.abs(pg.X - po.X).max() < 1e-6
