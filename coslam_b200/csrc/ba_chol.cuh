@@ -108,26 +108,35 @@ ba_chol_potf2_inv(double* __restrict__ S, int ld, int k0, int bs, double* __rest
   }
   if (tid == 0) s_fail = 0;
   __syncthreads();
+  const int lane = tid & 31;
   for (int k = 0; k < CB; ++k) {
     double d = A[k][k];
     if (!(d > 0) || !isfinite(d)) {  // uniform across the CTA
       if (tid == 0) s_fail = 1;
       d = 1.0;
     }
-    const double inv_d = 1.0 / d;
+    // one fp64 division / square root per WARP (not per thread: the fp64 pipe is only 64 wide)
+    double inv_d = 0, rsd = 0;
+    if (lane == 0) {
+      inv_d = 1.0 / d;
+      rsd = 1.0 / sqrt(d);
+    }
+    inv_d = __shfl_sync(0xffffffffu, inv_d, 0);
+    rsd = __shfl_sync(0xffffffffu, rsd, 0);
     const double lik = A[tx][k];
+    const double lik_s = lik * inv_d;
     if (tx > k)
-      for (int j = k + 1 + ty; j <= tx; j += 16) A[tx][j] -= lik * A[j][k] * inv_d;
-    if (ty == 0 && tx >= k) Lm[tx][k] = (tx == k) ? sqrt(d) : lik / sqrt(d);
+      for (int j = k + 1 + ty; j <= tx; j += 16) A[tx][j] -= lik_s * A[j][k];
+    if (ty == 0 && tx >= k) Lm[tx][k] = (tx == k) ? d * rsd : lik * rsd;
     __syncthreads();
   }
   // inverse of the lower triangular factor, column j by 16 cooperating threads (same half-warp)
   for (int t = tid; t < CB * CB; t += 1024) X[t >> 6][t & 63] = 0.0;
   __syncthreads();
+  if (tid < CB) X[tid][tid] = 1.0 / Lm[tid][tid];
+  __syncthreads();
   {
     const int j = tid >> 4, q = tid & 15;  // 64 columns x 16 lanes
-    if (q == 0) X[j][j] = 1.0 / Lm[j][j];
-    __syncwarp();
     // uniform trip count for the whole warp (two columns per warp), rows i <= j are idle
     for (int i = 1; i < CB; ++i) {
       double part = 0;
@@ -135,7 +144,7 @@ ba_chol_potf2_inv(double* __restrict__ S, int ld, int k0, int bs, double* __rest
         for (int p = j + q; p < i; p += 16) part += Lm[i][p] * X[p][j];
 #pragma unroll
       for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o, 16);
-      if (q == 0 && i > j) X[i][j] = -part / Lm[i][i];
+      if (q == 0 && i > j) X[i][j] = -part * X[i][i];
       __syncwarp();
     }
   }

@@ -1,0 +1,100 @@
+// Compile/link/run check of the reference-named shims: this file is written the way the
+// reference's own callers are (tracking/GPUKLT.cpp:98-161, app/SL_CoSLAMRobustBA.cpp:167-179,
+// app/SL_SingleSLAM.cpp:664) with minimal stand-ins for the LibVisualSLAM types they touch
+// (SURVEY.md Appendix D).  `shim_caller` without arguments only links; `shim_caller run` executes
+// on cuda:0.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "v3d_gpuklt.h"
+#include "SL_IntraCamPose.h"
+
+struct Mat_d {  // rows, cols, data -- as LibVisualSLAM's Mat_d is used by CoSLAM
+	int rows, cols;
+	double* data;
+	Mat_d(int r, int c, const double* src) : rows(r), cols(c), data(new double[r * c]) {
+		std::memcpy(data, src, sizeof(double) * r * c);
+	}
+	Mat_d(const Mat_d& o) : rows(o.rows), cols(o.cols), data(new double[o.rows * o.cols]) {
+		std::memcpy(data, o.data, sizeof(double) * rows * cols);
+	}
+	~Mat_d() { delete[] data; }
+};
+struct Point3d {
+	union { struct { double x, y, z; }; double M[3]; };
+	Point3d(double a, double b, double c) : x(a), y(b), z(c) {}
+};
+struct Meas2D {
+	int viewId; double x, y; int outlier;
+	Meas2D(int v, double a, double b) : viewId(v), x(a), y(b), outlier(0) {}
+};
+#include "SL_BundleAdjust.h"
+
+static int run() {
+	// --- KLT as GPUKLT::init/first/next drive it
+	const int W = 160, H = 120;
+	std::vector<unsigned char> img0(W * H), img1(W * H);
+	for (int y = 0; y < H; ++y)
+		for (int x = 0; x < W; ++x) {
+			img0[y * W + x] = (unsigned char) (128 + 60 * std::sin(0.35 * x) * std::cos(0.27 * y) + 40 * std::sin(0.11 * x * y / 40.0));
+			img1[y * W + x] = (unsigned char) (128 + 60 * std::sin(0.35 * (x - 1.5)) * std::cos(0.27 * (y - 0.5)) + 40 * std::sin(0.11 * (x - 1.5) * (y - 0.5) / 40.0));
+		}
+	V3D_GPU::KLT_SequenceTrackerConfig cfg;
+	cfg.minDistance = 8; cfg.minCornerness = 200; cfg.nLevels = 4; cfg.windowWidth = 6;
+	cfg.convergenceThreshold = 1.0f; cfg.SSD_Threshold = 20000; cfg.trackWithGain = true;
+	V3D_GPU::KLT_SequenceTracker* tracker = new V3D_GPU::KLT_SequenceTracker(cfg);
+	tracker->allocate(W, H, cfg.nLevels, 8, 8);
+	std::vector<V3D_GPU::KLT_TrackedFeature> feats(64);
+	int nDet = 0, nNew = 0;
+	tracker->detect(&img0[0], nDet, &feats[0]);
+	tracker->advanceFrame();
+	tracker->redetect(&img1[0], nNew, &feats[0]);
+	tracker->advanceFrame();
+	int tracked = 0;
+	for (int i = 0; i < 64; ++i) tracked += feats[i].status == 0;
+	std::printf("klt: detected %d, after next %d (%d tracked)\n", nDet, nNew, tracked);
+	tracker->deallocate();
+	delete tracker;
+	// --- pose as SingleSLAM::poseUpdate3D calls it
+	const double K[9] = {500, 0, 80, 0, 500, 60, 0, 0, 1}, R0[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t0[3] = {0.01, -0.01, 0.02};
+	std::vector<double> Ms, ms;
+	for (int i = 0; i < 30; ++i) {
+		const double X = (i % 6 - 2.5) * 0.4, Y = (i / 6 - 2) * 0.4, Z = 5 + 0.1 * i;
+		Ms.push_back(X); Ms.push_back(Y); Ms.push_back(Z);
+		ms.push_back(500 * X / Z + 80); ms.push_back(500 * Y / Z + 60);
+	}
+	double R[9], t[3];
+	IntraCamPoseOption opt;
+	const bool ok = intraCamEstimate(K, R0, t0, 30, 0, &Ms[0], &ms[0], 10.0, R, t, &opt);
+	std::printf("pose: ok %d |t| %.2e\n", (int) ok, std::sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]));
+	// --- BA as RobustBundleRTS::run calls it
+	std::vector<Mat_d> Ks, Rs, Ts;
+	const double t1[3] = {-0.5, 0, 0}, tz[3] = {0, 0, 0};
+	Ks.push_back(Mat_d(3, 3, K)); Rs.push_back(Mat_d(3, 3, R0)); Ts.push_back(Mat_d(3, 1, tz));
+	Ks.push_back(Mat_d(3, 3, K)); Rs.push_back(Mat_d(3, 3, R0)); Ts.push_back(Mat_d(3, 1, t1));
+	std::vector<Point3d> pts;
+	std::vector<std::vector<Meas2D> > meas;
+	for (int i = 0; i < 30; ++i) {
+		const double X = Ms[3 * i], Y = Ms[3 * i + 1], Z = Ms[3 * i + 2];
+		pts.push_back(Point3d(X + 0.01, Y - 0.01, Z + 0.05));
+		meas.push_back(std::vector<Meas2D>());
+		meas.back().push_back(Meas2D(0, 500 * X / Z + 80, 500 * Y / Z + 60));
+		meas.back().push_back(Meas2D(1, 500 * (X - 0.5) / Z + 80, 500 * Y / Z + 60));
+	}
+	try {
+		bundleAdjustRobust(1, Ks, Rs, Ts, 2, pts, meas, 6.0, 2, 10);
+	} catch (...) {
+		std::printf("bundle adjustment fail\n");
+		return 1;
+	}
+	std::printf("ba: point 5 -> (%.4f %.4f %.4f), truth (%.4f %.4f %.4f)\n", pts[5].x, pts[5].y, pts[5].z, Ms[15], Ms[16], Ms[17]);
+	return (ok && tracked > 0 && std::fabs(pts[5].z - Ms[17]) < 1e-2) ? 0 : 2;
+}
+
+int main(int argc, char** argv) {
+	if (argc > 1 && !std::strcmp(argv[1], "run")) return run();
+	std::printf("linked against %s\n", cosl_version());
+	return 0;
+}
