@@ -415,6 +415,14 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
                                  BA_CHOL_SMEM));
   COSL_CUDA(cudaFuncSetAttribute(ba_chol_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  BA_CHOL_SMEM));
+  {
+    const size_t bw = sizeof(double) * ((size_t)s->ns + CB * CB + CB);
+    if (!s->smallSolve && bw > 220 * 1024)
+      return set_error(COSL_E_INVALID, "reduced system too large for the backward solve (%d)", s->ns);
+    if (!s->smallSolve)
+      COSL_CUDA(cudaFuncSetAttribute(ba_chol_backward, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)bw));
+  }
   s->secLin = s->timer.section("ba_linearize");
   s->secSchur = s->timer.section("ba_schur");
   s->secSolve = s->timer.section("ba_solve");
@@ -526,8 +534,8 @@ int launch_blocked_solve(cosl_ba_solver* s, int* nLaunch) {
     }
     ++count;
   }
-  COSL_LAUNCH(ba_chol_backward, 1, 512, 0, s->stream, s->d.S, ld, ns, nb, s->d_Linv, s->d_firstBlk,
-              s->d_y, s->d_x);
+  COSL_LAUNCH(ba_chol_backward, 1, 1024, sizeof(double) * ((size_t)ns + CB * CB + CB), s->stream,
+              s->d.S, ld, ns, nb, s->d_Linv, s->d_firstBlk, s->d_x);
   *nLaunch = count + 1;
   return COSL_OK;
 }

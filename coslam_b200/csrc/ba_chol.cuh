@@ -118,8 +118,8 @@ ba_chol_potf2_inv(double* __restrict__ S, int ld, int k0, int bs, double* __rest
     // one fp64 division / square root per WARP (not per thread: the fp64 pipe is only 64 wide)
     double inv_d = 0, rsd = 0;
     if (lane == 0) {
-      inv_d = 1.0 / d;
-      rsd = 1.0 / sqrt(d);
+      rsd = rsqrt(d);     // short dependency chain: the pivot is on the critical path
+      inv_d = rsd * rsd;
     }
     inv_d = __shfl_sync(0xffffffffu, inv_d, 0);
     rsd = __shfl_sync(0xffffffffu, rsd, 0);
@@ -259,42 +259,51 @@ ba_chol_syrk(double* __restrict__ S, int ld, int ns, int nrows, int k0, int bs, 
 }
 
 // ------------------------------------------------------------------------------------------
-// Backward substitution L^T x = y, one persistent CTA: y is row ns of S (after the factorisation),
-// x_k = Linv_k^T y_k, then y_c -= sum_p L(k0 + p, c) x_k[p] for the columns c of the envelope of
-// block row k.
+// Backward substitution L^T x = y, one persistent 1024-thread CTA walking the block columns
+// backwards: y (row ns of S after the factorisation) lives in shared memory for the whole solve;
+// per block k: x_k = Linv_k^T y_k (Linv_k staged in shared memory with coalesced loads), then
+// y_c -= sum_p L(k0 + p, c) x_k[p] for the columns c of block row k's envelope -- one warp per
+// column, lanes over p (coalesced 512-byte column segments), shuffle reduction.
+// Dynamic shared memory: (ns + CB*CB + CB) doubles.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 ba_chol_backward(const double* __restrict__ S, int ld, int ns, int nb,
                  const double* __restrict__ Linv, const int* __restrict__ firstBlk,
-                 double* __restrict__ y, double* __restrict__ x) {
-  __shared__ double sx[CB];
-  const int tid = threadIdx.x;
-  for (int c = tid; c < ns; c += 512) y[c] = S[(size_t)c * ld + ns];
-  __syncthreads();
+                 double* __restrict__ x) {
+  extern __shared__ double s_dyn[];
+  double* sy = s_dyn;                 // [ns]
+  double* sLi = s_dyn + ns;           // [CB*CB] row-major Linv_k
+  double* sx = sLi + CB * CB;         // [CB]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int c = tid; c < ns; c += 1024) sy[c] = S[(size_t)c * ld + ns];
   for (int k = nb - 1; k >= 0; --k) {
     const int k0 = k * CB, bs = min(CB, ns - k0);
     const double* Li = Linv + (size_t)k * CB * CB;
-    // x_k[c] = sum_{r >= c} Linv(r, c) y_k[r]   (8 threads per output)
+    __syncthreads();
+    for (int t = tid; t < CB * CB; t += 1024) sLi[t] = Li[t];
+    __syncthreads();
+    // x_k[c] = sum_{r >= c} Linv(r, c) y_k[r]: 16 threads per output column
     {
-      const int c = tid >> 3, q = tid & 7;
+      const int c = tid >> 4, q = tid & 15;
       double part = 0;
-      if (c < bs)
-        for (int r = c + q; r < bs; r += 8) part += Li[r * CB + c] * y[k0 + r];
-      part += __shfl_xor_sync(0xffffffffu, part, 4, 8);
-      part += __shfl_xor_sync(0xffffffffu, part, 2, 8);
-      part += __shfl_xor_sync(0xffffffffu, part, 1, 8);
-      if (q == 0 && c < bs) sx[c] = part;
+      for (int r = c + q; r < bs; r += 16) part += sLi[r * CB + c] * sy[k0 + r];
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o, 16);
+      if (q == 0) sx[c] = (c < bs) ? part : 0.0;
     }
     __syncthreads();
     if (tid < bs) x[k0 + tid] = sx[tid];
     const int c0 = firstBlk[k] * CB;
-    for (int c = c0 + tid; c < k0; c += 512) {
+    const double x0 = sx[lane], x1 = sx[lane + 32];
+    for (int c = c0 + warp; c < k0; c += 32) {
       const double* col = S + (size_t)c * ld + k0;
       double s = 0;
-      for (int p = 0; p < bs; ++p) s += col[p] * sx[p];
-      y[c] -= s;
+      if (lane < bs) s = col[lane] * x0;
+      if (lane + 32 < bs) s += col[lane + 32] * x1;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) sy[c] -= s;
     }
-    __syncthreads();
   }
 }
 

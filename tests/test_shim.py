@@ -30,5 +30,5 @@ def test_shims_compile_and_link(tmp_path):
 def test_shims_run_on_gpu(tmp_path):
     exe = _build(str(tmp_path))
     out = subprocess.run([exe, "run"], capture_output=True, text=True)
-    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.returncode == 0, f"rc={out.returncode}\n{out.stdout}{out.stderr}"
     assert "klt:" in out.stdout and "pose: ok 1" in out.stdout and "ba:" in out.stdout
