@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -513,29 +514,42 @@ int linearize(cosl_ba_solver* s) {
   return COSL_OK;
 }
 
-int launch_blocked_solve(cosl_ba_solver* s, int* nLaunch) {
+// fine == true: per-kernel-class CUDA events (diagnostic, COSL_BA_NO_GRAPH=1), not capturable
+int launch_blocked_solve(cosl_ba_solver* s, int* nLaunch, bool fine = false) {
+  const int secP = fine ? s->timer.section("chol_potf2_inv") : 0;
+  const int secT = fine ? s->timer.section("chol_trsm") : 0;
+  const int secS = fine ? s->timer.section("chol_syrk") : 0;
+  const int secB = fine ? s->timer.section("chol_backward") : 0;
   const int ns = s->ns, ld = s->ld, nb = s->nb, nrows = ns + 1;
   const int extraBlk = ns / CB;  // block row that holds the right-hand-side row ns
   int count = 0;
   for (int k = 0; k < nb; ++k) {
     const int k0 = k * CB, bs = std::min(CB, ns - k0);
     double* Linv = s->d_Linv + (size_t)k * CB * CB;
+    if (fine) s->timer.begin(secP, s->stream);
     COSL_LAUNCH(ba_chol_potf2_inv, 1, 1024, BA_CHOL_SMEM, s->stream, s->d.S, ld, k0, bs, Linv, s->d_sc,
                 (int)SC_FAIL);
+    if (fine) s->timer.end(s->stream);
     const int nAct = s->lastBlk[k] - k;
     const bool extra = extraBlk > k + nAct || extraBlk == k;
     const int nT = nAct + (extra ? 1 : 0);
     if (nT > 0) {
+      if (fine) s->timer.begin(secT, s->stream);
       COSL_LAUNCH(ba_chol_trsm, nT, 256, BA_CHOL_SMEM, s->stream, s->d.S, ld, nrows, k0, bs, k, nAct,
                   extraBlk, Linv);
+      if (fine) s->timer.end(s->stream);
+      if (fine) s->timer.begin(secS, s->stream);
       COSL_LAUNCH(ba_chol_syrk, dim3(nT, nT), 256, 0, s->stream, s->d.S, ld, ns, nrows, k0, bs, k,
                   nAct, extraBlk);
+      if (fine) s->timer.end(s->stream);
       count += 2;
     }
     ++count;
   }
+  if (fine) s->timer.begin(secB, s->stream);
   COSL_LAUNCH(ba_chol_backward, 1, 1024, sizeof(double) * ((size_t)ns + CB * CB + CB), s->stream,
               s->d.S, ld, ns, nb, s->d_Linv, s->d_firstBlk, s->d_x);
+  if (fine) s->timer.end(s->stream);
   *nLaunch = count + 1;
   return COSL_OK;
 }
@@ -543,6 +557,13 @@ int launch_blocked_solve(cosl_ba_solver* s, int* nLaunch) {
 int dense_solve(cosl_ba_solver* s) {
   const int ns = s->ns;
   if (ns == 0) return COSL_OK;
+  static const bool noGraph = std::getenv("COSL_BA_NO_GRAPH") != nullptr;
+  if (!s->smallSolve && noGraph) {
+    int nl = 0;
+    COSL_TRY(launch_blocked_solve(s, &nl, s->timer.enabled));
+    COSL_CUDA(cudaGetLastError());
+    return COSL_OK;
+  }
   s->timer.begin(s->secSolve, s->stream);
   if (s->smallSolve) {
     COSL_LAUNCH(ba_chol_small, 1, 256, sizeof(double) * (size_t)ns * ns, s->stream, s->d.S, s->ld,

@@ -9,6 +9,7 @@
 
 #include "common.cuh"
 #include "klt_kernels.cuh"
+#include "klt_track.cuh"
 
 using namespace coslam;
 
@@ -142,7 +143,7 @@ int alloc_group(cosl_klt* g) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, klt_gain_fused, 256, 0);
     g->fusedOK = ok && coop && perSM > 0 && !(g->cfg.compat & COSL_KLT_PASS_KERNELS);
     const int T = F * C;
-    g->fusedBlocks = std::max(1, std::min(div_up(T, 8), nsm * perSM));
+    g->fusedBlocks = std::max(1, std::min(div_up(T, 16), nsm * perSM));  // 16 half-warps per CTA
     COSL_CUDA(cudaMalloc(&g->d_waitset, sizeof(int) * ws.size()));
     COSL_CUDA(cudaMemcpy(g->d_waitset, ws.data(), sizeof(int) * ws.size(), cudaMemcpyHostToDevice));
     COSL_CUDA(cudaMalloc(&g->d_state, sizeof(float4) * 2 * (size_t)T));
@@ -255,8 +256,9 @@ KltTrackParams track_params(const cosl_klt* g, bool strict) {
 int run_tracker(cosl_klt* g) {
   const float4* P0 = g->d_pyr[1 - g->cur];
   const float4* P1 = g->d_pyr[g->cur];
-  const int wpb = 8;  // warps per block
+  const int wpb = 8;  // warps per block (2x2 tracker: one warp per slot)
   dim3 grid(div_up(g->F, wpb), g->C);
+  dim3 gridHalf(div_up(g->F, 16), g->C);  // gain tracker: one half-warp per slot
   g->timer.begin(g->secTrack, g->stream);
   if (g->cfg.trackWithGain && g->fusedOK) {
     KltLevels LV;
@@ -302,7 +304,7 @@ int run_tracker(cosl_klt* g) {
         const bool last =
             (level - g->levelSkip < 0) && (iter == g->cfg.nIterations);
         float4* out = last ? g->d_res : bufs[which];
-        COSL_LAUNCH(klt_gain_pass, grid, wpb * 32, 0, g->stream, P0, P1, g->pyrStride,
+        COSL_LAUNCH(klt_gain_pass, gridHalf, 256, 0, g->stream, P0, P1, g->pyrStride,
                     g->lvOff[level], w, h, g->d_src, in, out, g->d_nbr, dsx, dsy,
                     track_params(g, strict), first);
         in = out;

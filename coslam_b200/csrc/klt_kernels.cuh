@@ -181,109 +181,6 @@ struct KltTrackParams {
   float lambda, delta;
 };
 
-// ------------------------------------------------------------------------------------------
-// One pass of the 3x3 LK solve with gain (klt_tracker_with_gain.cg:42-148): one warp per feature
-// slot, the (2hw+1)^2 window pixels spread over the lanes, ten running sums reduced with warp
-// shuffles, closed-form adjugate solve by every lane, lane 0 stores.
-//   X0buf : positions in the previous frame (features0_tex)
-//   in/out: (x, y, beta) ping-pong (features_tex / render target)
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float4 klt_gain_iteration(const float4* __restrict__ L0,
-                                                     const float4* __restrict__ L1, int w, int h,
-                                                     float X0x, float X0y, float X1x, float X1y,
-                                                     float beta, float nbterm, float dsx, float dsy,
-                                                     const KltTrackParams& P, int lane) {
-  const int hw = P.halfWidth, fwid = 2 * hw + 1, npx = fwid * fwid;
-  const float Wf = (float)P.W, Hf = (float)P.H;
-  float a0 = 0, a1 = 0, a2 = 0, d0 = 0, d1 = 0, d2 = 0, r0 = 0, r1 = 0, r2 = 0, ssd = 0;
-  for (int p = lane; p < npx; p += 32) {
-    const int py = p / fwid, px = p - py * fwid;
-    const float fx = (float)(px - hw), fy = (float)(py - hw);
-    const float3 I0 = klt_sample(L0, w, h, X0x + fx * dsx, X0y + fy * dsy);
-    const float3 I1 = klt_sample(L1, w, h, X1x + fx * dsx, X1y + fy * dsy);
-    const float e = beta * I0.x - I1.x;
-    const float Jx = (beta * I0.y + I1.y) * Wf * 0.5f;
-    const float Jy = (beta * I0.z + I1.z) * Hf * 0.5f;
-    const float g0 = sqrtf(I0.y * I0.y + I0.z * I0.z);
-    const float g1 = sqrtf(I1.y * I1.y + I1.z * I1.z);
-    a0 += Jx * Jx;
-    a1 += Jx * Jy;
-    a2 += Jx * -I0.x;
-    d0 += Jy * Jy;
-    d1 += Jy * -I0.x;
-    d2 += I0.x * I0.x + P.lambda * g0 * g0 + P.delta * 8.0f;
-    r0 += e * Jx;
-    r1 += e * Jy;
-    r2 += -e * I0.x + P.lambda * g0 * (g1 - beta * g0) + P.delta * nbterm;
-    ssd += e * e;
-  }
-  a0 = warp_sum(a0);
-  a1 = warp_sum(a1);
-  a2 = warp_sum(a2);
-  d0 = warp_sum(d0);
-  d1 = warp_sum(d1);
-  d2 = warp_sum(d2);
-  r0 = warp_sum(r0);
-  r1 = warp_sum(r1);
-  r2 = warp_sum(r2);
-  ssd = warp_sum(ssd);
-  // det3x3symm / adjoint3x3symm (klt_tracker_with_gain.cg:12-40)
-  const float a = a0, b = a1, c = a2, d = d0, e = d1, f = d2;
-  float det = a * d * f + 2 * b * c * e;
-  det -= a * e * e + b * b * f + c * c * d;
-  const float rdet = 1.0f / det;
-  const float A = d * f - e * e, B = c * e - b * f, Cc = b * e - c * d;
-  const float D = a * f - c * c, E = b * c - a * e, Fq = a * d - b * b;
-  float ux = (A * r0 + B * r1 + Cc * r2) * rdet;
-  float uy = (B * r0 + D * r1 + E * r2) * rdet;
-  const float ub = (Cc * r0 + E * r1 + Fq * r2) * rdet;
-  X1x += ux;
-  X1y += uy;
-  ux *= Wf;
-  uy *= Hf;
-  const float sqrLen = ux * ux + uy * uy;
-  bool invalid = (det < 0.00001f);
-  invalid = invalid || (ssd > P.ssdThr);
-  invalid = invalid || (sqrLen > P.sqrConv);
-  invalid = invalid || (X1x < P.vr0 || X1y < P.vr1) || (X1x > P.vr2 || X1y > P.vr3);
-  return invalid ? make_float4(-1.f, -1.f, -1.f, 0.f) : make_float4(X1x, X1y, beta + ub, 0.f);
-}
-
-__global__ void __launch_bounds__(256)
-klt_gain_pass(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1, long long pyrStride,
-              long long lvOff, int w, int h, const float4* __restrict__ X0buf,
-              const float4* __restrict__ in, float4* __restrict__ out,
-              const int* __restrict__ nbr, float dsx, float dsy, KltTrackParams P, int firstPass) {
-  const int cam = blockIdx.y;
-  const int slot = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (slot >= P.F) return;
-  const float4* L0 = pyr0 + (size_t)cam * pyrStride + lvOff;
-  const float4* L1 = pyr1 + (size_t)cam * pyrStride + lvOff;
-  const size_t fb = (size_t)cam * P.F;
-  const float4 x0 = X0buf[fb + slot];
-  float4 cur = in[fb + slot];
-  if (firstPass) cur.z = 1.0f;  // gain cleared to 1 before the first pass (v3d_gpuklt.cpp:223-227)
-  const float beta = cur.z;
-  // gain smoothness neighbours (klt_tracker_with_gain.cg:64-75), lanes 0..7 fetch one each
-  float bn = 0.f;
-  if (lane < 8) {
-    float b = firstPass ? 1.0f : in[fb + nbr[slot * 8 + lane]].z;
-    bn = (b < 0.f) ? beta : b;
-  }
-  // s4[k] = bn[k] + bn[4+k] - 2 beta; nbterm = ((s0+s1)+s2)+s3
-  const float hi = __shfl_sync(0xffffffffu, bn, (lane & 3) + 4);
-  const float s4 = bn + hi - 2.0f * beta;
-  const float s0 = __shfl_sync(0xffffffffu, s4, 0), s1 = __shfl_sync(0xffffffffu, s4, 1);
-  const float s2 = __shfl_sync(0xffffffffu, s4, 2), s3 = __shfl_sync(0xffffffffu, s4, 3);
-  const float nbterm = ((s0 + s1) + s2) + s3;
-  const bool pre_invalid = (cur.x < 0.f) || (x0.x < 0.f);
-  float4 res = klt_gain_iteration(L0, L1, w, h, x0.x, x0.y, cur.x, cur.y, beta, nbterm, dsx, dsy,
-                                  P, lane);
-  if (pre_invalid) res = make_float4(-1.f, -1.f, -1.f, 0.f);
-  if (lane == 0) out[fb + slot] = res;
-}
-
 struct KltLevels {
   int n;             // number of levels visited
   int level[8];
@@ -291,100 +188,6 @@ struct KltLevels {
   long long off[8];
   float mult[8];
 };
-
-// ------------------------------------------------------------------------------------------
-// All passes of the gain tracker in ONE persistent cooperative kernel (replaces the reference's
-// levels x iterations draw calls, v3d_gpuklt.cpp:254-295, without changing the pass-synchronous
-// semantics).  The only coupling between feature slots is the gain-smoothness term, which reads
-// the beta of <= 8 neighbour slots produced by the PREVIOUS pass.  Instead of a grid-wide barrier
-// per pass, every slot publishes (x, y, beta) of pass p into a parity double buffer followed by a
-// version number; a slot starts pass p as soon as the slots it reads from have published p-1.  A
-// slot may overwrite its pass p-1 record (when publishing p+1) only after all slots that read it
-// have consumed it, which is guaranteed because it waits for the pass-p record of its readers too
-// (wait set = neighbours + reverse neighbours, symmetric closure built on the host).
-// Work item = (camera, slot); warp w owns items w, w+G, ... and walks the passes in order, so the
-// globally least advanced item can always run: no deadlock as long as all warps are co-resident
-// (cooperative launch).
-//   state[2][T] float4 (x, y, beta, -), ver[2][T] int (pass number of the record)
-//   waitset[F][16]: first 8 = neighbours (values + versions), last 8 = reverse neighbours or -1
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int ld_volatile_int(const int* p) {
-  int v;
-  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-
-__global__ void __launch_bounds__(256)
-klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
-               long long pyrStride, KltLevels LV, int nIter, const float4* __restrict__ X0buf,
-               float4* __restrict__ state, int* __restrict__ ver, const int* __restrict__ waitset,
-               float4* __restrict__ out, int C, KltTrackParams Plax, KltTrackParams Pstrict,
-               int verBase) {
-  const int lane = threadIdx.x & 31;
-  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int G = gridDim.x * (blockDim.x >> 5);
-  const int F = Plax.F;
-  const int T = C * F;
-  const int nPass = LV.n * nIter;
-  for (int pass = 1; pass <= nPass; ++pass) {
-    const int li = (pass - 1) / nIter, it = (pass - 1) - li * nIter + 1;
-    const int w = LV.w[li], h = LV.h[li];
-    const float dsx = 1.0f / (float)w, dsy = 1.0f / (float)h;
-    // thresholds are lax except on the last iteration of each level (v3d_gpuklt.cpp:266-279)
-    const bool strict = (it == nIter) && (it != 1);
-    const int rd = (pass - 1) & 1, wr = pass & 1;
-    for (int item = warp; item < T; item += G) {
-      const int cam = item / F, slot = item - cam * F;
-      const float4* L0 = pyr0 + (size_t)cam * pyrStride + LV.off[li];
-      const float4* L1 = pyr1 + (size_t)cam * pyrStride + LV.off[li];
-      const float4 x0 = X0buf[item];
-      float4 cur;
-      float bn = 0.f;
-      if (pass == 1) {
-        cur = make_float4(x0.x, x0.y, 1.0f, 0.f);  // X1 <- X0, gain cleared to 1 (:223-227)
-        if (lane < 8) bn = 1.0f;
-      } else {
-        // wait for the pass-(p-1) records of everything this slot reads or is read by
-        if (lane < 16) {
-          const int nb = waitset[slot * 16 + lane];
-          if (nb >= 0) {
-            const int* vp = ver + (size_t)rd * T + (size_t)cam * F + nb;
-            const int need = verBase + pass - 1;
-            while (ld_volatile_int(vp) < need) __nanosleep(20);
-          }
-        }
-        __syncwarp();
-        __threadfence();
-        cur = __ldcg(&state[(size_t)rd * T + item]);
-        if (lane < 8) {
-          const int nb = waitset[slot * 16 + lane];
-          bn = __ldcg(&state[(size_t)rd * T + (size_t)cam * F + nb]).z;
-        }
-      }
-      const float beta = cur.z;
-      if (lane < 8) bn = (bn < 0.f) ? beta : bn;
-      const float hi = __shfl_sync(0xffffffffu, bn, (lane & 3) + 4);
-      const float s4 = bn + hi - 2.0f * beta;
-      const float s0 = __shfl_sync(0xffffffffu, s4, 0), s1 = __shfl_sync(0xffffffffu, s4, 1);
-      const float s2 = __shfl_sync(0xffffffffu, s4, 2), s3 = __shfl_sync(0xffffffffu, s4, 3);
-      const float nbterm = ((s0 + s1) + s2) + s3;
-      const bool pre_invalid = (cur.x < 0.f) || (x0.x < 0.f);
-      float4 res = make_float4(-1.f, -1.f, -1.f, 0.f);
-      if (!pre_invalid)  // warp-uniform
-        res = klt_gain_iteration(L0, L1, w, h, x0.x, x0.y, cur.x, cur.y, beta, nbterm, dsx, dsy,
-                                 strict ? Pstrict : Plax, lane);
-      if (lane == 0) {
-        if (pass == nPass) out[item] = res;
-        state[(size_t)wr * T + item] = res;
-        __threadfence();
-        asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(ver + (size_t)wr * T + item),
-                     "r"(verBase + pass)
-                     : "memory");
-      }
-      __syncwarp();
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------
 // 2x2 LK (klt_tracker.cg:24-132): all levels and iterations inside one kernel, one warp per

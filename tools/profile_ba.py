@@ -13,5 +13,9 @@ if which == "c4":
 else:
     prob, _ = synth.make_ba_scene(4, 5, 20000, 1280, 720, seed=synth.BASE_SEED + 3, m_con=8, n_con=2)
 s = api.BaSolver(prob, BaOptions.defaults())
+s.run_fixed(2)
+s.reset()
+s.profile_enable(True)
 info = s.run_fixed(trials)
+print({k: (round(v[0], 3), v[1], round(1e3 * v[0] / max(1, v[1]), 2)) for k, v in s.timers().items()})
 print(which, "trials", info[9], "cost", info[0], "->", info[1], "launches", api.kernel_launch_count())
