@@ -4,6 +4,7 @@
 // frame costs one H2D copy per camera, one D2H copy of the feature table and one synchronise.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -45,8 +46,8 @@ struct cosl_klt {
   float4* h_present = nullptr;
   bool havePrev = false;
   // persistent fused gain tracker (klt_gain_fused)
-  float4* d_state = nullptr;  // [2][C*F]
-  int* d_ver = nullptr;       // [2][C*F]
+  float4* d_state = nullptr;             // [C*F]
+  unsigned long long* d_ver = nullptr;   // [2][C*F] (pass << 32 | beta bits)
   int* d_waitset = nullptr;   // [F][16]
   bool fusedOK = false;
   int fusedBlocks = 0;
@@ -140,15 +141,15 @@ int alloc_group(cosl_klt* g) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, klt_gain_fused, 256, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, klt_gain_fused, KLT_FUSED_THREADS, 0);
     g->fusedOK = ok && coop && perSM > 0 && !(g->cfg.compat & COSL_KLT_PASS_KERNELS);
     const int T = F * C;
-    g->fusedBlocks = std::max(1, std::min(div_up(T, 16), nsm * perSM));  // 16 half-warps per CTA
+    g->fusedBlocks = std::max(1, std::min(div_up(T, KLT_FUSED_THREADS / 16), nsm * perSM));
     COSL_CUDA(cudaMalloc(&g->d_waitset, sizeof(int) * ws.size()));
     COSL_CUDA(cudaMemcpy(g->d_waitset, ws.data(), sizeof(int) * ws.size(), cudaMemcpyHostToDevice));
     COSL_CUDA(cudaMalloc(&g->d_state, sizeof(float4) * 2 * (size_t)T));
-    COSL_CUDA(cudaMalloc(&g->d_ver, sizeof(int) * 2 * (size_t)T));
-    COSL_CUDA(cudaMemset(g->d_ver, 0, sizeof(int) * 2 * (size_t)T));
+    COSL_CUDA(cudaMalloc(&g->d_ver, sizeof(unsigned long long) * 2 * (size_t)T));
+    COSL_CUDA(cudaMemset(g->d_ver, 0, sizeof(unsigned long long) * 2 * (size_t)T));
     g->verBase = 0;
   }
   // dynamic shared memory opt-ins
@@ -274,18 +275,21 @@ int run_tracker(cosl_klt* g) {
     int nIter = g->cfg.nIterations, C = g->C;
     const int nPass = LV.n * nIter;
     if (g->verBase > 2000000000 - 2 * nPass) {  // version wrap: restart the counters
-      COSL_CUDA(cudaMemsetAsync(g->d_ver, 0, sizeof(int) * 2 * (size_t)g->F * g->C, g->stream));
+      COSL_CUDA(cudaMemsetAsync(g->d_ver, 0, sizeof(unsigned long long) * 2 * (size_t)g->F * g->C,
+                                g->stream));
       g->verBase = 0;
     }
     long long pyrStride = g->pyrStride;
     KltTrackParams Plax = track_params(g, false), Pstrict = track_params(g, true);
     int verBase = g->verBase;
+    static const bool noSync = std::getenv("COSL_KLT_NOSYNC") != nullptr;  // timing experiment only
+    if (noSync) verBase = -1000000000;
     void* args[] = {(void*)&P0,          (void*)&P1,     (void*)&pyrStride, (void*)&LV,
                     (void*)&nIter,       (void*)&g->d_src, (void*)&g->d_state, (void*)&g->d_ver,
                     (void*)&g->d_waitset, (void*)&g->d_res, (void*)&C,        (void*)&Plax,
                     (void*)&Pstrict,     (void*)&verBase};
     COSL_CUDA(cudaLaunchCooperativeKernel((const void*)klt_gain_fused, dim3(g->fusedBlocks),
-                                          dim3(256), args, 0, g->stream));
+                                          dim3(KLT_FUSED_THREADS), args, 0, g->stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     g->verBase += nPass;
   } else if (g->cfg.trackWithGain) {

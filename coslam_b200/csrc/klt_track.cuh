@@ -203,28 +203,36 @@ klt_gain_pass(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1, 
 
 // ------------------------------------------------------------------------------------------
 // All passes in one persistent cooperative launch.
-//   state[2][T] float4 (x, y, beta, -), ver[2][T] int (pass number of the record)
+//   rec[2][T] u64 = (pass number << 32) | float_bits(beta): value and version travel in ONE naturally
+//   atomic 8-byte word, so publishing needs no fence and a reader gets beta with the poll itself;
+//   state[T] float4 holds (x, y, beta) of items that are not register-resident
 //   waitset[F][16]: first 8 = neighbours (values + versions), last 8 = reverse neighbours or -1
 // Work item = (camera, slot); half-warp q (global index) owns items q, q + Q, ...; the first item
 // of a half-warp uses the shared-memory tile, further items (only when T > Q) the global path.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ int ld_volatile_int(const int* p) {
-  int v;
-  asm volatile("ld.volatile.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
-__global__ void __launch_bounds__(256, 4)
+constexpr int KLT_FUSED_THREADS = 128;  // 8 half-warps per CTA
+
+__global__ void __launch_bounds__(KLT_FUSED_THREADS, 7)
 klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
                long long pyrStride, KltLevels LV, int nIter, const float4* __restrict__ X0buf,
-               float4* __restrict__ state, int* __restrict__ ver, const int* __restrict__ waitset,
+               float4* __restrict__ state, unsigned long long* __restrict__ rec,
+               const int* __restrict__ waitset,
                float4* __restrict__ out, int C, KltTrackParams Plax, KltTrackParams Pstrict,
                int verBase) {
-  __shared__ float4 s_tile[16][KLT_TW * KLT_TW];  // one tile per half-warp of the CTA
+  __shared__ float4 s_tile[KLT_FUSED_THREADS / 16][KLT_TW * KLT_TW];  // one tile per half-warp
   const int hl = threadIdx.x & 15, halfBase = threadIdx.x & 16;
   const int halfInBlock = threadIdx.x >> 4;
-  const int q = blockIdx.x * 16 + halfInBlock;
-  const int Q = gridDim.x * 16;
+  const int q = blockIdx.x * (KLT_FUSED_THREADS / 16) + halfInBlock;
+  const int Q = gridDim.x * (KLT_FUSED_THREADS / 16);
   const int F = Plax.F;
   const int T = C * F;
   const int hw = Plax.halfWidth, fwid = 2 * hw + 1, npx = fwid * fwid;
@@ -263,19 +271,23 @@ klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
           cur = make_float4(x0.x, x0.y, 1.0f, 0.f);  // X1 <- X0, gain cleared to 1 (:223-227)
           if (hl < 8) bn = 1.0f;
         } else {
-          // wait for the pass-(p-1) records of everything this slot reads or is read by
+          // wait for the pass-(p-1) records of everything this slot reads or is read by; the
+          // first 8 entries also deliver the neighbour gains
           if (active) {
             const int nb = waitset[slot * 16 + hl];
             if (nb >= 0) {
-              const int* vp = ver + (size_t)rd * T + (size_t)cam * F + nb;
+              const unsigned long long* rp = rec + (size_t)rd * T + (size_t)cam * F + nb;
               const int need = verBase + pass - 1;
-              while (ld_volatile_int(vp) < need) __nanosleep(32);
+              unsigned long long v = ld_relaxed_u64(rp);
+              while ((int)(v >> 32) < need) {
+                __nanosleep(20);
+                v = ld_relaxed_u64(rp);
+              }
+              bn = __uint_as_float((unsigned)v);
             }
           }
           __syncwarp();
-          __threadfence();
-          cur = (staged) ? cur0 : __ldcg(&state[(size_t)rd * T + item]);
-          if (hl < 8) bn = __ldcg(&state[(size_t)rd * T + (size_t)cam * F + waitset[slot * 16 + hl]]).z;
+          cur = (staged) ? cur0 : __ldcg(&state[item]);
         }
         const float beta = cur.z;
         const float nbterm = klt_nbterm(bn, beta, hl, halfBase);
@@ -332,11 +344,10 @@ klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
         if (staged) cur0 = res;
         if (hl == 0 && active) {
           if (pass == LV.n * nIter) out[item] = res;
-          state[(size_t)wr * T + item] = res;
-          __threadfence();
-          asm volatile("st.volatile.global.s32 [%0], %1;" ::"l"(ver + (size_t)wr * T + item),
-                       "r"(verBase + pass)
-                       : "memory");
+          if (!staged) __stcg(&state[item], res);
+          st_relaxed_u64(rec + (size_t)wr * T + item,
+                         ((unsigned long long)(unsigned)(verBase + pass) << 32) |
+                             (unsigned long long)__float_as_uint(res.z));
         }
         __syncwarp();
       }
