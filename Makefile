@@ -12,6 +12,8 @@ LIB := coslam_b200/libcoslam_b200.so
 all: $(LIB) oracle
 
 $(CSRC)/pose.o: NVFLAGS += -fmad=false
+# LK solve is tolerance-parity: approximate sqrt/div there; bit-exact kernels use explicit _rn intrinsics
+$(CSRC)/klt.o: NVFLAGS += -prec-sqrt=false -prec-div=false
 
 $(CSRC)/%.o: $(CSRC)/%.cu $(wildcard $(CSRC)/*.cuh) include/coslam_b200.h
 	$(NVCC) $(NVFLAGS) -c $< -o $@ 2> $(@:.o=.ptxas.log) || (cat $(@:.o=.ptxas.log); exit 1)

@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "klt_kernels.cuh"
 #include "klt_track.cuh"
+#include "klt_front.cuh"
 
 using namespace coslam;
 
@@ -45,6 +46,7 @@ struct cosl_klt {
   int* h_counters = nullptr;
   float4* h_present = nullptr;
   bool havePrev = false;
+  bool cornValid = false;  // cornerness of the current frame already produced by klt_front
   // persistent fused gain tracker (klt_gain_fused)
   float4* d_state = nullptr;             // [C*F]
   unsigned long long* d_ver = nullptr;   // [2][C*F] (pass << 32 | beta bits)
@@ -153,6 +155,8 @@ int alloc_group(cosl_klt* g) {
     g->verBase = 0;
   }
   // dynamic shared memory opt-ins
+  COSL_CUDA(cudaFuncSetAttribute(klt_front, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(FrontSmem)));
   COSL_CUDA(cudaFuncSetAttribute(klt_select_refill, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  g->smemKeys * (int)sizeof(unsigned long long)));
   const int TS = NM_T + 2 * r;
@@ -209,13 +213,18 @@ int upload_images(cosl_klt* g, const uint8_t* const* imgs, size_t pitch, cudaMem
 }
 
 // PyramidWithDerivativesCreator::buildPyramidForGrayscaleImage (v3d_gpupyramid.cpp:366-429)
-int build_pyramid(cosl_klt* g) {
+int build_pyramid(cosl_klt* g, bool wantCorn) {
   float4* P = g->d_pyr[g->cur];
   g->timer.begin(g->secPyr, g->stream);
-  dim3 g0(div_up(g->W, P0_TW), div_up(g->H, P0_TH), g->C);
-  COSL_LAUNCH(klt_pyr_level0, g0, 256, 0, g->stream, g->d_img, g->imgPitch, g->imgStride, P,
-              g->pyrStride, g->W, g->H);
-  for (int l = 1; l < g->L; ++l) {
+  // level 0 + level 1 + (optionally) the detector's cornerness map in one pass over the image
+  const float Wf = (float)g->W, Hf = (float)g->H, mg = g->detectMargin;
+  dim3 g0(div_up(g->W, FR_TW), div_up(g->H, FR_TH), g->C);
+  COSL_LAUNCH(klt_front, g0, 256, sizeof(FrontSmem), g->stream, g->d_img, g->imgPitch, g->imgStride,
+              P, g->pyrStride, g->L > 1 ? g->lvOff[1] : 0, g->d_corn, g->W, g->H, g->L > 1 ? 1 : 0,
+              wantCorn ? 1 : 0, g->cfg.minCornerness, mg / Wf, mg / Hf, 1.0f - mg / Wf,
+              1.0f - mg / Hf);
+  g->cornValid = wantCorn;
+  for (int l = 2; l < g->L; ++l) {
     dim3 gl(div_up(g->lvW[l], PD_TW), div_up(g->lvH[l], PD_TH), g->C);
     COSL_LAUNCH(klt_pyr_down, gl, 256, 0, g->stream, P + g->lvOff[l - 1], P + g->lvOff[l],
                 g->pyrStride, g->lvW[l - 1], g->lvH[l - 1], g->lvW[l], g->lvH[l]);
@@ -354,9 +363,12 @@ int run_status(cosl_klt* g) {
 int run_detector(cosl_klt* g, int mode, int nPresentExt) {
   const float Wf = (float)g->W, Hf = (float)g->H, mg = g->detectMargin;
   g->timer.begin(g->secDetect, g->stream);
-  dim3 gc(div_up(g->W, DC_TW), div_up(g->H, DC_TH), g->C);
-  COSL_LAUNCH(klt_cornerness, gc, 256, 0, g->stream, g->d_pyr[g->cur], g->pyrStride, g->d_corn,
-              g->W, g->H, g->cfg.minCornerness, mg / Wf, mg / Hf, 1.0f - mg / Wf, 1.0f - mg / Hf);
+  if (!g->cornValid) {
+    dim3 gc(div_up(g->W, DC_TW), div_up(g->H, DC_TH), g->C);
+    COSL_LAUNCH(klt_cornerness, gc, 256, 0, g->stream, g->d_pyr[g->cur], g->pyrStride, g->d_corn,
+                g->W, g->H, g->cfg.minCornerness, mg / Wf, mg / Hf, 1.0f - mg / Wf, 1.0f - mg / Hf);
+  }
+  g->cornValid = false;  // the suppression below modifies the map
   if (mode == 1) {
     dim3 gs(div_up(g->F, 256), g->C);
     COSL_LAUNCH(klt_suppress, gs, 256, 0, g->stream, g->d_res, g->F, g->F, g->d_corn, g->W, g->H);
@@ -399,8 +411,8 @@ int advance(cosl_klt* g) {
   return COSL_OK;
 }
 
-int do_track(cosl_klt* g) {
-  COSL_TRY(build_pyramid(g));
+int do_track(cosl_klt* g, bool wantCorn = false) {
+  COSL_TRY(build_pyramid(g, wantCorn));
   COSL_TRY(run_tracker(g));
   COSL_TRY(zero_counters(g));
   COSL_TRY(run_status(g));
@@ -408,13 +420,13 @@ int do_track(cosl_klt* g) {
 }
 
 int do_redetect(cosl_klt* g) {
-  COSL_TRY(do_track(g));
+  COSL_TRY(do_track(g, true));
   COSL_TRY(run_detector(g, 1, 0));
   return COSL_OK;
 }
 
 int do_detect(cosl_klt* g, int nPresentExt) {
-  COSL_TRY(build_pyramid(g));
+  COSL_TRY(build_pyramid(g, true));
   COSL_TRY(zero_counters(g));
   COSL_TRY(run_detector(g, 0, nPresentExt));
   return COSL_OK;

@@ -83,7 +83,7 @@ __device__ __forceinline__ float3 klt_fetch_tile(const float4* __restrict__ tile
                                                  const float4* __restrict__ lv, int w, int h,
                                                  const KltSamplePos& p) {
   const int a = p.xi - tx0, b = p.yi - ty0;
-  if (a >= 0 && a + 1 < KLT_TW && b >= 0 && b + 1 < KLT_TW) {
+  if ((unsigned)a < (unsigned)(KLT_TW - 1) && (unsigned)b < (unsigned)(KLT_TW - 1)) {
     const float4* q = tile + b * KLT_TW + a;
     return klt_lerp4(q[0], q[1], q[KLT_TW], q[KLT_TW + 1], p.ax, p.ay);
   }
@@ -244,6 +244,15 @@ klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
 
   // state of the FIRST owned item lives in registers across passes
   float3 I0r[KLT_ROUNDS];
+  // window offsets of this lane's pixels, hoisted out of every loop (no integer division inside)
+  float fxr[KLT_ROUNDS], fyr[KLT_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < KLT_ROUNDS; ++r) {
+    const int p = min(hl + 16 * r, npx - 1);
+    const int py = p / fwid, px = p - py * fwid;
+    fxr[r] = (float)(px - hw);
+    fyr[r] = (float)(py - hw);
+  }
   float4 cur0 = make_float4(-1.f, -1.f, -1.f, 0.f);
   int tx0 = 0, ty0 = 0;
 
@@ -297,8 +306,7 @@ klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
 #pragma unroll
           for (int r = 0; r < KLT_ROUNDS; ++r) {
             const int p = hl + 16 * r;
-            const int py = p / fwid, px = p - py * fwid;
-            const float fx = (float)(px - hw), fy = (float)(py - hw);
+            const float fx = fxr[r], fy = fyr[r];
             I0r[r] = (p < npx && !pre_invalid)
                          ? klt_fetch_global(L0, w, h, klt_sample_pos(w, h, x0.x + fx * dsx, x0.y + fy * dsy))
                          : make_float3(0.f, 0.f, 0.f);
@@ -322,8 +330,7 @@ klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
             for (int r = 0; r < KLT_ROUNDS; ++r) {
               const int p = hl + 16 * r;
               if (p < npx) {
-                const int py = p / fwid, px = p - py * fwid;
-                const float fx = (float)(px - hw), fy = (float)(py - hw);
+                const float fx = fxr[r], fy = fyr[r];
                 const float3 I1 = klt_fetch_tile(tile, tx0, ty0, L1, w, h,
                                                  klt_sample_pos(w, h, cur.x + fx * dsx, cur.y + fy * dsy));
                 klt_acc_pixel(A, I0r[r], I1, beta, nbterm, Wf, Hf, Plax.lambda, Plax.delta);
