@@ -167,7 +167,7 @@ def run_reference(args):
                "e2e": {"value": info[9] / ba_dt, "unit": "LM-iter/s", "h2d_bytes_per_step": 0,
                        "d2h_bytes_per_step": 0}},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 # =================================================================== CUDA arm
@@ -310,7 +310,7 @@ def run_cuda(args):
             line["cpu_baseline"] = cpu
         if ba is not None:
             line["ba"] = ba
-        print(json.dumps(line))
+        emit(line)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -441,7 +441,20 @@ def run_ba(args, api, synth, BaOptions, torch, dist, rank, world, local, barrier
     return out
 
 
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, C-level prints of
+    libraries) was redirected to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # fd 1 -> stderr for the rest of the process
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

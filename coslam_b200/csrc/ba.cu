@@ -90,6 +90,10 @@ struct cosl_ba_solver {
   double *d_y = nullptr, *d_x = nullptr;
   double* d_Linv = nullptr;   // [nb][64*64] inverses of the diagonal Cholesky blocks
   int* d_firstBlk = nullptr;
+  int* d_rowEnd = nullptr;        // [nb] end row (exclusive) of block column J's envelope
+  long long* d_envOff = nullptr;  // [nb + 1] packed offsets for the enveloped all-reduce
+  double* d_envBuf = nullptr;
+  long long envCount = 0;
   double* d_sc = nullptr;
   unsigned char* d_outlier = nullptr;
   BaPairItem* d_items = nullptr;
@@ -203,7 +207,8 @@ void free_solver(cosl_ba_solver* s) {
   void* bufs[] = {s->d_camK, s->d_camR0, s->d_pa, s->d_na, s->d_dpa, s->d_pb, s->d_nb, s->d_dpb,
                   s->d_cam, s->d_pt, s->d_cobs, s->d_ccam, s->d_xy, s->d_wgt, s->d_ptr, s->d_W,
                   s->d_V, s->d_eb, s->d_Uea, s->d_Srhs, s->d_y, s->d_x, s->d_sc, s->d_outlier,
-                  s->d_items, s->d_entries, s->d_Linv, s->d_firstBlk};
+                  s->d_items, s->d_entries, s->d_Linv, s->d_firstBlk, s->d_rowEnd, s->d_envOff,
+                  s->d_envBuf};
   if (s->solveGraph) cudaGraphExecDestroy(s->solveGraph);
   for (void* b : bufs) cudaFree(b);
   if (s->h_sc) cudaFreeHost(s->h_sc);
@@ -356,6 +361,22 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
     }
     COSL_CUDA(cudaMemcpy(s->d_firstBlk, s->firstBlk.data(), sizeof(int) * std::max(1, nbk),
                          cudaMemcpyHostToDevice));
+    // envelope of block COLUMN J: rows [J*CB, rowEnd[J]) (the small solve keeps everything dense)
+    std::vector<int> rowEnd(std::max(1, nbk), 0);
+    std::vector<long long> envOff(nbk + 2, 0);
+    for (int J = 0; J < nbk; ++J) {
+      rowEnd[J] = std::min(s->ns, (s->lastBlk[J] + 1) * CB);
+      envOff[J + 1] = envOff[J] + (long long)std::min(CB, s->ns - J * CB) * (rowEnd[J] - J * CB);
+    }
+    s->envCount = envOff[nbk] + s->ns;
+    COSL_TRY(dev_alloc(&s->d_rowEnd, (size_t)std::max(1, nbk)));
+    COSL_TRY(dev_alloc(&s->d_envOff, (size_t)nbk + 2));
+    COSL_TRY(dev_alloc(&s->d_envBuf, (size_t)std::max<long long>(1, s->envCount)));
+    COSL_CUDA(cudaMemcpy(s->d_rowEnd, rowEnd.data(), sizeof(int) * std::max(1, nbk),
+                         cudaMemcpyHostToDevice));
+    COSL_CUDA(cudaMemcpy(s->d_envOff, envOff.data(), sizeof(long long) * (nbk + 1),
+                         cudaMemcpyHostToDevice));
+    COSL_CUDA(cudaMemset(s->d_Srhs, 0, sizeof(double) * (size_t)s->ld * (s->ns ? s->ns : 1)));
   }
   COSL_TRY(dev_alloc(&s->d_y, (size_t)s->ns));
   COSL_TRY(dev_alloc(&s->d_x, (size_t)s->ns));
@@ -412,9 +433,9 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   if (s->smallSolve && smallBytes > 32 * 1024)
     COSL_CUDA(cudaFuncSetAttribute(ba_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smallBytes));
-  COSL_CUDA(cudaFuncSetAttribute(ba_chol_potf2_inv, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 BA_CHOL_SMEM));
   COSL_CUDA(cudaFuncSetAttribute(ba_chol_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 BA_CHOL_SMEM));
+  COSL_CUDA(cudaFuncSetAttribute(ba_chol_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  BA_CHOL_SMEM));
   {
     const size_t bw = sizeof(double) * ((size_t)s->ns + CB * CB + CB);
@@ -527,7 +548,7 @@ int launch_blocked_solve(cosl_ba_solver* s, int* nLaunch, bool fine = false) {
     const int k0 = k * CB, bs = std::min(CB, ns - k0);
     double* Linv = s->d_Linv + (size_t)k * CB * CB;
     if (fine) s->timer.begin(secP, s->stream);
-    COSL_LAUNCH(ba_chol_potf2_inv, 1, 1024, BA_CHOL_SMEM, s->stream, s->d.S, ld, k0, bs, Linv, s->d_sc,
+    COSL_LAUNCH(ba_chol_potf2_inv, 1, 256, 0, s->stream, s->d.S, ld, k0, bs, Linv, s->d_sc,
                 (int)SC_FAIL);
     if (fine) s->timer.end(s->stream);
     const int nAct = s->lastBlk[k] - k;
@@ -539,7 +560,7 @@ int launch_blocked_solve(cosl_ba_solver* s, int* nLaunch, bool fine = false) {
                   extraBlk, Linv);
       if (fine) s->timer.end(s->stream);
       if (fine) s->timer.begin(secS, s->stream);
-      COSL_LAUNCH(ba_chol_syrk, dim3(nT, nT), 256, 0, s->stream, s->d.S, ld, ns, nrows, k0, bs, k,
+      COSL_LAUNCH(ba_chol_syrk, dim3(nT, nT), 256, BA_CHOL_SMEM, s->stream, s->d.S, ld, ns, nrows, k0, bs, k,
                   nAct, extraBlk);
       if (fine) s->timer.end(s->stream);
       count += 2;
@@ -602,14 +623,20 @@ int solve_trial(cosl_ba_solver* s, double mu, bool* solved) {
   s->timer.begin(s->secSchur, s->stream);
   const long long ns = s->ns;
   if (ns) {
-    COSL_LAUNCH(ba_init_S, (unsigned)div_up64((long long)s->ld * ns, 256), 256, 0, s->stream, s->d, mu,
-                r0 ? 1 : 0);
+    COSL_LAUNCH(ba_init_S, s->nb, 256, 0, s->stream, s->d, mu, r0 ? 1 : 0, s->d_rowEnd);
     if (s->nItems)
       COSL_LAUNCH(ba_schur_pairs, div_up(s->nItems, 4), 128, 0, s->stream, s->d, s->d_items,
                   s->nItems, s->d_entries, mu);
   }
   s->timer.end(s->stream);
-  if (ns) COSL_TRY(allreduce(s, s->d_Srhs, (size_t)s->ld * (size_t)ns, ncclSum));
+  if (ns && multi(s)) {
+    // only the envelope travels: pack -> one ncclAllReduce -> unpack
+    COSL_LAUNCH(ba_env_pack, s->nb + 1, 256, 0, s->stream, s->d.S, s->ld, s->ns, s->d_rowEnd,
+                s->d_envOff, s->nb, s->d_envBuf, 0, s->d.S);
+    COSL_TRY(allreduce(s, s->d_envBuf, (size_t)s->envCount, ncclSum));
+    COSL_LAUNCH(ba_env_pack, s->nb + 1, 256, 0, s->stream, s->d.S, s->ld, s->ns, s->d_rowEnd,
+                s->d_envOff, s->nb, s->d_envBuf, 1, s->d.S);
+  }
   COSL_TRY(dense_solve(s));
   s->timer.begin(s->secBack, s->stream);
   COSL_LAUNCH(ba_cam_update, div_up(6 * s->m, 256), 256, 0, s->stream, s->d, s->d_pa, s->d_x,

@@ -86,74 +86,84 @@ ba_chol_small(double* __restrict__ S, int ld, int ns, double* __restrict__ xout,
 }
 
 // ------------------------------------------------------------------------------------------
-// Diagonal block: Cholesky factor (written back into S) and its inverse Linv (dense bs x bs,
-// row-major: Linv[r * CB + c], lower triangular).  1024 threads: tx = row, ty = column phase.
+// Diagonal block: Cholesky factor (written back into S) and its inverse Linv (dense, row-major
+// Linv[r * CB + c], lower triangular).  256 threads, register resident:
+//   factor : thread (i = tid & 63, g = tid >> 6) owns row i, columns j == g (mod 4) in 16
+//            registers; per pivot the raw column goes through a double-buffered shared vector,
+//            every thread scales it itself (one rsqrt per thread, no second barrier) and applies
+//            the rank-1 update to its registers: ONE barrier per pivot, all loops fully unrolled
+//            so the register arrays are statically indexed;
+//   inverse: thread (c = tid >> 2, gg = tid & 3) owns X[p][c], p == gg (mod 4); row by row forward
+//            substitution with a 4-lane shuffle reduction.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(256)
 ba_chol_potf2_inv(double* __restrict__ S, int ld, int k0, int bs, double* __restrict__ Linv,
                   double* __restrict__ sc, int scFail) {
-  // dynamic shared memory: two 64 x 65 matrices (BA_CHOL_SMEM bytes); the inverse X reuses the
-  // working copy A once the factorisation is finished
-  extern __shared__ double s_dyn[];
-  double (*A)[CB + 1] = reinterpret_cast<double (*)[CB + 1]>(s_dyn);
-  double (*Lm)[CB + 1] = reinterpret_cast<double (*)[CB + 1]>(s_dyn + CB * (CB + 1));
-  double (*X)[CB + 1] = A;
+  __shared__ double colraw[2][CB];
+  __shared__ double rdiag[CB];
+  __shared__ double Lm[CB][CB + 1];
   __shared__ int s_fail;
   const int tid = threadIdx.x;
-  const int tx = tid & 63, ty = tid >> 6;  // 64 rows x 16 phases
-  for (int t = tid; t < CB * CB; t += 1024) {
-    const int j = t >> 6, i = t & 63;
-    A[i][j] = (i < bs && j < bs && i >= j) ? S[(size_t)(k0 + j) * ld + k0 + i] : ((i == j) ? 1.0 : 0.0);
-    Lm[i][j] = 0.0;
-  }
   if (tid == 0) s_fail = 0;
-  __syncthreads();
-  const int lane = tid & 31;
-  for (int k = 0; k < CB; ++k) {
-    double d = A[k][k];
-    if (!(d > 0) || !isfinite(d)) {  // uniform across the CTA
-      if (tid == 0) s_fail = 1;
-      d = 1.0;
-    }
-    // one fp64 division / square root per WARP (not per thread: the fp64 pipe is only 64 wide)
-    double inv_d = 0, rsd = 0;
-    if (lane == 0) {
-      rsd = rsqrt(d);     // short dependency chain: the pivot is on the critical path
-      inv_d = rsd * rsd;
-    }
-    inv_d = __shfl_sync(0xffffffffu, inv_d, 0);
-    rsd = __shfl_sync(0xffffffffu, rsd, 0);
-    const double lik = A[tx][k];
-    const double lik_s = lik * inv_d;
-    if (tx > k)
-      for (int j = k + 1 + ty; j <= tx; j += 16) A[tx][j] -= lik_s * A[j][k];
-    if (ty == 0 && tx >= k) Lm[tx][k] = (tx == k) ? d * rsd : lik * rsd;
-    __syncthreads();
-  }
-  // inverse of the lower triangular factor, column j by 16 cooperating threads (same half-warp)
-  for (int t = tid; t < CB * CB; t += 1024) X[t >> 6][t & 63] = 0.0;
-  __syncthreads();
-  if (tid < CB) X[tid][tid] = 1.0 / Lm[tid][tid];
-  __syncthreads();
   {
-    const int j = tid >> 4, q = tid & 15;  // 64 columns x 16 lanes
-    // uniform trip count for the whole warp (two columns per warp), rows i <= j are idle
-    for (int i = 1; i < CB; ++i) {
-      double part = 0;
-      if (i > j)
-        for (int p = j + q; p < i; p += 16) part += Lm[i][p] * X[p][j];
+    const int i = tid & 63, g = tid >> 6;
+    double a[16];
 #pragma unroll
-      for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o, 16);
-      if (q == 0 && i > j) X[i][j] = -part * X[i][i];
-      __syncwarp();
+    for (int q = 0; q < 16; ++q) {
+      const int j = g + 4 * q;
+      a[q] = (i < bs && j < bs && j <= i) ? S[(size_t)(k0 + j) * ld + k0 + i] : ((i == j) ? 1.0 : 0.0);
+    }
+#pragma unroll
+    for (int k = 0; k < CB; ++k) {
+      const int qk = k >> 2, gk = k & 3, buf = k & 1;
+      if (g == gk) colraw[buf][i] = a[qk];  // (a[] stays in registers: static indices only)
+      __syncthreads();
+      double d = colraw[buf][k];
+      if (!(d > 0) || !isfinite(d)) {
+        if (tid == 0) s_fail = 1;
+        d = 1.0;
+      }
+      const double rs = rsqrt(d);
+      const double li = colraw[buf][i] * rs;  // L(i, k) for i > k; sqrt(d) for i == k
+      if (g == gk) Lm[i][k] = (i >= k) ? li : 0.0;
+      if (tid == k) rdiag[k] = rs;
+#pragma unroll
+      for (int q = qk; q < 16; ++q) {
+        const int j = g + 4 * q;
+        if (j > k && j <= i) a[q] -= li * (colraw[buf][j] * rs);
+      }
     }
   }
   __syncthreads();
-  if (s_fail && tid == 0) sc[scFail] = 1.0;
-  for (int t = tid; t < CB * CB; t += 1024) {
+  // write the factor back (coalesced along the rows of a column)
+  for (int t = tid; t < CB * CB; t += 256) {
     const int j = t >> 6, i = t & 63;
     if (i < bs && j < bs && i >= j) S[(size_t)(k0 + j) * ld + k0 + i] = Lm[i][j];
-    Linv[i * CB + j] = (i < bs && j < bs) ? X[i][j] : 0.0;
+  }
+  if (s_fail && tid == 0) sc[scFail] = 1.0;
+  {
+    const int c = tid >> 2, gg = tid & 3;
+    double x[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) x[q] = 0.0;
+#pragma unroll
+    for (int r = 0; r < CB; ++r) {
+      double s = 0.0;
+#pragma unroll
+      for (int q = 0; q <= ((r - 1) >> 2); ++q) {
+        const int p = gg + 4 * q;
+        if (r > 0 && p < r) s += Lm[r][p] * x[q];
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      const double xr = (((r == c) ? 1.0 : 0.0) - s) * rdiag[r];
+      x[r >> 2] = (gg == (r & 3)) ? ((r >= c) ? xr : 0.0) : x[r >> 2];
+    }
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int r = gg + 4 * q;
+      Linv[r * CB + c] = (r < bs && c < bs) ? x[q] : 0.0;
+    }
   }
 }
 
@@ -216,46 +226,80 @@ ba_chol_syrk(double* __restrict__ S, int ld, int ns, int nrows, int k0, int bs, 
   if (tiI < tjI) return;
   const int bi = (tiI < nAct) ? (kblk + 1 + tiI) : extraBlk;
   const int bj = (tjI < nAct) ? (kblk + 1 + tjI) : extraBlk;
-  constexpr int KC = 32;
-  __shared__ double sAi[KC][CB + 1];
-  __shared__ double sAj[KC][CB + 1];
+  extern __shared__ double s_dyn[];
+  double (*sAi)[CB + 1] = reinterpret_cast<double (*)[CB + 1]>(s_dyn);                  // [p][row]
+  double (*sAj)[CB + 1] = reinterpret_cast<double (*)[CB + 1]>(s_dyn + CB * (CB + 1));
   const int i0 = bi * CB, j0 = bj * CB;
   const int rowMin = k0 + bs;  // only the trailing part (rows/cols beyond the panel) is updated
   const int tid = threadIdx.x;
   const int tx = tid & 15, ty = tid >> 4;
+  // prefetch the C tile (independent of the panel loads -> one memory round trip for everything)
+  double cold[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int i = i0 + tx + 16 * a, j = j0 + ty + 16 * b;
+      cold[a][b] = (i < nrows && j < ns && i >= j && j >= rowMin) ? S[(size_t)j * ld + i] : 0.0;
+    }
+  for (int t = tid; t < bs * CB; t += 256) {
+    const int p = t >> 6, r = t & 63;
+    sAi[p][r] = (i0 + r < nrows && i0 + r >= rowMin) ? S[(size_t)(k0 + p) * ld + i0 + r] : 0.0;
+    sAj[p][r] = (j0 + r < nrows && j0 + r >= rowMin) ? S[(size_t)(k0 + p) * ld + j0 + r] : 0.0;
+  }
+  __syncthreads();
   double c[4][4];
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) c[a][b] = 0;
-  for (int p0 = 0; p0 < bs; p0 += KC) {
-    const int pc = min(KC, bs - p0);
-    __syncthreads();
-    for (int t = tid; t < pc * CB; t += 256) {
-      const int p = t >> 6, r = t & 63;
-      sAi[p][r] = (i0 + r < nrows && i0 + r >= rowMin) ? S[(size_t)(k0 + p0 + p) * ld + i0 + r] : 0.0;
-      sAj[p][r] = (j0 + r < nrows && j0 + r >= rowMin) ? S[(size_t)(k0 + p0 + p) * ld + j0 + r] : 0.0;
-    }
-    __syncthreads();
-    for (int p = 0; p < pc; ++p) {
-      double ai[4], aj[4];
+  for (int p = 0; p < bs; ++p) {
+    double ai[4], aj[4];
 #pragma unroll
-      for (int a = 0; a < 4; ++a) ai[a] = sAi[p][tx + 16 * a];
+    for (int a = 0; a < 4; ++a) ai[a] = sAi[p][tx + 16 * a];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) aj[b] = sAj[p][ty + 16 * b];
+    for (int b = 0; b < 4; ++b) aj[b] = sAj[p][ty + 16 * b];
 #pragma unroll
-      for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < 4; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) c[a][b] += ai[a] * aj[b];
-    }
+      for (int b = 0; b < 4; ++b) c[a][b] += ai[a] * aj[b];
   }
 #pragma unroll
   for (int a = 0; a < 4; ++a)
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       const int i = i0 + tx + 16 * a, j = j0 + ty + 16 * b;
-      if (i < nrows && j < ns && i >= j && j >= rowMin) S[(size_t)j * ld + i] -= c[a][b];
+      if (i < nrows && j < ns && i >= j && j >= rowMin) S[(size_t)j * ld + i] = cold[a][b] - c[a][b];
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// Envelope helpers.  Column c of block column J holds structural non-zeros in rows
+// [J*CB, rowEnd[J]) plus the right-hand-side row ns.  envOff[J] = packed offset (in doubles) of
+// block column J in the communication buffer (CB columns x (rowEnd[J] - J*CB) rows, column-major),
+// the rhs row follows at envOff[nb].
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ba_env_pack(const double* __restrict__ S, int ld, int ns, const int* __restrict__ rowEnd,
+            const long long* __restrict__ envOff, int nb, double* __restrict__ buf, int unpack,
+            double* __restrict__ Sout) {
+  const int J = blockIdx.x;
+  if (J == nb) {  // rhs row
+    for (int c = threadIdx.x; c < ns; c += 256) {
+      if (unpack) Sout[(size_t)c * ld + ns] = buf[envOff[nb] + c];
+      else buf[envOff[nb] + c] = S[(size_t)c * ld + ns];
+    }
+    return;
+  }
+  const int r0 = J * CB, r1 = rowEnd[J], len = r1 - r0;
+  const int ncol = min(CB, ns - r0);
+  double* b = buf + envOff[J];
+  for (int t = threadIdx.x; t < ncol * len; t += 256) {
+    const int cc = t / len, rr = t - cc * len;
+    const size_t si = (size_t)(r0 + cc) * ld + r0 + rr;
+    if (unpack) Sout[si] = b[t];
+    else b[t] = S[si];
+  }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -341,27 +341,35 @@ __global__ void __launch_bounds__(256) ba_stats_kernel(BaDev d) {
 
 // S <- 0 with the damped camera blocks U*_j on the diagonal, rhs <- ea.  addU: this rank
 // contributes U/ea/mu (rank 0 only in the multi-GPU case, where U/ea are already all-reduced).
-__global__ void __launch_bounds__(256) ba_init_S(BaDev d, double mu, int addU) {
-  // one thread per element of the (ns+1) x ns trapezoid stored with leading dimension ld:
-  // memory index t = c * ld + r  (column c of the column-major lower factor == row c of the
-  // row-major upper Schur complement), r == ns is the right-hand side
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long ns = d.ns, ld = d.ld;
-  if (t >= ld * ns) return;
-  const int c = (int)(t / ld), r = (int)(t - (long long)c * ld);
-  double v = 0;
-  if (r < ns) {
-    const int jb = c / 6, kb = r / 6;
-    if (addU && jb == kb && r >= c) {
-      const int a = c - 6 * jb, b = r - 6 * kb;
-      const int idx = a * 6 - (a * (a - 1)) / 2 + (b - a);  // packed upper index of (a, b), a<=b
-      v = d.U[21 * (size_t)(jb + d.mcon) + idx];
-      if (a == b) v += mu;
+__global__ void __launch_bounds__(256)
+ba_init_S(BaDev d, double mu, int addU, const int* __restrict__ rowEnd) {
+  // one CTA per 64-wide block column J: (re)initialise only the envelope rows [J*64, rowEnd[J])
+  // of its columns plus the right-hand-side row ns.  Everything outside the envelope is zero from
+  // the allocation-time memset and is never written (Schur terms and Cholesky fill stay inside).
+  // Memory index = c * ld + r (column c of the column-major lower factor == row c of the
+  // row-major upper Schur complement).
+  const int J = blockIdx.x;
+  const int ns = d.ns, ld = d.ld;
+  const int c0 = J * 64, ncol = min(64, ns - c0);
+  const int r0 = c0, r1 = rowEnd[J], len = r1 - r0;
+  for (int t = threadIdx.x; t < ncol * (len + 1); t += 256) {
+    const int cc = t / (len + 1), rr = t - cc * (len + 1);
+    const int c = c0 + cc;
+    const int r = (rr < len) ? (r0 + rr) : ns;
+    double v = 0;
+    if (r < ns) {
+      const int jb = c / 6, kb = r / 6;
+      if (addU && jb == kb && r >= c) {
+        const int a = c - 6 * jb, b = r - 6 * kb;
+        const int idx = a * 6 - (a * (a - 1)) / 2 + (b - a);  // packed upper index of (a, b), a<=b
+        v = d.U[21 * (size_t)(jb + d.mcon) + idx];
+        if (a == b) v += mu;
+      }
+    } else {
+      v = addU ? d.ea[6 * (size_t)d.mcon + c] : 0.0;
     }
-  } else if (r == ns) {
-    v = addU ? d.ea[6 * (size_t)d.mcon + c] : 0.0;
+    d.S[(size_t)c * ld + r] = v;
   }
-  d.S[t] = v;
 }
 
 // ------------------------------------------------------------------------------------------
