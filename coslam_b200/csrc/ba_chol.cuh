@@ -182,11 +182,22 @@ ba_chol_trsm(double* __restrict__ S, int ld, int nrows, int k0, int bs, int kblk
   const int blk = (blockIdx.x < nAct) ? (kblk + 1 + blockIdx.x) : extraBlk;
   const int r0 = blk * CB;
   const int tid = threadIdx.x;
-  for (int t = tid; t < CB * CB; t += 256) {
-    const int p = t >> 6, r = t & 63;
-    sA[p][r] = (p < bs && r0 + r < nrows && r0 + r >= rowMin) ? S[(size_t)(k0 + p) * ld + r0 + r] : 0.0;
-    const int c = t >> 6, pp = t & 63;
-    sI[pp][c] = Linv[c * CB + pp];
+  {
+    // stage with all 32 global loads in flight before the first shared store (one L2 round trip)
+    double ra[16], ri[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int t = tid + 256 * u;
+      const int p = t >> 6, r = t & 63;
+      ra[u] = (p < bs && r0 + r < nrows && r0 + r >= rowMin) ? S[(size_t)(k0 + p) * ld + r0 + r] : 0.0;
+      ri[u] = Linv[t];  // Linv(c = t >> 6, pp = t & 63)
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int t = tid + 256 * u;
+      sA[t >> 6][t & 63] = ra[u];
+      sI[t & 63][t >> 6] = ri[u];
+    }
   }
   __syncthreads();
   const int tx = tid & 15, ty = tid >> 4;
@@ -242,10 +253,21 @@ ba_chol_syrk(double* __restrict__ S, int ld, int ns, int nrows, int k0, int bs, 
       const int i = i0 + tx + 16 * a, j = j0 + ty + 16 * b;
       cold[a][b] = (i < nrows && j < ns && i >= j && j >= rowMin) ? S[(size_t)j * ld + i] : 0.0;
     }
-  for (int t = tid; t < bs * CB; t += 256) {
-    const int p = t >> 6, r = t & 63;
-    sAi[p][r] = (i0 + r < nrows && i0 + r >= rowMin) ? S[(size_t)(k0 + p) * ld + i0 + r] : 0.0;
-    sAj[p][r] = (j0 + r < nrows && j0 + r >= rowMin) ? S[(size_t)(k0 + p) * ld + j0 + r] : 0.0;
+  {
+    double ri[16], rj[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int t = tid + 256 * u;
+      const int p = t >> 6, r = t & 63;
+      ri[u] = (p < bs && i0 + r < nrows && i0 + r >= rowMin) ? S[(size_t)(k0 + p) * ld + i0 + r] : 0.0;
+      rj[u] = (p < bs && j0 + r < nrows && j0 + r >= rowMin) ? S[(size_t)(k0 + p) * ld + j0 + r] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int t = tid + 256 * u;
+      sAi[t >> 6][t & 63] = ri[u];
+      sAj[t >> 6][t & 63] = rj[u];
+    }
   }
   __syncthreads();
   double c[4][4];
@@ -320,11 +342,19 @@ ba_chol_backward(const double* __restrict__ S, int ld, int ns, int nb,
   double* sx = sLi + CB * CB;         // [CB]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int c = tid; c < ns; c += 1024) sy[c] = S[(size_t)c * ld + ns];
+  // Linv of the next block to process is prefetched into registers one step ahead
+  double nxt[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) nxt[u] = Linv[(size_t)(nb - 1) * CB * CB + tid + 1024 * u];
   for (int k = nb - 1; k >= 0; --k) {
     const int k0 = k * CB, bs = min(CB, ns - k0);
-    const double* Li = Linv + (size_t)k * CB * CB;
     __syncthreads();
-    for (int t = tid; t < CB * CB; t += 1024) sLi[t] = Li[t];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) sLi[tid + 1024 * u] = nxt[u];
+    if (k > 0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) nxt[u] = Linv[(size_t)(k - 1) * CB * CB + tid + 1024 * u];
+    }
     __syncthreads();
     // x_k[c] = sum_{r >= c} Linv(r, c) y_k[r]: 16 threads per output column
     {
@@ -339,14 +369,24 @@ ba_chol_backward(const double* __restrict__ S, int ld, int ns, int nb,
     if (tid < bs) x[k0 + tid] = sx[tid];
     const int c0 = firstBlk[k] * CB;
     const double x0 = sx[lane], x1 = sx[lane + 32];
-    for (int c = c0 + warp; c < k0; c += 32) {
-      const double* col = S + (size_t)c * ld + k0;
-      double s = 0;
-      if (lane < bs) s = col[lane] * x0;
-      if (lane + 32 < bs) s += col[lane + 32] * x1;
+    // one warp per column, 8 columns per warp in flight (all loads issued before the reductions)
+    for (int cb = c0 + warp; cb < k0; cb += 32 * 8) {
+      double v0[8], v1[8];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0) sy[c] -= s;
+      for (int u = 0; u < 8; ++u) {
+        const int c = cb + 32 * u;
+        const double* col = S + (size_t)c * ld + k0;
+        v0[u] = (c < k0 && lane < bs) ? col[lane] : 0.0;
+        v1[u] = (c < k0 && lane + 32 < bs) ? col[lane + 32] : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = cb + 32 * u;
+        double s = v0[u] * x0 + v1[u] * x1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0 && c < k0) sy[c] -= s;
+      }
     }
   }
 }
