@@ -6,6 +6,14 @@
 // sums are reduced with width-16 butterfly shuffles and every lane solves the 3x3 system in closed
 // form (adjugate), so control flow is uniform.
 //
+// Window sampling.  The window samples of a level are one texel apart (ds = 1 / w_level), so all
+// (2hw+1)^2 bilinear taps of a window share the fractional offsets of the window centre and their
+// integer texel coordinates are centre + (dx, dy).  The kernels evaluate the centre once per pass
+// (same expression as the oracle's sample(): u = s*w - 0.5, clamped, floor) and address the taps
+// as centre + offset; the oracle evaluates u per pixel in fp32, which differs from centre + offset
+// by at most one ulp of u (~3e-5 texel) -- far below the 1/256-texel weights of the GL hardware the
+// reference ran on, and covered by the tolerance of the LK parity tests.
+//
 // Two drivers share the same arithmetic (bit-identical results, checked by
 // tests/test_gpu_klt.py::test_fused_gain_tracker_equals_pass_kernels):
 //   klt_gain_pass   one launch per (level, iteration) pass, like the reference's draw calls
@@ -14,16 +22,17 @@
 //       once and kept in registers, and a 12x12-texel tile of the current-frame pyramid around the
 //       feature is staged in shared memory (clamped 128-bit loads; TMA box loads cannot reproduce
 //       CLAMP_TO_EDGE, and at the coarse levels most windows straddle the border) -- the
-//       iterations then sample from shared memory, with a global-memory fallback for samples that
-//       drift outside the tile;
+//       iterations then sample from shared memory; if a window drifts out of its tile the pass
+//       falls back to clamped global loads (same values, same arithmetic);
 //     * the only coupling between slots, the gain-smoothness term that reads beta of <= 8
-//       neighbour slots from the PREVIOUS pass, is synchronised without grid barriers: each slot
-//       publishes (x, y, beta) of pass p into a parity double buffer followed by a version number;
-//       a slot starts pass p once every slot in its wait set (neighbours + reverse neighbours) has
-//       published p-1.  Waiting also on the reverse neighbours makes overwriting the p-1 record
-//       (when publishing p+1) safe on non-square slot grids whose neighbour relation is not
-//       symmetric.  Warps own their items for the whole launch and walk the passes in order, so the
-//       least advanced item can always run (cooperative launch guarantees co-residency).
+//       neighbour slots from the PREVIOUS pass, is synchronised without grid barriers and without
+//       fences: each slot publishes (pass number, beta) as ONE naturally atomic 8-byte word into a
+//       parity double buffer; a slot starts pass p once every slot in its wait set (neighbours +
+//       reverse neighbours) has published p-1, and gets the neighbour gains with the poll itself.
+//       Waiting also on the reverse neighbours makes overwriting the p-1 record (when publishing
+//       p+1) safe on non-square slot grids whose neighbour relation is not symmetric.  Warps own
+//       their items for the whole launch and walk the passes in order, so the least advanced item
+//       can always run (cooperative launch guarantees co-residency).
 #pragma once
 #include "klt_kernels.cuh"
 
@@ -32,18 +41,18 @@ namespace coslam {
 constexpr int KLT_TW = 12;      // staged I1 tile side (texels): 2*hw + 2 + 2*margin with hw = 3
 constexpr int KLT_ROUNDS = 4;   // window pixels per lane on the fast path (<= 64 pixels)
 
-struct KltSamplePos {
-  float ax, ay;
-  int xi, yi;  // unclamped integer texel coordinates of the top-left tap
+struct KltCentre {
+  float ax, ay;  // bilinear weights shared by the whole window
+  int xi, yi;    // unclamped integer texel coordinates of the centre's top-left tap
 };
 
-__device__ __forceinline__ KltSamplePos klt_sample_pos(int w, int h, float s, float t) {
+__device__ __forceinline__ KltCentre klt_centre(int w, int h, float s, float t) {
   float u = s * (float)w - 0.5f;
   float v = t * (float)h - 0.5f;
   u = fminf(fmaxf(u, -2.0f), (float)w + 1.0f);
   v = fminf(fmaxf(v, -2.0f), (float)h + 1.0f);
   const float fu = floorf(u), fv = floorf(v);
-  KltSamplePos p;
+  KltCentre p;
   p.ax = u - fu;
   p.ay = v - fv;
   p.xi = (int)fu;
@@ -69,25 +78,13 @@ __device__ __forceinline__ float3 klt_lerp4(const float4 p00, const float4 p10, 
   return r;
 }
 
+// tap (xi, yi) of a level with clamp-to-edge, weights (ax, ay)
 __device__ __forceinline__ float3 klt_fetch_global(const float4* __restrict__ lv, int w, int h,
-                                                   const KltSamplePos& p) {
-  const int x0 = clampi(p.xi, 0, w - 1), x1 = clampi(p.xi + 1, 0, w - 1);
-  const int y0 = clampi(p.yi, 0, h - 1), y1 = clampi(p.yi + 1, 0, h - 1);
+                                                   int xi, int yi, float ax, float ay) {
+  const int x0 = clampi(xi, 0, w - 1), x1 = clampi(xi + 1, 0, w - 1);
+  const int y0 = clampi(yi, 0, h - 1), y1 = clampi(yi + 1, 0, h - 1);
   return klt_lerp4(__ldg(&lv[(size_t)y0 * w + x0]), __ldg(&lv[(size_t)y0 * w + x1]),
-                   __ldg(&lv[(size_t)y1 * w + x0]), __ldg(&lv[(size_t)y1 * w + x1]), p.ax, p.ay);
-}
-
-// tile[b * KLT_TW + a] == level[clamp(ty0 + b)][clamp(tx0 + a)], so indexing it with the UNCLAMPED
-// tap coordinates reproduces the clamped fetches exactly
-__device__ __forceinline__ float3 klt_fetch_tile(const float4* __restrict__ tile, int tx0, int ty0,
-                                                 const float4* __restrict__ lv, int w, int h,
-                                                 const KltSamplePos& p) {
-  const int a = p.xi - tx0, b = p.yi - ty0;
-  if ((unsigned)a < (unsigned)(KLT_TW - 1) && (unsigned)b < (unsigned)(KLT_TW - 1)) {
-    const float4* q = tile + b * KLT_TW + a;
-    return klt_lerp4(q[0], q[1], q[KLT_TW], q[KLT_TW + 1], p.ax, p.ay);
-  }
-  return klt_fetch_global(lv, w, h, p);
+                   __ldg(&lv[(size_t)y1 * w + x0]), __ldg(&lv[(size_t)y1 * w + x1]), ax, ay);
 }
 
 __device__ __forceinline__ float half_sum(float v) {
@@ -96,7 +93,6 @@ __device__ __forceinline__ float half_sum(float v) {
   return v;
 }
 
-// accumulate one window pixel
 struct KltAcc {
   float a0, a1, a2, d0, d1, d2, r0, r1, r2, ssd;
 };
@@ -170,6 +166,8 @@ klt_gain_pass(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1, 
               long long lvOff, int w, int h, const float4* __restrict__ X0buf,
               const float4* __restrict__ in, float4* __restrict__ out,
               const int* __restrict__ nbr, float dsx, float dsy, KltTrackParams P, int firstPass) {
+  (void)dsx;
+  (void)dsy;
   const int cam = blockIdx.y;
   const int hl = threadIdx.x & 15, halfBase = threadIdx.x & 16;
   int slot = blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
@@ -188,12 +186,14 @@ klt_gain_pass(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1, 
   const bool pre_invalid = (cur.x < 0.f) || (x0.x < 0.f);
   const int hw = P.halfWidth, fwid = 2 * hw + 1, npx = fwid * fwid;
   const float Wf = (float)P.W, Hf = (float)P.H;
+  const KltCentre c0 = klt_centre(w, h, x0.x, x0.y);
+  const KltCentre c1 = klt_centre(w, h, cur.x, cur.y);
   KltAcc A = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   for (int p = hl; p < npx; p += 16) {
     const int py = p / fwid, px = p - py * fwid;
-    const float fx = (float)(px - hw), fy = (float)(py - hw);
-    const float3 I0 = klt_fetch_global(L0, w, h, klt_sample_pos(w, h, x0.x + fx * dsx, x0.y + fy * dsy));
-    const float3 I1 = klt_fetch_global(L1, w, h, klt_sample_pos(w, h, cur.x + fx * dsx, cur.y + fy * dsy));
+    const int dx = px - hw, dy = py - hw;
+    const float3 I0 = klt_fetch_global(L0, w, h, c0.xi + dx, c0.yi + dy, c0.ax, c0.ay);
+    const float3 I1 = klt_fetch_global(L1, w, h, c1.xi + dx, c1.yi + dy, c1.ax, c1.ay);
     klt_acc_pixel(A, I0, I1, beta, nbterm, Wf, Hf, P.lambda, P.delta);
   }
   float4 res = klt_gain_finish(A, cur.x, cur.y, beta, P);
@@ -238,28 +238,27 @@ klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
   const int hw = Plax.halfWidth, fwid = 2 * hw + 1, npx = fwid * fwid;
   const bool fast = (npx <= 16 * KLT_ROUNDS) && (2 * hw + 2 + 2 <= KLT_TW);
   const float Wf = (float)Plax.W, Hf = (float)Plax.H;
-  float4* tile = s_tile[halfInBlock];
+  const float4* tile = s_tile[halfInBlock];
   // both halves of a warp must execute the same number of outer iterations (full-mask shuffles)
   const int nOwn = (T + Q - 1) / Q;
 
-  // state of the FIRST owned item lives in registers across passes
-  float3 I0r[KLT_ROUNDS];
-  // window offsets of this lane's pixels, hoisted out of every loop (no integer division inside)
-  float fxr[KLT_ROUNDS], fyr[KLT_ROUNDS];
+  // window offsets of this lane's pixels, hoisted out of every loop
+  int dxr[KLT_ROUNDS], dyr[KLT_ROUNDS];
 #pragma unroll
   for (int r = 0; r < KLT_ROUNDS; ++r) {
     const int p = min(hl + 16 * r, npx - 1);
     const int py = p / fwid, px = p - py * fwid;
-    fxr[r] = (float)(px - hw);
-    fyr[r] = (float)(py - hw);
+    dxr[r] = px - hw;
+    dyr[r] = py - hw;
   }
+  // state of the FIRST owned item lives in registers across passes
+  float3 I0r[KLT_ROUNDS];
   float4 cur0 = make_float4(-1.f, -1.f, -1.f, 0.f);
   int tx0 = 0, ty0 = 0;
 
   int pass = 0;
   for (int li = 0; li < LV.n; ++li) {
     const int w = LV.w[li], h = LV.h[li];
-    const float dsx = 1.0f / (float)w, dsy = 1.0f / (float)h;
     for (int it = 1; it <= nIter; ++it) {
       ++pass;
       // thresholds are lax except on the last iteration of a level (v3d_gpuklt.cpp:266-279)
@@ -301,47 +300,66 @@ klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
         const float beta = cur.z;
         const float nbterm = klt_nbterm(bn, beta, hl, halfBase);
         const bool pre_invalid = (cur.x < 0.f) || (x0.x < 0.f);
+        const KltCentre c1 = klt_centre(w, h, cur.x, cur.y);
         // ---- per-level staging (first iteration of a level): I0 samples + I1 tile
         if (staged && it == 1) {
+          const KltCentre c0 = klt_centre(w, h, x0.x, x0.y);
 #pragma unroll
           for (int r = 0; r < KLT_ROUNDS; ++r) {
             const int p = hl + 16 * r;
-            const float fx = fxr[r], fy = fyr[r];
             I0r[r] = (p < npx && !pre_invalid)
-                         ? klt_fetch_global(L0, w, h, klt_sample_pos(w, h, x0.x + fx * dsx, x0.y + fy * dsy))
+                         ? klt_fetch_global(L0, w, h, c0.xi + dxr[r], c0.yi + dyr[r], c0.ax, c0.ay)
                          : make_float3(0.f, 0.f, 0.f);
           }
-          const KltSamplePos c = klt_sample_pos(w, h, cur.x, cur.y);
-          tx0 = c.xi - hw - 2;
-          ty0 = c.yi - hw - 2;
+          tx0 = c1.xi - hw - 2;
+          ty0 = c1.yi - hw - 2;
           if (!pre_invalid) {
-            for (int i = hl; i < KLT_TW * KLT_TW; i += 16) {
+            float4* tw = s_tile[halfInBlock];
+            float4 tv[KLT_TW * KLT_TW / 16];
+#pragma unroll
+            for (int u = 0; u < KLT_TW * KLT_TW / 16; ++u) {  // all 9 loads in flight first
+              const int i = hl + 16 * u;
               const int b = i / KLT_TW, a = i - b * KLT_TW;
-              tile[i] = __ldg(&L1[(size_t)clampi(ty0 + b, 0, h - 1) * w + clampi(tx0 + a, 0, w - 1)]);
+              tv[u] = __ldg(&L1[(size_t)clampi(ty0 + b, 0, h - 1) * w + clampi(tx0 + a, 0, w - 1)]);
             }
+#pragma unroll
+            for (int u = 0; u < KLT_TW * KLT_TW / 16; ++u) tw[hl + 16 * u] = tv[u];
           }
           __syncwarp();
         }
         // ---- the iteration
         KltAcc A = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         if (!pre_invalid) {
-          if (staged) {
+          // tile[b * KLT_TW + a] == level[clamp(ty0 + b)][clamp(tx0 + a)]: indexing with the
+          // unclamped tap coordinates reproduces the clamped fetches exactly
+          const int a0 = c1.xi - tx0, b0 = c1.yi - ty0;
+          const bool inTile = staged && (a0 - hw >= 0) && (a0 + hw + 1 < KLT_TW) && (b0 - hw >= 0) &&
+                              (b0 + hw + 1 < KLT_TW);
+          if (inTile) {
+            const float4* tc = tile + b0 * KLT_TW + a0;
 #pragma unroll
             for (int r = 0; r < KLT_ROUNDS; ++r) {
-              const int p = hl + 16 * r;
-              if (p < npx) {
-                const float fx = fxr[r], fy = fyr[r];
-                const float3 I1 = klt_fetch_tile(tile, tx0, ty0, L1, w, h,
-                                                 klt_sample_pos(w, h, cur.x + fx * dsx, cur.y + fy * dsy));
+              if (hl + 16 * r < npx) {
+                const float4* t4 = tc + dyr[r] * KLT_TW + dxr[r];
+                const float3 I1 = klt_lerp4(t4[0], t4[1], t4[KLT_TW], t4[KLT_TW + 1], c1.ax, c1.ay);
+                klt_acc_pixel(A, I0r[r], I1, beta, nbterm, Wf, Hf, Plax.lambda, Plax.delta);
+              }
+            }
+          } else if (staged) {
+#pragma unroll
+            for (int r = 0; r < KLT_ROUNDS; ++r) {
+              if (hl + 16 * r < npx) {
+                const float3 I1 = klt_fetch_global(L1, w, h, c1.xi + dxr[r], c1.yi + dyr[r], c1.ax, c1.ay);
                 klt_acc_pixel(A, I0r[r], I1, beta, nbterm, Wf, Hf, Plax.lambda, Plax.delta);
               }
             }
           } else {
+            const KltCentre c0 = klt_centre(w, h, x0.x, x0.y);
             for (int p = hl; p < npx; p += 16) {
               const int py = p / fwid, px = p - py * fwid;
-              const float fx = (float)(px - hw), fy = (float)(py - hw);
-              const float3 I0 = klt_fetch_global(L0, w, h, klt_sample_pos(w, h, x0.x + fx * dsx, x0.y + fy * dsy));
-              const float3 I1 = klt_fetch_global(L1, w, h, klt_sample_pos(w, h, cur.x + fx * dsx, cur.y + fy * dsy));
+              const int dx = px - hw, dy = py - hw;
+              const float3 I0 = klt_fetch_global(L0, w, h, c0.xi + dx, c0.yi + dy, c0.ax, c0.ay);
+              const float3 I1 = klt_fetch_global(L1, w, h, c1.xi + dx, c1.yi + dy, c1.ax, c1.ay);
               klt_acc_pixel(A, I0, I1, beta, nbterm, Wf, Hf, Plax.lambda, Plax.delta);
             }
           }
