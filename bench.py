@@ -51,28 +51,26 @@ class ClockSampler:
         self.gpu, self.rows, self.proc = gpu_index, [], None
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms",
-                 "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
-                text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+        # one-shot queries from a polling thread (a looping nvidia-smi block-buffers its pipe)
+        self.stop_flag = False
+        self.t = threading.Thread(target=self._poll, daemon=True)
+        self.t.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip().split(", "))
+    def _poll(self):
+        cmd = ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+               str(self.gpu)]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(cmd, capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append(line.strip().split(", "))
+            except Exception:
+                pass
+            time.sleep(0.05)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        self.stop_flag = True
+        self.t.join(timeout=6)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:

@@ -160,7 +160,7 @@ int alloc_group(cosl_klt* g) {
   COSL_CUDA(cudaFuncSetAttribute(klt_select_refill, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  g->smemKeys * (int)sizeof(unsigned long long)));
   const int TS = NM_T + 2 * r;
-  const int nmBytes = (TS * TS + TS * NM_T) * (int)sizeof(float);
+  const int nmBytes = (3 * TS * TS + TS * NM_T) * (int)sizeof(float);
   if (nmBytes > 48 * 1024)
     COSL_CUDA(cudaFuncSetAttribute(klt_nonmax_compact, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    nmBytes));
@@ -379,7 +379,7 @@ int run_detector(cosl_klt* g, int mode, int nPresentExt) {
   }
   const int r = std::max(1, g->cfg.minDistance);
   const int TS = NM_T + 2 * r;
-  const int nmBytes = (TS * TS + TS * NM_T) * (int)sizeof(float);
+  const int nmBytes = (3 * TS * TS + TS * NM_T) * (int)sizeof(float);
   dim3 gn(div_up(g->W, NM_T), div_up(g->H, NM_T), g->C);
   COSL_LAUNCH(klt_nonmax_compact, gn, 256, nmBytes, g->stream, g->d_corn, g->W, g->H, r, g->d_cand,
               g->candCap, g->d_counters);

@@ -374,6 +374,15 @@ __global__ void klt_suppress(const float4* __restrict__ pts, int n, int ptsStrid
 // ------------------------------------------------------------------------------------------
 constexpr int NM_T = 32;
 
+// exclusive window maximum over [x-r, x-1] U [x+1, x+r] from block prefix / suffix maxima
+// (van Herk / Gil-Werman with block size r): a window of length r spans at most two r-blocks.
+__device__ __forceinline__ float nm_excl_max(const float* __restrict__ P, const float* __restrict__ S,
+                                            int x, int r, int stride) {
+  const float left = fmaxf(S[(x - r) * stride], P[(x - 1) * stride]);
+  const float right = fmaxf(S[(x + 1) * stride], P[(x + r) * stride]);
+  return fmaxf(left, right);
+}
+
 __global__ void __launch_bounds__(256)
 klt_nonmax_compact(const float* __restrict__ corn, int W, int H, int r,
                    unsigned long long* __restrict__ cand, int candCap,
@@ -381,7 +390,9 @@ klt_nonmax_compact(const float* __restrict__ corn, int W, int H, int r,
   extern __shared__ float s_nm[];
   const int TS = NM_T + 2 * r;            // tile side incl. halo
   float* s_c = s_nm;                      // [TS][TS] signed cornerness
-  float* s_h = s_nm + TS * TS;            // [TS][NM_T] horizontal pass result
+  float* s_p = s_c + TS * TS;             // [TS][TS] prefix maxima of |.| inside r-blocks
+  float* s_s = s_p + TS * TS;             // [TS][TS] suffix maxima
+  float* s_h = s_s + TS * TS;             // [TS][NM_T] horizontal pass result (signed)
   const int cam = blockIdx.z;
   const float* cm = corn + (size_t)cam * W * H;
   const int x0 = blockIdx.x * NM_T, y0 = blockIdx.y * NM_T;
@@ -396,34 +407,57 @@ klt_nonmax_compact(const float* __restrict__ corn, int W, int H, int r,
     if (v > 0.f && ty >= r && ty < r + NM_T && tx >= r && tx < r + NM_T) anyPos = 1;
   }
   if (!__syncthreads_or(anyPos)) return;  // nothing positive in the inner tile: no survivor
+  // ---- horizontal pass (klt_detector_nonmax.cg:12-26 with ds = (1/W, 0)): the sequential
+  // "if |n| >= |m| then m = -|n|" scan equals: m = c if |c| > max|n| else -max|n|
+  const int nbk = (TS + r - 1) / r;
+  for (int i = tid; i < TS * nbk; i += 256) {
+    const int row = i / nbk, b = i - row * nbk;
+    const int xs = b * r, xe = min(TS, xs + r);
+    float m = 0.f;
+    for (int x = xs; x < xe; ++x) {
+      m = fmaxf(m, fabsf(s_c[row * TS + x]));
+      s_p[row * TS + x] = m;
+    }
+    m = 0.f;
+    for (int x = xe - 1; x >= xs; --x) {
+      m = fmaxf(m, fabsf(s_c[row * TS + x]));
+      s_s[row * TS + x] = m;
+    }
+  }
+  __syncthreads();
   for (int i = tid; i < TS * NM_T; i += 256) {
     const int ty = i / NM_T, tx = i - ty * NM_T;
-    const float* row = s_c + ty * TS + tx + r;
-    float mx = row[0];
-    for (int k = -r; k < 0; ++k) {
-      const float cc = fabsf(row[k]);
-      mx = (cc >= fabsf(mx)) ? -cc : mx;
+    const int x = tx + r;
+    const float c = s_c[ty * TS + x];
+    const float ex = nm_excl_max(s_p + ty * TS, s_s + ty * TS, x, r, 1);
+    s_h[i] = (fabsf(c) > ex) ? c : -ex;
+  }
+  __syncthreads();
+  // ---- vertical pass on the horizontal result
+  float* v_p = s_p;  // reuse: [TS][NM_T]
+  float* v_s = s_s;
+  for (int i = tid; i < NM_T * nbk; i += 256) {
+    const int col = i % NM_T, b = i / NM_T;
+    const int ys = b * r, ye = min(TS, ys + r);
+    float m = 0.f;
+    for (int y = ys; y < ye; ++y) {
+      m = fmaxf(m, fabsf(s_h[y * NM_T + col]));
+      v_p[y * NM_T + col] = m;
     }
-    for (int k = 1; k <= r; ++k) {
-      const float cc = fabsf(row[k]);
-      mx = (cc >= fabsf(mx)) ? -cc : mx;
+    m = 0.f;
+    for (int y = ye - 1; y >= ys; --y) {
+      m = fmaxf(m, fabsf(s_h[y * NM_T + col]));
+      v_s[y * NM_T + col] = m;
     }
-    s_h[i] = mx;
   }
   __syncthreads();
   for (int i = tid; i < NM_T * NM_T; i += 256) {
     const int ty = i / NM_T, tx = i - ty * NM_T;
     const int gx = x0 + tx, gy = y0 + ty;
-    const float* col = s_h + (ty + r) * NM_T + tx;
-    float mx = col[0];
-    for (int k = -r; k < 0; ++k) {
-      const float cc = fabsf(col[k * NM_T]);
-      mx = (cc >= fabsf(mx)) ? -cc : mx;
-    }
-    for (int k = 1; k <= r; ++k) {
-      const float cc = fabsf(col[k * NM_T]);
-      mx = (cc >= fabsf(mx)) ? -cc : mx;
-    }
+    const int y = ty + r;
+    const float c = s_h[y * NM_T + tx];
+    const float ex = nm_excl_max(v_p + tx, v_s + tx, y, r, NM_T);
+    const float mx = (fabsf(c) > ex) ? c : -ex;
     const bool surv = (gx < W && gy < H && mx > 0.f);
     const unsigned m = __ballot_sync(0xffffffffu, surv);
     if (m) {

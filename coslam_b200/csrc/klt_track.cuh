@@ -60,21 +60,19 @@ __device__ __forceinline__ KltCentre klt_centre(int w, int h, float s, float t) 
   return p;
 }
 
+// All LK arithmetic below is written with explicit fma/mul/add intrinsics: the two drivers inline
+// these helpers into different surroundings, and only a fixed operation sequence keeps their
+// results bit-identical (the compiler is otherwise free to contract a*b+c differently per site).
+__device__ __forceinline__ float lerp1(float p0, float p1, float a) {
+  return __fmaf_rn(a, __fsub_rn(p1, p0), p0);
+}
+
 __device__ __forceinline__ float3 klt_lerp4(const float4 p00, const float4 p10, const float4 p01,
                                             const float4 p11, float ax, float ay) {
   float3 r;
-  {
-    const float top = p00.x + ax * (p10.x - p00.x), bot = p01.x + ax * (p11.x - p01.x);
-    r.x = top + ay * (bot - top);
-  }
-  {
-    const float top = p00.y + ax * (p10.y - p00.y), bot = p01.y + ax * (p11.y - p01.y);
-    r.y = top + ay * (bot - top);
-  }
-  {
-    const float top = p00.z + ax * (p10.z - p00.z), bot = p01.z + ax * (p11.z - p01.z);
-    r.z = top + ay * (bot - top);
-  }
+  r.x = lerp1(lerp1(p00.x, p10.x, ax), lerp1(p01.x, p11.x, ax), ay);
+  r.y = lerp1(lerp1(p00.y, p10.y, ax), lerp1(p01.y, p11.y, ax), ay);
+  r.z = lerp1(lerp1(p00.z, p10.z, ax), lerp1(p01.z, p11.z, ax), ay);
   return r;
 }
 
@@ -89,7 +87,7 @@ __device__ __forceinline__ float3 klt_fetch_global(const float4* __restrict__ lv
 
 __device__ __forceinline__ float half_sum(float v) {
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o, 16);
+  for (int o = 8; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o, 16));
   return v;
 }
 
@@ -100,21 +98,24 @@ struct KltAcc {
 __device__ __forceinline__ void klt_acc_pixel(KltAcc& A, const float3 I0, const float3 I1, float beta,
                                               float nbterm, float Wf, float Hf, float lambda,
                                               float delta) {
-  const float e = beta * I0.x - I1.x;
-  const float Jx = (beta * I0.y + I1.y) * Wf * 0.5f;
-  const float Jy = (beta * I0.z + I1.z) * Hf * 0.5f;
-  const float g0 = sqrtf(I0.y * I0.y + I0.z * I0.z);
-  const float g1 = sqrtf(I1.y * I1.y + I1.z * I1.z);
-  A.a0 += Jx * Jx;
-  A.a1 += Jx * Jy;
-  A.a2 += Jx * -I0.x;
-  A.d0 += Jy * Jy;
-  A.d1 += Jy * -I0.x;
-  A.d2 += I0.x * I0.x + lambda * g0 * g0 + delta * 8.0f;
-  A.r0 += e * Jx;
-  A.r1 += e * Jy;
-  A.r2 += -e * I0.x + lambda * g0 * (g1 - beta * g0) + delta * nbterm;
-  A.ssd += e * e;
+  const float e = __fmaf_rn(beta, I0.x, -I1.x);
+  const float Jx = __fmul_rn(__fmul_rn(__fmaf_rn(beta, I0.y, I1.y), Wf), 0.5f);
+  const float Jy = __fmul_rn(__fmul_rn(__fmaf_rn(beta, I0.z, I1.z), Hf), 0.5f);
+  const float n0 = __fmaf_rn(I0.y, I0.y, __fmul_rn(I0.z, I0.z));
+  const float n1 = __fmaf_rn(I1.y, I1.y, __fmul_rn(I1.z, I1.z));
+  const float g0 = sqrtf(n0);  // -prec-sqrt=false for klt.cu: MUFU based
+  const float g1 = sqrtf(n1);
+  A.a0 = __fmaf_rn(Jx, Jx, A.a0);
+  A.a1 = __fmaf_rn(Jx, Jy, A.a1);
+  A.a2 = __fmaf_rn(Jx, -I0.x, A.a2);
+  A.d0 = __fmaf_rn(Jy, Jy, A.d0);
+  A.d1 = __fmaf_rn(Jy, -I0.x, A.d1);
+  A.d2 = __fadd_rn(A.d2, __fmaf_rn(delta, 8.0f, __fmaf_rn(__fmul_rn(lambda, g0), g0, __fmul_rn(I0.x, I0.x))));
+  A.r0 = __fmaf_rn(e, Jx, A.r0);
+  A.r1 = __fmaf_rn(e, Jy, A.r1);
+  const float t = __fmaf_rn(__fmul_rn(lambda, g0), __fmaf_rn(-beta, g0, g1), __fmul_rn(-e, I0.x));
+  A.r2 = __fadd_rn(A.r2, __fmaf_rn(delta, nbterm, t));
+  A.ssd = __fmaf_rn(e, e, A.ssd);
 }
 
 // reduce over the half-warp, solve, test (klt_tracker_with_gain.cg:12-40,124-147)
@@ -124,24 +125,28 @@ __device__ __forceinline__ float4 klt_gain_finish(KltAcc A, float X1x, float X1y
   const float d = half_sum(A.d0), e = half_sum(A.d1), f = half_sum(A.d2);
   const float r0 = half_sum(A.r0), r1 = half_sum(A.r1), r2 = half_sum(A.r2);
   const float ssd = half_sum(A.ssd);
-  float det = a * d * f + 2 * b * c * e;
-  det -= a * e * e + b * b * f + c * c * d;
-  const float rdet = 1.0f / det;
-  const float Aa = d * f - e * e, Bb = c * e - b * f, Cc = b * e - c * d;
-  const float Dd = a * f - c * c, Ee = b * c - a * e, Ff = a * d - b * b;
-  float ux = (Aa * r0 + Bb * r1 + Cc * r2) * rdet;
-  float uy = (Bb * r0 + Dd * r1 + Ee * r2) * rdet;
-  const float ub = (Cc * r0 + Ee * r1 + Ff * r2) * rdet;
-  X1x += ux;
-  X1y += uy;
-  ux *= (float)P.W;
-  uy *= (float)P.H;
-  const float sqrLen = ux * ux + uy * uy;
+  // det3x3symm: a*d*f + 2*b*c*e - (a*e*e + b*b*f + c*c*d)
+  const float detp = __fmaf_rn(__fmul_rn(2.0f, __fmul_rn(b, c)), e, __fmul_rn(__fmul_rn(a, d), f));
+  const float detm = __fmaf_rn(__fmul_rn(c, c), d, __fmaf_rn(__fmul_rn(b, b), f, __fmul_rn(__fmul_rn(a, e), e)));
+  const float det = __fsub_rn(detp, detm);
+  const float rdet = __fdividef(1.0f, det);
+  const float Aa = __fmaf_rn(d, f, -__fmul_rn(e, e)), Bb = __fmaf_rn(c, e, -__fmul_rn(b, f));
+  const float Cc = __fmaf_rn(b, e, -__fmul_rn(c, d)), Dd = __fmaf_rn(a, f, -__fmul_rn(c, c));
+  const float Ee = __fmaf_rn(b, c, -__fmul_rn(a, e)), Ff = __fmaf_rn(a, d, -__fmul_rn(b, b));
+  float ux = __fmul_rn(__fmaf_rn(Cc, r2, __fmaf_rn(Bb, r1, __fmul_rn(Aa, r0))), rdet);
+  float uy = __fmul_rn(__fmaf_rn(Ee, r2, __fmaf_rn(Dd, r1, __fmul_rn(Bb, r0))), rdet);
+  const float ub = __fmul_rn(__fmaf_rn(Ff, r2, __fmaf_rn(Ee, r1, __fmul_rn(Cc, r0))), rdet);
+  X1x = __fadd_rn(X1x, ux);
+  X1y = __fadd_rn(X1y, uy);
+  ux = __fmul_rn(ux, (float)P.W);
+  uy = __fmul_rn(uy, (float)P.H);
+  const float sqrLen = __fmaf_rn(ux, ux, __fmul_rn(uy, uy));
   bool invalid = (det < 0.00001f);
   invalid = invalid || (ssd > P.ssdThr);
   invalid = invalid || (sqrLen > P.sqrConv);
   invalid = invalid || (X1x < P.vr0 || X1y < P.vr1) || (X1x > P.vr2 || X1y > P.vr3);
-  return invalid ? make_float4(-1.f, -1.f, -1.f, 0.f) : make_float4(X1x, X1y, beta + ub, 0.f);
+  return invalid ? make_float4(-1.f, -1.f, -1.f, 0.f)
+                 : make_float4(X1x, X1y, __fadd_rn(beta, ub), 0.f);
 }
 
 // dot(float4(1), betaN1 + betaN2 - 2*beta) of klt_tracker_with_gain.cg:111 from the eight
@@ -149,12 +154,12 @@ __device__ __forceinline__ float4 klt_gain_finish(KltAcc A, float X1x, float X1y
 __device__ __forceinline__ float klt_nbterm(float bn, float beta, int hl, int halfBase) {
   bn = (bn < 0.f) ? beta : bn;
   const float hi = __shfl_sync(0xffffffffu, bn, halfBase + (hl & 3) + 4);
-  const float s4 = bn + hi - 2.0f * beta;
+  const float s4 = __fsub_rn(__fadd_rn(bn, hi), __fmul_rn(2.0f, beta));
   const float s0 = __shfl_sync(0xffffffffu, s4, halfBase + 0);
   const float s1 = __shfl_sync(0xffffffffu, s4, halfBase + 1);
   const float s2 = __shfl_sync(0xffffffffu, s4, halfBase + 2);
   const float s3 = __shfl_sync(0xffffffffu, s4, halfBase + 3);
-  return ((s0 + s1) + s2) + s3;
+  return __fadd_rn(__fadd_rn(__fadd_rn(s0, s1), s2), s3);
 }
 
 // ------------------------------------------------------------------------------------------
