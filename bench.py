@@ -232,7 +232,6 @@ def run_cuda(args):
     barrier()
     gpu_launches = api.kernel_launch_count() - launches0
     ms_val = max_over_ranks(e0.elapsed_time(e1))
-    clk = clocks.stop()
     feats, cnt = grp.fetch()
     tracked_frac = float(np.mean([(feats[c]["status"] == 0).mean() for c in range(KLT_C)]))
     # ---- roofline: second pass of the same region with per-kernel-class CUDA events
@@ -272,9 +271,35 @@ def run_cuda(args):
     grp.sync()
     wall = time.perf_counter() - t_wall
     ms_e2e = max_over_ranks(max(e2.elapsed_time(e3), wall * 1e3))
+    clk = clocks.stop()  # sampled across the device-resident, profiled and end-to-end regions
     barrier()
     klt_value = world * KLT_C * F * K / (ms_val * 1e-3)
     klt_e2e = world * KLT_C * F * K / (ms_e2e * 1e-3)
+
+    # ------------------------------------------------------------------ pose (latency, rank 0)
+    pose = None
+    if rank == 0:
+        cases = [synth.make_pose_case(192, KLT_W, KLT_H, seed=100 + c) for c in range(KLT_C)]
+        pa = ([c[0] for c in cases], [c[1] for c in cases], [c[2] for c in cases],
+              [c[3] for c in cases], [c[4] for c in cases], 10.0)
+        for _ in range(3):
+            api.pose_intracam_batch(*pa, device=local)
+        nrep = 40
+        t0 = time.perf_counter()
+        for _ in range(nrep):
+            api.pose_intracam_batch(*pa, device=local)
+        us = (time.perf_counter() - t0) / nrep * 1e6
+        pose = {"metric": "pose_batch_latency", "value": us, "unit": "us per call", "higher_is_better": False,
+                "config": {"workload": "intraCamEstimate for 4 cameras x 192 points in one launch, "
+                                       "host arrays in/out (cosl_pose_intracam_batch)"}}
+        if world == 1 and not args.no_cpu:
+            from oracle import orc as _orc
+            t0 = time.perf_counter()
+            for _ in range(10):
+                for c in cases:
+                    _orc.pose_intracam(c[0], c[1], c[2], c[3], c[4], 10.0)
+            pose["cpu_baseline"] = {"value": (time.perf_counter() - t0) / 10 * 1e6, "unit": "us per 4 cameras",
+                                    "cores": 1, "kind": "port", "sample": "10 repetitions"}
 
     # ------------------------------------------------------------------ BA (c4), sharded
     ba = run_ba(args, api, synth, BaOptions, torch, dist, rank, world, local, barrier,
@@ -308,6 +333,8 @@ def run_cuda(args):
             line["cpu_baseline"] = cpu
         if ba is not None:
             line["ba"] = ba
+        if pose is not None:
+            line["pose"] = pose
         emit(line)
     if dist is not None:
         dist.barrier()
@@ -455,7 +482,7 @@ def main():
     os.dup2(2, 1)  # fd 1 -> stderr for the rest of the process
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")

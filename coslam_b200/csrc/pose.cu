@@ -8,7 +8,9 @@
 // The Jacobian is the reference's forward difference (eps = 1e-8, :43-117) evaluated with non-fused
 // fp64 operations (this file is compiled with -fmad=false) so that the differences see the same
 // roundings as the oracle.
+#include <algorithm>
 #include <cmath>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -30,6 +32,17 @@ struct PoseOut {
   double R[9], t[3];
   double lambda0, lambda, err0, err, errRW;
   int retTypeLM, npts, nIterLM, nIterRW, ok;
+};
+
+struct PoseOut;
+struct PoseCam;
+struct PoseWorkspace {
+  cudaStream_t stream = nullptr;
+  PoseCam* d_cams = nullptr;
+  double *d_M = nullptr, *d_m = nullptr, *d_p = nullptr, *d_W = nullptr;
+  PoseOut* d_out = nullptr;
+  int capC = 0;
+  long long capPts = 0;
 };
 
 struct PoseCfg {
@@ -426,10 +439,12 @@ int cosl_pose_intracam_batch(int C, const double* K9, const double* R0, const do
     if (opts[c].lambda0 != opts[0].lambda0 || opts[c].maxIterLM != opts[0].maxIterLM ||
         opts[c].maxIterRW != opts[0].maxIterRW)
       return set_error(COSL_E_INVALID, "batched pose solve needs identical options per camera");
-  PoseCam* d_cams = nullptr;
-  double *d_M = nullptr, *d_m = nullptr, *d_p = nullptr, *d_W = nullptr;
-  PoseOut* d_out = nullptr;
-  cudaStream_t st = nullptr;
+  // per-device workspace, reused across calls: the solve is latency-bound, a cudaMalloc/cudaFree
+  // pair per call would cost more than the kernel
+  static std::mutex mtx;
+  static PoseWorkspace ws[64];
+  std::lock_guard<std::mutex> lock(mtx);
+  PoseWorkspace& W = ws[device & 63];
   int rc = COSL_OK;
   std::vector<PoseOut> outs(C);
 #define POSE_CK(expr)                                                               \
@@ -437,32 +452,41 @@ int cosl_pose_intracam_batch(int C, const double* K9, const double* R0, const do
     cudaError_t _e = (expr);                                                        \
     if (_e != cudaSuccess) rc = set_error(COSL_E_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
   }
-  POSE_CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-  POSE_CK(cudaMalloc(&d_cams, sizeof(PoseCam) * C));
-  POSE_CK(cudaMalloc(&d_M, sizeof(double) * 3 * totA));
-  POSE_CK(cudaMalloc(&d_m, sizeof(double) * 2 * totA));
-  POSE_CK(cudaMalloc(&d_p, sizeof(double) * totA));
-  POSE_CK(cudaMalloc(&d_W, sizeof(double) * totA));
-  POSE_CK(cudaMalloc(&d_out, sizeof(PoseOut) * C));
-  POSE_CK(cudaMemcpyAsync(d_cams, cams.data(), sizeof(PoseCam) * C, cudaMemcpyHostToDevice, st));
-  POSE_CK(cudaMemcpyAsync(d_M, hM.data(), sizeof(double) * 3 * totA, cudaMemcpyHostToDevice, st));
-  POSE_CK(cudaMemcpyAsync(d_m, hm.data(), sizeof(double) * 2 * totA, cudaMemcpyHostToDevice, st));
-  POSE_CK(cudaMemcpyAsync(d_p, hp.data(), sizeof(double) * totA, cudaMemcpyHostToDevice, st));
+  if (!W.stream) POSE_CK(cudaStreamCreateWithFlags(&W.stream, cudaStreamNonBlocking));
+  if (rc == COSL_OK && (W.capC < C || W.capPts < totA)) {
+    cudaFree(W.d_cams);
+    cudaFree(W.d_M);
+    cudaFree(W.d_m);
+    cudaFree(W.d_p);
+    cudaFree(W.d_W);
+    cudaFree(W.d_out);
+    W = PoseWorkspace{W.stream};
+    const int capC = std::max(C, 16);
+    const long long capP = std::max<long long>(totA, 4096);
+    POSE_CK(cudaMalloc(&W.d_cams, sizeof(PoseCam) * capC));
+    POSE_CK(cudaMalloc(&W.d_M, sizeof(double) * 3 * capP));
+    POSE_CK(cudaMalloc(&W.d_m, sizeof(double) * 2 * capP));
+    POSE_CK(cudaMalloc(&W.d_p, sizeof(double) * capP));
+    POSE_CK(cudaMalloc(&W.d_W, sizeof(double) * capP));
+    POSE_CK(cudaMalloc(&W.d_out, sizeof(PoseOut) * capC));
+    if (rc == COSL_OK) {
+      W.capC = capC;
+      W.capPts = capP;
+    }
+  }
+  cudaStream_t st = W.stream;
+  POSE_CK(cudaMemcpyAsync(W.d_cams, cams.data(), sizeof(PoseCam) * C, cudaMemcpyHostToDevice, st));
+  POSE_CK(cudaMemcpyAsync(W.d_M, hM.data(), sizeof(double) * 3 * totA, cudaMemcpyHostToDevice, st));
+  POSE_CK(cudaMemcpyAsync(W.d_m, hm.data(), sizeof(double) * 2 * totA, cudaMemcpyHostToDevice, st));
+  POSE_CK(cudaMemcpyAsync(W.d_p, hp.data(), sizeof(double) * totA, cudaMemcpyHostToDevice, st));
   if (rc == COSL_OK) {
-    COSL_LAUNCH(pose_intracam_kernel, C, POSE_THREADS, 0, st, d_cams, d_M, d_m, d_p, d_W, cfg,
-                d_out);
+    COSL_LAUNCH(pose_intracam_kernel, C, POSE_THREADS, 0, st, W.d_cams, W.d_M, W.d_m, W.d_p, W.d_W,
+                cfg, W.d_out);
   }
   POSE_CK(cudaGetLastError());
-  POSE_CK(cudaMemcpyAsync(outs.data(), d_out, sizeof(PoseOut) * C, cudaMemcpyDeviceToHost, st));
+  POSE_CK(cudaMemcpyAsync(outs.data(), W.d_out, sizeof(PoseOut) * C, cudaMemcpyDeviceToHost, st));
   POSE_CK(cudaStreamSynchronize(st));
 #undef POSE_CK
-  cudaFree(d_cams);
-  cudaFree(d_M);
-  cudaFree(d_m);
-  cudaFree(d_p);
-  cudaFree(d_W);
-  cudaFree(d_out);
-  if (st) cudaStreamDestroy(st);
   if (rc != COSL_OK) return rc;
   for (int c = 0; c < C; ++c) {
     std::memcpy(R_opt + 9 * c, outs[c].R, sizeof(double) * 9);
