@@ -146,7 +146,7 @@ int alloc_group(cosl_klt* g) {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, klt_gain_fused, KLT_FUSED_THREADS, 0);
     g->fusedOK = ok && coop && perSM > 0 && !(g->cfg.compat & COSL_KLT_PASS_KERNELS);
     const int T = F * C;
-    g->fusedBlocks = std::max(1, std::min(div_up(T, KLT_FUSED_THREADS / 16), nsm * perSM));
+    g->fusedBlocks = std::max(1, std::min(div_up(T, KLT_GPB), nsm * perSM));
     COSL_CUDA(cudaMalloc(&g->d_waitset, sizeof(int) * ws.size()));
     COSL_CUDA(cudaMemcpy(g->d_waitset, ws.data(), sizeof(int) * ws.size(), cudaMemcpyHostToDevice));
     COSL_CUDA(cudaMalloc(&g->d_state, sizeof(float4) * 2 * (size_t)T));
@@ -268,7 +268,7 @@ int run_tracker(cosl_klt* g) {
   const float4* P1 = g->d_pyr[g->cur];
   const int wpb = 8;  // warps per block (2x2 tracker: one warp per slot)
   dim3 grid(div_up(g->F, wpb), g->C);
-  dim3 gridHalf(div_up(g->F, 16), g->C);  // gain tracker: one half-warp per slot
+  dim3 gridHalf(div_up(g->F, 256 / KLT_G), g->C);  // gain tracker: one lane group per slot
   g->timer.begin(g->secTrack, g->stream);
   if (g->cfg.trackWithGain && g->fusedOK) {
     KltLevels LV;

@@ -47,11 +47,39 @@ klt_front(const uint8_t* __restrict__ img, size_t imgPitch, size_t imgStride,
   const int x0 = blockIdx.x * FR_TW, y0 = blockIdx.y * FR_TH;
   const uint8_t* im = img + (size_t)cam * imgStride;
   const int tid = threadIdx.x;
-  // ---- u8 tile, halo 5
-  for (int i = tid; i < FR_UH * FR_UW; i += 256) {
-    const int uy = i / FR_UW, ux = i - uy * FR_UW;
-    const int gy = clampi(y0 - 5 + uy, 0, H - 1), gx = clampi(x0 - 5 + ux, 0, W - 1);
-    S.u.a.u8[uy][ux] = im[(size_t)gy * imgPitch + gx];
+  // ---- u8 tile, halo 5.  Interior tiles fetch aligned 32-bit words (x0 is a multiple of 64 and
+  // the pitch a multiple of 16), all loads of a thread in flight before the first shared store;
+  // tiles that touch the left/right image border clamp per byte.
+  if (x0 - 8 >= 0 && x0 + FR_TW + 8 <= W) {
+    constexpr int WPR = (FR_TW + 16) / 4;  // 20 words per row cover columns x0-8 .. x0+71
+    unsigned int wv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = tid + 256 * u;
+      if (i < FR_UH * WPR) {
+        const int uy = i / WPR, wx = i - uy * WPR;
+        const int gy = clampi(y0 - 5 + uy, 0, H - 1);
+        wv[u] = __ldg(reinterpret_cast<const unsigned int*>(im + (size_t)gy * imgPitch + (x0 - 8)) + wx);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = tid + 256 * u;
+      if (i < FR_UH * WPR) {
+        const int uy = i / WPR, wx = i - uy * WPR;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const int ux = 4 * wx + b - 3;  // column x0-8+4wx+b  ->  tile index relative to x0-5
+          if (ux >= 0 && ux < FR_UW) S.u.a.u8[uy][ux] = (unsigned char)((wv[u] >> (8 * b)) & 0xff);
+        }
+      }
+    }
+  } else {
+    for (int i = tid; i < FR_UH * FR_UW; i += 256) {
+      const int uy = i / FR_UW, ux = i - uy * FR_UW;
+      const int gy = clampi(y0 - 5 + uy, 0, H - 1), gx = clampi(x0 - 5 + ux, 0, W - 1);
+      S.u.a.u8[uy][ux] = im[(size_t)gy * imgPitch + gx];
+    }
   }
   __syncthreads();
   // ---- vertical pass of level 0 at the rows of the level-0 tile (clamped row coordinate)

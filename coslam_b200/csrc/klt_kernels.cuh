@@ -398,13 +398,28 @@ klt_nonmax_compact(const float* __restrict__ corn, int W, int H, int r,
   const int x0 = blockIdx.x * NM_T, y0 = blockIdx.y * NM_T;
   const int tid = threadIdx.x;
   int anyPos = 0;
-  for (int i = tid; i < TS * TS; i += 256) {
-    const int ty = i / TS, tx = i - ty * TS;
-    const int gy = clampi(y0 + ty - r, 0, H - 1), gx = clampi(x0 + tx - r, 0, W - 1);
-    const float v = cm[(size_t)gy * W + gx];
-    s_c[i] = v;
-    // only the inner tile can produce candidates
-    if (v > 0.f && ty >= r && ty < r + NM_T && tx >= r && tx < r + NM_T) anyPos = 1;
+  // stage the tile with up to 12 independent loads in flight per thread (one memory round trip)
+  for (int base = 0; base < TS * TS; base += 256 * 12) {
+    float v[12];
+#pragma unroll
+    for (int u = 0; u < 12; ++u) {
+      const int i = base + tid + 256 * u;
+      if (i < TS * TS) {
+        const int ty = i / TS, tx = i - ty * TS;
+        const int gy = clampi(y0 + ty - r, 0, H - 1), gx = clampi(x0 + tx - r, 0, W - 1);
+        v[u] = __ldg(&cm[(size_t)gy * W + gx]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 12; ++u) {
+      const int i = base + tid + 256 * u;
+      if (i < TS * TS) {
+        const int ty = i / TS, tx = i - ty * TS;
+        s_c[i] = v[u];
+        // only the inner tile can produce candidates
+        if (v[u] > 0.f && ty >= r && ty < r + NM_T && tx >= r && tx < r + NM_T) anyPos = 1;
+      }
+    }
   }
   if (!__syncthreads_or(anyPos)) return;  // nothing positive in the inner tile: no survivor
   // ---- horizontal pass (klt_detector_nonmax.cg:12-26 with ds = (1/W, 0)): the sequential

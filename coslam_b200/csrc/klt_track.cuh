@@ -1,10 +1,11 @@
 // klt_track.cuh -- the 3x3 Lucas-Kanade solve with gain (klt_tracker_with_gain.cg:42-148, host loop
 // v3d_gpuklt.cpp:205-305) for sm_100a.
 //
-// Mapping: one HALF-WARP (16 lanes) per feature slot, two slots per warp.  The (2hw+1)^2 window
-// pixels are spread over the 16 lanes in ROUNDS rounds (49 pixels -> 4 rounds), the ten running
-// sums are reduced with width-16 butterfly shuffles and every lane solves the 3x3 system in closed
-// form (adjugate), so control flow is uniform.
+// Mapping: one QUARTER-WARP (KLT_G = 8 lanes) per feature slot, four slots per warp.  The (2hw+1)^2
+// window pixels are spread over the 8 lanes in ROUNDS rounds (49 pixels -> 7 rounds, 87.5 % lane
+// use), the running sums are reduced with width-8 butterfly shuffles and every lane solves the 3x3
+// system in closed form (adjugate), so control flow is uniform.  The per-pass overhead (neighbour
+// wait, reduction, solve, publish) is paid once per warp, i.e. shared by four slots.
 //
 // Window sampling.  The window samples of a level are one texel apart (ds = 1 / w_level), so all
 // (2hw+1)^2 bilinear taps of a window share the fractional offsets of the window centre and their
@@ -19,11 +20,12 @@
 //   klt_gain_pass   one launch per (level, iteration) pass, like the reference's draw calls
 //   klt_gain_fused  ALL passes in one persistent cooperative launch:
 //     * per level, the I0 window samples (constant over the iterations of a level) are computed
-//       once and kept in registers, and a 12x12-texel tile of the current-frame pyramid around the
-//       feature is staged in shared memory (clamped 128-bit loads; TMA box loads cannot reproduce
-//       CLAMP_TO_EDGE, and at the coarse levels most windows straddle the border) -- the
-//       iterations then sample from shared memory; if a window drifts out of its tile the pass
-//       falls back to clamped global loads (same values, same arithmetic);
+//       once and kept in registers together with the I0-only sum of the normal matrix, and a
+//       12x12-texel tile of the current-frame pyramid around the feature is staged in shared memory
+//       (clamped 128-bit loads; TMA box loads cannot reproduce CLAMP_TO_EDGE, and at the coarse
+//       levels most windows straddle the border) -- the iterations then sample from shared memory;
+//       if a window drifts out of its tile the pass falls back to clamped global loads (same
+//       values, same arithmetic);
 //     * the only coupling between slots, the gain-smoothness term that reads beta of <= 8
 //       neighbour slots from the PREVIOUS pass, is synchronised without grid barriers and without
 //       fences: each slot publishes (pass number, beta) as ONE naturally atomic 8-byte word into a
@@ -39,7 +41,8 @@
 namespace coslam {
 
 constexpr int KLT_TW = 12;      // staged I1 tile side (texels): 2*hw + 2 + 2*margin with hw = 3
-constexpr int KLT_ROUNDS = 4;   // window pixels per lane on the fast path (<= 64 pixels)
+constexpr int KLT_G = 8;        // lanes per feature slot
+constexpr int KLT_ROUNDS = 7;   // window pixels per lane on the fast path (<= 56 pixels)
 
 struct KltCentre {
   float ax, ay;  // bilinear weights shared by the whole window
@@ -85,22 +88,29 @@ __device__ __forceinline__ float3 klt_fetch_global(const float4* __restrict__ lv
                    __ldg(&lv[(size_t)y1 * w + x0]), __ldg(&lv[(size_t)y1 * w + x1]), ax, ay);
 }
 
-__device__ __forceinline__ float half_sum(float v) {
+__device__ __forceinline__ float grp_sum(float v) {
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o, 16));
+  for (int o = KLT_G / 2; o > 0; o >>= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o, KLT_G));
   return v;
 }
 
 struct KltAcc {
-  float a0, a1, a2, d0, d1, d2, r0, r1, r2, ssd;
+  float a0, a1, a2, d0, d1, r0, r1, r2, ssd;
 };
 
+// the I0-only entry of the normal matrix (constant over the iterations of a level)
+__device__ __forceinline__ float klt_d2_term(const float3 I0, float lambda, float delta) {
+  const float g0 = sqrtf(__fmaf_rn(I0.y, I0.y, __fmul_rn(I0.z, I0.z)));
+  return __fmaf_rn(delta, 8.0f, __fmaf_rn(__fmul_rn(lambda, g0), g0, __fmul_rn(I0.x, I0.x)));
+}
+
+// halfW = 0.5 * W, halfH = 0.5 * H (the factor 0.5 is exact, so (x * W) * 0.5 == x * (0.5 W))
 __device__ __forceinline__ void klt_acc_pixel(KltAcc& A, const float3 I0, const float3 I1, float beta,
-                                              float nbterm, float Wf, float Hf, float lambda,
+                                              float nbterm, float halfW, float halfH, float lambda,
                                               float delta) {
   const float e = __fmaf_rn(beta, I0.x, -I1.x);
-  const float Jx = __fmul_rn(__fmul_rn(__fmaf_rn(beta, I0.y, I1.y), Wf), 0.5f);
-  const float Jy = __fmul_rn(__fmul_rn(__fmaf_rn(beta, I0.z, I1.z), Hf), 0.5f);
+  const float Jx = __fmul_rn(__fmaf_rn(beta, I0.y, I1.y), halfW);
+  const float Jy = __fmul_rn(__fmaf_rn(beta, I0.z, I1.z), halfH);
   const float n0 = __fmaf_rn(I0.y, I0.y, __fmul_rn(I0.z, I0.z));
   const float n1 = __fmaf_rn(I1.y, I1.y, __fmul_rn(I1.z, I1.z));
   const float g0 = sqrtf(n0);  // -prec-sqrt=false for klt.cu: MUFU based
@@ -110,7 +120,6 @@ __device__ __forceinline__ void klt_acc_pixel(KltAcc& A, const float3 I0, const 
   A.a2 = __fmaf_rn(Jx, -I0.x, A.a2);
   A.d0 = __fmaf_rn(Jy, Jy, A.d0);
   A.d1 = __fmaf_rn(Jy, -I0.x, A.d1);
-  A.d2 = __fadd_rn(A.d2, __fmaf_rn(delta, 8.0f, __fmaf_rn(__fmul_rn(lambda, g0), g0, __fmul_rn(I0.x, I0.x))));
   A.r0 = __fmaf_rn(e, Jx, A.r0);
   A.r1 = __fmaf_rn(e, Jy, A.r1);
   const float t = __fmaf_rn(__fmul_rn(lambda, g0), __fmaf_rn(-beta, g0, g1), __fmul_rn(-e, I0.x));
@@ -118,13 +127,14 @@ __device__ __forceinline__ void klt_acc_pixel(KltAcc& A, const float3 I0, const 
   A.ssd = __fmaf_rn(e, e, A.ssd);
 }
 
-// reduce over the half-warp, solve, test (klt_tracker_with_gain.cg:12-40,124-147)
-__device__ __forceinline__ float4 klt_gain_finish(KltAcc A, float X1x, float X1y, float beta,
+// reduce over the lane group, solve, test (klt_tracker_with_gain.cg:12-40,124-147)
+// f = group sum of klt_d2_term over the window
+__device__ __forceinline__ float4 klt_gain_finish(KltAcc A, float f, float X1x, float X1y, float beta,
                                                   const KltTrackParams& P) {
-  const float a = half_sum(A.a0), b = half_sum(A.a1), c = half_sum(A.a2);
-  const float d = half_sum(A.d0), e = half_sum(A.d1), f = half_sum(A.d2);
-  const float r0 = half_sum(A.r0), r1 = half_sum(A.r1), r2 = half_sum(A.r2);
-  const float ssd = half_sum(A.ssd);
+  const float a = grp_sum(A.a0), b = grp_sum(A.a1), c = grp_sum(A.a2);
+  const float d = grp_sum(A.d0), e = grp_sum(A.d1);
+  const float r0 = grp_sum(A.r0), r1 = grp_sum(A.r1), r2 = grp_sum(A.r2);
+  const float ssd = grp_sum(A.ssd);
   // det3x3symm: a*d*f + 2*b*c*e - (a*e*e + b*b*f + c*c*d)
   const float detp = __fmaf_rn(__fmul_rn(2.0f, __fmul_rn(b, c)), e, __fmul_rn(__fmul_rn(a, d), f));
   const float detm = __fmaf_rn(__fmul_rn(c, c), d, __fmaf_rn(__fmul_rn(b, b), f, __fmul_rn(__fmul_rn(a, e), e)));
@@ -150,21 +160,22 @@ __device__ __forceinline__ float4 klt_gain_finish(KltAcc A, float X1x, float X1y
 }
 
 // dot(float4(1), betaN1 + betaN2 - 2*beta) of klt_tracker_with_gain.cg:111 from the eight
-// neighbour gains held by half-lanes 0..7 (bn); invalid (< 0) neighbours count as own beta
-__device__ __forceinline__ float klt_nbterm(float bn, float beta, int hl, int halfBase) {
+// neighbour gains held by the 8 lanes of the group (bn); invalid (< 0) neighbours count as own beta
+__device__ __forceinline__ float klt_nbterm(float bn, float beta, int gl, int grpBase) {
   bn = (bn < 0.f) ? beta : bn;
-  const float hi = __shfl_sync(0xffffffffu, bn, halfBase + (hl & 3) + 4);
+  const float hi = __shfl_sync(0xffffffffu, bn, grpBase + (gl & 3) + 4);
   const float s4 = __fsub_rn(__fadd_rn(bn, hi), __fmul_rn(2.0f, beta));
-  const float s0 = __shfl_sync(0xffffffffu, s4, halfBase + 0);
-  const float s1 = __shfl_sync(0xffffffffu, s4, halfBase + 1);
-  const float s2 = __shfl_sync(0xffffffffu, s4, halfBase + 2);
-  const float s3 = __shfl_sync(0xffffffffu, s4, halfBase + 3);
+  const float s0 = __shfl_sync(0xffffffffu, s4, grpBase + 0);
+  const float s1 = __shfl_sync(0xffffffffu, s4, grpBase + 1);
+  const float s2 = __shfl_sync(0xffffffffu, s4, grpBase + 2);
+  const float s3 = __shfl_sync(0xffffffffu, s4, grpBase + 3);
   return __fadd_rn(__fadd_rn(__fadd_rn(s0, s1), s2), s3);
 }
 
+
 // ------------------------------------------------------------------------------------------
-// One pass per launch (diagnostic / fallback).  Grid: x = ceil(F / 16) blocks of 256 threads
-// (16 half-warps), y = camera.
+// One pass per launch (diagnostic / fallback).  Grid: x = ceil(F / 32) blocks of 256 threads
+// (32 lane groups), y = camera.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 klt_gain_pass(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1, long long pyrStride,
@@ -174,8 +185,8 @@ klt_gain_pass(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1, 
   (void)dsx;
   (void)dsy;
   const int cam = blockIdx.y;
-  const int hl = threadIdx.x & 15, halfBase = threadIdx.x & 16;
-  int slot = blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
+  const int gl = threadIdx.x & (KLT_G - 1), grpBase = threadIdx.x & (32 - KLT_G);
+  int slot = blockIdx.x * (blockDim.x / KLT_G) + (threadIdx.x / KLT_G);
   const bool active = slot < P.F;
   if (!active) slot = P.F - 1;  // keep the whole warp in the shuffles; result is discarded
   const float4* L0 = pyr0 + (size_t)cam * pyrStride + lvOff;
@@ -185,25 +196,26 @@ klt_gain_pass(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1, 
   float4 cur = in[fb + slot];
   if (firstPass) cur.z = 1.0f;  // gain cleared to 1 before the first pass (v3d_gpuklt.cpp:223-227)
   const float beta = cur.z;
-  float bn = 0.f;
-  if (hl < 8) bn = firstPass ? 1.0f : in[fb + nbr[slot * 8 + hl]].z;
-  const float nbterm = klt_nbterm(bn, beta, hl, halfBase);
+  const float bn = firstPass ? 1.0f : in[fb + nbr[slot * 8 + gl]].z;
+  const float nbterm = klt_nbterm(bn, beta, gl, grpBase);
   const bool pre_invalid = (cur.x < 0.f) || (x0.x < 0.f);
   const int hw = P.halfWidth, fwid = 2 * hw + 1, npx = fwid * fwid;
-  const float Wf = (float)P.W, Hf = (float)P.H;
+  const float halfW = 0.5f * (float)P.W, halfH = 0.5f * (float)P.H;
   const KltCentre c0 = klt_centre(w, h, x0.x, x0.y);
   const KltCentre c1 = klt_centre(w, h, cur.x, cur.y);
-  KltAcc A = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  for (int p = hl; p < npx; p += 16) {
+  KltAcc A = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  float d2 = 0.f;
+  for (int p = gl; p < npx; p += KLT_G) {
     const int py = p / fwid, px = p - py * fwid;
     const int dx = px - hw, dy = py - hw;
     const float3 I0 = klt_fetch_global(L0, w, h, c0.xi + dx, c0.yi + dy, c0.ax, c0.ay);
     const float3 I1 = klt_fetch_global(L1, w, h, c1.xi + dx, c1.yi + dy, c1.ax, c1.ay);
-    klt_acc_pixel(A, I0, I1, beta, nbterm, Wf, Hf, P.lambda, P.delta);
+    d2 = __fadd_rn(d2, klt_d2_term(I0, P.lambda, P.delta));
+    klt_acc_pixel(A, I0, I1, beta, nbterm, halfW, halfH, P.lambda, P.delta);
   }
-  float4 res = klt_gain_finish(A, cur.x, cur.y, beta, P);
+  float4 res = klt_gain_finish(A, grp_sum(d2), cur.x, cur.y, beta, P);
   if (pre_invalid) res = make_float4(-1.f, -1.f, -1.f, 0.f);
-  if (hl == 0 && active) out[fb + slot] = res;
+  if (gl == 0 && active) out[fb + slot] = res;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -212,8 +224,9 @@ klt_gain_pass(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1, 
 //   atomic 8-byte word, so publishing needs no fence and a reader gets beta with the poll itself;
 //   state[T] float4 holds (x, y, beta) of items that are not register-resident
 //   waitset[F][16]: first 8 = neighbours (values + versions), last 8 = reverse neighbours or -1
-// Work item = (camera, slot); half-warp q (global index) owns items q, q + Q, ...; the first item
-// of a half-warp uses the shared-memory tile, further items (only when T > Q) the global path.
+// Work item = (camera, slot); lane group q (global index) owns items q, q + Q, ...; the first item
+// of a group is "resident": its invariants, I0 samples and state live in registers and its I1 tile
+// in shared memory; further items (only when T > Q) take the global path.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
   unsigned long long v;
@@ -224,40 +237,46 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned l
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-constexpr int KLT_FUSED_THREADS = 128;  // 8 half-warps per CTA
+constexpr int KLT_FUSED_THREADS = 128;                  // 16 lane groups per CTA
+constexpr int KLT_GPB = KLT_FUSED_THREADS / KLT_G;
 
-__global__ void __launch_bounds__(KLT_FUSED_THREADS, 7)
+__global__ void __launch_bounds__(KLT_FUSED_THREADS, 4)
 klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
                long long pyrStride, KltLevels LV, int nIter, const float4* __restrict__ X0buf,
                float4* __restrict__ state, unsigned long long* __restrict__ rec,
                const int* __restrict__ waitset,
                float4* __restrict__ out, int C, KltTrackParams Plax, KltTrackParams Pstrict,
                int verBase) {
-  __shared__ float4 s_tile[KLT_FUSED_THREADS / 16][KLT_TW * KLT_TW];  // one tile per half-warp
-  const int hl = threadIdx.x & 15, halfBase = threadIdx.x & 16;
-  const int halfInBlock = threadIdx.x >> 4;
-  const int q = blockIdx.x * (KLT_FUSED_THREADS / 16) + halfInBlock;
-  const int Q = gridDim.x * (KLT_FUSED_THREADS / 16);
+  __shared__ float4 s_tile[KLT_GPB][KLT_TW * KLT_TW];  // one tile per lane group
+  const int gl = threadIdx.x & (KLT_G - 1), grpBase = threadIdx.x & (32 - KLT_G);
+  const int grpInBlock = threadIdx.x / KLT_G;
+  const int q = blockIdx.x * KLT_GPB + grpInBlock;
+  const int Q = gridDim.x * KLT_GPB;
   const int F = Plax.F;
   const int T = C * F;
   const int hw = Plax.halfWidth, fwid = 2 * hw + 1, npx = fwid * fwid;
-  const bool fast = (npx <= 16 * KLT_ROUNDS) && (2 * hw + 2 + 2 <= KLT_TW);
-  const float Wf = (float)Plax.W, Hf = (float)Plax.H;
-  const float4* tile = s_tile[halfInBlock];
-  // both halves of a warp must execute the same number of outer iterations (full-mask shuffles)
+  const bool fast = (npx <= KLT_G * KLT_ROUNDS) && (2 * hw + 2 + 2 <= KLT_TW);
+  const float halfW = 0.5f * (float)Plax.W, halfH = 0.5f * (float)Plax.H;
+  float4* tile = s_tile[grpInBlock];
+  // all groups of a warp must execute the same number of outer iterations (full-mask shuffles)
   const int nOwn = (T + Q - 1) / Q;
 
-  // window offsets of this lane's pixels, hoisted out of every loop
-  int dxr[KLT_ROUNDS], dyr[KLT_ROUNDS];
+  // ---- invariants of the resident item
+  const bool active0 = q < T;
+  const int item0 = active0 ? q : T - 1;
+  const int cam0 = item0 / F, slot0 = item0 - cam0 * F;
+  const float4 x00 = X0buf[item0];
+  const int wsA0 = waitset[slot0 * 16 + gl], wsB0 = waitset[slot0 * 16 + 8 + gl];
+  // tile offset of this lane's window pixels
+  int toff[KLT_ROUNDS];
 #pragma unroll
   for (int r = 0; r < KLT_ROUNDS; ++r) {
-    const int p = min(hl + 16 * r, npx - 1);
+    const int p = min(gl + KLT_G * r, npx - 1);
     const int py = p / fwid, px = p - py * fwid;
-    dxr[r] = px - hw;
-    dyr[r] = py - hw;
+    toff[r] = (py - hw) * KLT_TW + (px - hw);
   }
-  // state of the FIRST owned item lives in registers across passes
   float3 I0r[KLT_ROUNDS];
+  float f0 = 0.f;  // group sum of klt_d2_term of the resident item at the current level
   float4 cur0 = make_float4(-1.f, -1.f, -1.f, 0.f);
   int tx0 = 0, ty0 = 0;
 
@@ -270,70 +289,91 @@ klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
       const bool strict = (it == nIter) && (it != 1);
       const int rd = (pass - 1) & 1, wr = pass & 1;
       for (int own = 0; own < nOwn; ++own) {
-        int item = q + own * Q;
-        const bool active = item < T;
-        if (!active) item = T - 1;
-        const int cam = item / F, slot = item - cam * F;
-        const float4* L0 = pyr0 + (size_t)cam * pyrStride + LV.off[li];
-        const float4* L1 = pyr1 + (size_t)cam * pyrStride + LV.off[li];
-        const float4 x0 = X0buf[item];
         const bool staged = fast && (own == 0);
+        int item = item0, cam = cam0, wsA = wsA0, wsB = wsB0;
+        bool active = active0;
+        float4 x0 = x00;
+        if (own != 0) {
+          item = q + own * Q;
+          active = item < T;
+          if (!active) item = T - 1;
+          cam = item / F;
+          const int slot = item - cam * F;
+          x0 = X0buf[item];
+          wsA = waitset[slot * 16 + gl];
+          wsB = waitset[slot * 16 + 8 + gl];
+        }
         float4 cur;
-        float bn = 0.f;
+        float bn;
         if (pass == 1) {
           cur = make_float4(x0.x, x0.y, 1.0f, 0.f);  // X1 <- X0, gain cleared to 1 (:223-227)
-          if (hl < 8) bn = 1.0f;
+          bn = 1.0f;
         } else {
           // wait for the pass-(p-1) records of everything this slot reads or is read by; the
           // first 8 entries also deliver the neighbour gains
+          bn = -1.0f;
           if (active) {
-            const int nb = waitset[slot * 16 + hl];
-            if (nb >= 0) {
-              const unsigned long long* rp = rec + (size_t)rd * T + (size_t)cam * F + nb;
-              const int need = verBase + pass - 1;
-              unsigned long long v = ld_relaxed_u64(rp);
-              while ((int)(v >> 32) < need) {
-                __nanosleep(20);
-                v = ld_relaxed_u64(rp);
-              }
-              bn = __uint_as_float((unsigned)v);
+            const unsigned long long* rb = rec + (size_t)rd * T + (size_t)cam * F;
+            const int need = verBase + pass - 1;
+            // wsA is always a valid slot (neighbour lists are clamped), wsB may be -1
+            const unsigned long long* ra = rb + wsA;
+            const unsigned long long* rbp = rb + (wsB >= 0 ? wsB : wsA);
+            unsigned long long va = ld_relaxed_u64(ra), vb = ld_relaxed_u64(rbp);
+            while ((int)(va >> 32) < need) {
+              __nanosleep(20);
+              va = ld_relaxed_u64(ra);
             }
+            while ((int)(vb >> 32) < need) {
+              __nanosleep(20);
+              vb = ld_relaxed_u64(rbp);
+            }
+            bn = __uint_as_float((unsigned)va);
           }
           __syncwarp();
           cur = (staged) ? cur0 : __ldcg(&state[item]);
         }
         const float beta = cur.z;
-        const float nbterm = klt_nbterm(bn, beta, hl, halfBase);
+        const float nbterm = klt_nbterm(bn, beta, gl, grpBase);
         const bool pre_invalid = (cur.x < 0.f) || (x0.x < 0.f);
         const KltCentre c1 = klt_centre(w, h, cur.x, cur.y);
         // ---- per-level staging (first iteration of a level): I0 samples + I1 tile
         if (staged && it == 1) {
+          const float4* L0 = pyr0 + (size_t)cam * pyrStride + LV.off[li];
+          const float4* L1 = pyr1 + (size_t)cam * pyrStride + LV.off[li];
           const KltCentre c0 = klt_centre(w, h, x0.x, x0.y);
+          float d2 = 0.f;
 #pragma unroll
           for (int r = 0; r < KLT_ROUNDS; ++r) {
-            const int p = hl + 16 * r;
+            const int p = gl + KLT_G * r;
+            const int py = p / fwid, px = p - py * fwid;
             I0r[r] = (p < npx && !pre_invalid)
-                         ? klt_fetch_global(L0, w, h, c0.xi + dxr[r], c0.yi + dyr[r], c0.ax, c0.ay)
+                         ? klt_fetch_global(L0, w, h, c0.xi + px - hw, c0.yi + py - hw, c0.ax, c0.ay)
                          : make_float3(0.f, 0.f, 0.f);
+            if (p < npx) d2 = __fadd_rn(d2, klt_d2_term(I0r[r], Plax.lambda, Plax.delta));
           }
+          f0 = grp_sum(d2);
           tx0 = c1.xi - hw - 2;
           ty0 = c1.yi - hw - 2;
           if (!pre_invalid) {
-            float4* tw = s_tile[halfInBlock];
-            float4 tv[KLT_TW * KLT_TW / 16];
+            constexpr int NLD = KLT_TW * KLT_TW / KLT_G;  // 18 texels per lane, two batches of 9
 #pragma unroll
-            for (int u = 0; u < KLT_TW * KLT_TW / 16; ++u) {  // all 9 loads in flight first
-              const int i = hl + 16 * u;
-              const int b = i / KLT_TW, a = i - b * KLT_TW;
-              tv[u] = __ldg(&L1[(size_t)clampi(ty0 + b, 0, h - 1) * w + clampi(tx0 + a, 0, w - 1)]);
+            for (int half = 0; half < 2; ++half) {
+              float4 tv[NLD / 2];
+#pragma unroll
+              for (int u = 0; u < NLD / 2; ++u) {  // all loads of a batch in flight first
+                const int i = gl + KLT_G * (u + half * (NLD / 2));
+                const int b = i / KLT_TW, a = i - b * KLT_TW;
+                tv[u] = __ldg(&L1[(size_t)clampi(ty0 + b, 0, h - 1) * w + clampi(tx0 + a, 0, w - 1)]);
+              }
+#pragma unroll
+              for (int u = 0; u < NLD / 2; ++u) tile[gl + KLT_G * (u + half * (NLD / 2))] = tv[u];
             }
-#pragma unroll
-            for (int u = 0; u < KLT_TW * KLT_TW / 16; ++u) tw[hl + 16 * u] = tv[u];
           }
           __syncwarp();
         }
         // ---- the iteration
-        KltAcc A = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+        KltAcc A = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        float f = f0;
         if (!pre_invalid) {
           // tile[b * KLT_TW + a] == level[clamp(ty0 + b)][clamp(tx0 + a)]: indexing with the
           // unclamped tap coordinates reproduces the clamped fetches exactly
@@ -344,35 +384,49 @@ klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
             const float4* tc = tile + b0 * KLT_TW + a0;
 #pragma unroll
             for (int r = 0; r < KLT_ROUNDS; ++r) {
-              if (hl + 16 * r < npx) {
-                const float4* t4 = tc + dyr[r] * KLT_TW + dxr[r];
+              if (gl + KLT_G * r < npx) {
+                const float4* t4 = tc + toff[r];
                 const float3 I1 = klt_lerp4(t4[0], t4[1], t4[KLT_TW], t4[KLT_TW + 1], c1.ax, c1.ay);
-                klt_acc_pixel(A, I0r[r], I1, beta, nbterm, Wf, Hf, Plax.lambda, Plax.delta);
+                klt_acc_pixel(A, I0r[r], I1, beta, nbterm, halfW, halfH, Plax.lambda, Plax.delta);
               }
             }
           } else if (staged) {
-#pragma unroll
+            const float4* L1 = pyr1 + (size_t)cam * pyrStride + LV.off[li];
+#pragma unroll 1
             for (int r = 0; r < KLT_ROUNDS; ++r) {
-              if (hl + 16 * r < npx) {
-                const float3 I1 = klt_fetch_global(L1, w, h, c1.xi + dxr[r], c1.yi + dyr[r], c1.ax, c1.ay);
-                klt_acc_pixel(A, I0r[r], I1, beta, nbterm, Wf, Hf, Plax.lambda, Plax.delta);
+              const int p = gl + KLT_G * r;
+              if (p < npx) {
+                const int py = p / fwid, px = p - py * fwid;
+                const float3 I1 = klt_fetch_global(L1, w, h, c1.xi + px - hw, c1.yi + py - hw, c1.ax, c1.ay);
+                // I0r is indexed dynamically only on this rare path
+                float3 I0 = I0r[0];
+#pragma unroll
+                for (int k = 1; k < KLT_ROUNDS; ++k)
+                  if (r == k) I0 = I0r[k];
+                klt_acc_pixel(A, I0, I1, beta, nbterm, halfW, halfH, Plax.lambda, Plax.delta);
               }
             }
           } else {
+            const float4* L0 = pyr0 + (size_t)cam * pyrStride + LV.off[li];
+            const float4* L1 = pyr1 + (size_t)cam * pyrStride + LV.off[li];
             const KltCentre c0 = klt_centre(w, h, x0.x, x0.y);
-            for (int p = hl; p < npx; p += 16) {
+            float d2 = 0.f;
+            for (int p = gl; p < npx; p += KLT_G) {
               const int py = p / fwid, px = p - py * fwid;
               const int dx = px - hw, dy = py - hw;
               const float3 I0 = klt_fetch_global(L0, w, h, c0.xi + dx, c0.yi + dy, c0.ax, c0.ay);
               const float3 I1 = klt_fetch_global(L1, w, h, c1.xi + dx, c1.yi + dy, c1.ax, c1.ay);
-              klt_acc_pixel(A, I0, I1, beta, nbterm, Wf, Hf, Plax.lambda, Plax.delta);
+              d2 = __fadd_rn(d2, klt_d2_term(I0, Plax.lambda, Plax.delta));
+              klt_acc_pixel(A, I0, I1, beta, nbterm, halfW, halfH, Plax.lambda, Plax.delta);
             }
+            f = d2;
           }
         }
-        float4 res = klt_gain_finish(A, cur.x, cur.y, beta, strict ? Pstrict : Plax);
+        if (!staged) f = grp_sum(f);  // warp-uniform branch: staged depends on own only
+        float4 res = klt_gain_finish(A, f, cur.x, cur.y, beta, strict ? Pstrict : Plax);
         if (pre_invalid) res = make_float4(-1.f, -1.f, -1.f, 0.f);
         if (staged) cur0 = res;
-        if (hl == 0 && active) {
+        if (gl == 0 && active) {
           if (pass == LV.n * nIter) out[item] = res;
           if (!staged) __stcg(&state[item], res);
           st_relaxed_u64(rec + (size_t)wr * T + item,
