@@ -12,7 +12,8 @@ from .ctypes_defs import (COSL_BA_INFOSZ, FEAT_DTYPE, BaOptions, BaProblem, KltC
                           PoseOpt)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcoslam_b200.so")
+# COSLAM_B200_LIB selects another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("COSLAM_B200_LIB") or os.path.join(_HERE, "libcoslam_b200.so")
 
 
 class CoslError(RuntimeError):

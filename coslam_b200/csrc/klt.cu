@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <new>
 #include <vector>
 
@@ -291,8 +292,6 @@ int run_tracker(cosl_klt* g) {
     long long pyrStride = g->pyrStride;
     KltTrackParams Plax = track_params(g, false), Pstrict = track_params(g, true);
     int verBase = g->verBase;
-    static const bool noSync = std::getenv("COSL_KLT_NOSYNC") != nullptr;  // timing experiment only
-    if (noSync) verBase = -1000000000;
     void* args[] = {(void*)&P0,          (void*)&P1,     (void*)&pyrStride, (void*)&LV,
                     (void*)&nIter,       (void*)&g->d_src, (void*)&g->d_state, (void*)&g->d_ver,
                     (void*)&g->d_waitset, (void*)&g->d_res, (void*)&C,        (void*)&Plax,
@@ -301,6 +300,30 @@ int run_tracker(cosl_klt* g) {
                                           dim3(KLT_FUSED_THREADS), args, 0, g->stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
     g->verBase += nPass;
+#if KLT_EXP_CLOCK
+    {
+      static int calls = 0;
+      if (++calls == 50) {
+        cudaStreamSynchronize(g->stream);
+        const int nw = g->fusedBlocks * KLT_FUSED_THREADS / 32;
+        std::vector<float> hs((size_t)nw * 8);
+        cudaMemcpy(hs.data(), g->d_state, sizeof(float) * hs.size(), cudaMemcpyDeviceToHost);
+        double acc[6] = {0, 0, 0, 0, 0, 0}, mx = 0;
+        unsigned s0 = ~0u, s1 = 0, e0 = ~0u, e1 = 0;
+        for (int i = 0; i < nw; ++i) {
+          for (int k = 0; k < 6; ++k) acc[k] += hs[(size_t)i * 8 + k];
+          mx = std::max(mx, (double)hs[(size_t)i * 8 + 5]);
+          unsigned a, b;
+          memcpy(&a, &hs[(size_t)i * 8 + 6], 4);
+          memcpy(&b, &hs[(size_t)i * 8 + 7], 4);
+          s0 = std::min(s0, a); s1 = std::max(s1, a); e0 = std::min(e0, b); e1 = std::max(e1, b);
+        }
+        fprintf(stderr, "[klt clock] globaltimer ns: start spread %u, end spread %u, first start -> last end %u, last start -> first end %u\n", s1 - s0, e1 - e0, e1 - s0, e0 - s1);
+        fprintf(stderr, "[klt clock] warps %d  mean cycles: poll %.0f  pre+stage %.0f  loop %.0f  finish %.0f  (stage-only %.0f)  total %.0f max %.0f\n", nw,
+                acc[0] / nw, acc[1] / nw, acc[2] / nw, acc[3] / nw, acc[4] / nw, acc[5] / nw, mx);
+      }
+    }
+#endif
   } else if (g->cfg.trackWithGain) {
     const float4* in = g->d_src;
     float4* bufs[2] = {g->d_ping, g->d_pong};

@@ -41,6 +41,11 @@
 namespace coslam {
 
 constexpr int KLT_TW = 12;      // staged I1 tile side (texels): 2*hw + 2 + 2*margin with hw = 3
+// Row pitch of the tile in shared memory.  A lane group reads 8 consecutive window pixels
+// p = 7*py + px per LDS.128, i.e. float4 index p + py*(pitch - 7); with pitch = 15 that is
+// p (mod 8), so the 8 lanes of a quarter-warp hit 8 distinct 16-byte bank groups (pitch 12 gave
+// 2-way conflicts on every tap).
+constexpr int KLT_TP = 15;
 constexpr int KLT_G = 8;        // lanes per feature slot
 constexpr int KLT_ROUNDS = 7;   // window pixels per lane on the fast path (<= 56 pixels)
 
@@ -94,27 +99,37 @@ __device__ __forceinline__ float grp_sum(float v) {
   return v;
 }
 
+// sqrt.approx.ftz: one MUFU, no denormal rescaling (gradient magnitudes here are 0 or >> 1e-38)
+__device__ __forceinline__ float klt_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 struct KltAcc {
   float a0, a1, a2, d0, d1, r0, r1, r2, ssd;
 };
 
 // the I0-only entry of the normal matrix (constant over the iterations of a level)
 __device__ __forceinline__ float klt_d2_term(const float3 I0, float lambda, float delta) {
-  const float g0 = sqrtf(__fmaf_rn(I0.y, I0.y, __fmul_rn(I0.z, I0.z)));
+  const float g0 = klt_sqrt(__fmaf_rn(I0.y, I0.y, __fmul_rn(I0.z, I0.z)));
   return __fmaf_rn(delta, 8.0f, __fmaf_rn(__fmul_rn(lambda, g0), g0, __fmul_rn(I0.x, I0.x)));
 }
 
 // halfW = 0.5 * W, halfH = 0.5 * H (the factor 0.5 is exact, so (x * W) * 0.5 == x * (0.5 W))
+// The neighbour term delta * nbterm of klt_tracker_with_gain.cg:111 is the same for every window
+// pixel; it is added once, as npx * (delta * nbterm), in klt_gain_finish (the shader adds it per
+// pixel -- a rounding-level difference, inside the LK parity tolerance), so the pixel loop does
+// not depend on the neighbours' gains.
 __device__ __forceinline__ void klt_acc_pixel(KltAcc& A, const float3 I0, const float3 I1, float beta,
-                                              float nbterm, float halfW, float halfH, float lambda,
-                                              float delta) {
+                                              float halfW, float halfH, float lambda) {
   const float e = __fmaf_rn(beta, I0.x, -I1.x);
   const float Jx = __fmul_rn(__fmaf_rn(beta, I0.y, I1.y), halfW);
   const float Jy = __fmul_rn(__fmaf_rn(beta, I0.z, I1.z), halfH);
   const float n0 = __fmaf_rn(I0.y, I0.y, __fmul_rn(I0.z, I0.z));
   const float n1 = __fmaf_rn(I1.y, I1.y, __fmul_rn(I1.z, I1.z));
-  const float g0 = sqrtf(n0);  // -prec-sqrt=false for klt.cu: MUFU based
-  const float g1 = sqrtf(n1);
+  const float g0 = klt_sqrt(n0);
+  const float g1 = klt_sqrt(n1);
   A.a0 = __fmaf_rn(Jx, Jx, A.a0);
   A.a1 = __fmaf_rn(Jx, Jy, A.a1);
   A.a2 = __fmaf_rn(Jx, -I0.x, A.a2);
@@ -123,17 +138,19 @@ __device__ __forceinline__ void klt_acc_pixel(KltAcc& A, const float3 I0, const 
   A.r0 = __fmaf_rn(e, Jx, A.r0);
   A.r1 = __fmaf_rn(e, Jy, A.r1);
   const float t = __fmaf_rn(__fmul_rn(lambda, g0), __fmaf_rn(-beta, g0, g1), __fmul_rn(-e, I0.x));
-  A.r2 = __fadd_rn(A.r2, __fmaf_rn(delta, nbterm, t));
+  A.r2 = __fadd_rn(A.r2, t);
   A.ssd = __fmaf_rn(e, e, A.ssd);
 }
 
 // reduce over the lane group, solve, test (klt_tracker_with_gain.cg:12-40,124-147)
 // f = group sum of klt_d2_term over the window
-__device__ __forceinline__ float4 klt_gain_finish(KltAcc A, float f, float X1x, float X1y, float beta,
+__device__ __forceinline__ float4 klt_gain_finish(KltAcc A, float f, float nbterm, float npxf,
+                                                  float X1x, float X1y, float beta,
                                                   const KltTrackParams& P) {
   const float a = grp_sum(A.a0), b = grp_sum(A.a1), c = grp_sum(A.a2);
   const float d = grp_sum(A.d0), e = grp_sum(A.d1);
-  const float r0 = grp_sum(A.r0), r1 = grp_sum(A.r1), r2 = grp_sum(A.r2);
+  const float r0 = grp_sum(A.r0), r1 = grp_sum(A.r1);
+  const float r2 = __fmaf_rn(npxf, __fmul_rn(P.delta, nbterm), grp_sum(A.r2));
   const float ssd = grp_sum(A.ssd);
   // det3x3symm: a*d*f + 2*b*c*e - (a*e*e + b*b*f + c*c*d)
   const float detp = __fmaf_rn(__fmul_rn(2.0f, __fmul_rn(b, c)), e, __fmul_rn(__fmul_rn(a, d), f));
@@ -211,9 +228,9 @@ klt_gain_pass(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1, 
     const float3 I0 = klt_fetch_global(L0, w, h, c0.xi + dx, c0.yi + dy, c0.ax, c0.ay);
     const float3 I1 = klt_fetch_global(L1, w, h, c1.xi + dx, c1.yi + dy, c1.ax, c1.ay);
     d2 = __fadd_rn(d2, klt_d2_term(I0, P.lambda, P.delta));
-    klt_acc_pixel(A, I0, I1, beta, nbterm, halfW, halfH, P.lambda, P.delta);
+    klt_acc_pixel(A, I0, I1, beta, halfW, halfH, P.lambda);
   }
-  float4 res = klt_gain_finish(A, grp_sum(d2), cur.x, cur.y, beta, P);
+  float4 res = klt_gain_finish(A, grp_sum(d2), nbterm, (float)npx, cur.x, cur.y, beta, P);
   if (pre_invalid) res = make_float4(-1.f, -1.f, -1.f, 0.f);
   if (gl == 0 && active) out[fb + slot] = res;
 }
@@ -233,21 +250,41 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+// same load without the compiler-level memory barrier: a hint whose result is re-validated
+__device__ __forceinline__ unsigned long long ld_hint_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-constexpr int KLT_FUSED_THREADS = 128;                  // 16 lane groups per CTA
+#ifndef KLT_EXP_CLOCK
+#define KLT_EXP_CLOCK 0  // per-section cycle counters written to state[] (experiment builds)
+#endif
+#if KLT_EXP_CLOCK
+#define KLT_CLK(v) const long long v = clock64()
+#else
+#define KLT_CLK(v)
+#endif
+#ifndef KLT_FUSED_THREADS_N
+#define KLT_FUSED_THREADS_N 128
+#endif
+#ifndef KLT_FUSED_MINBLOCKS
+#define KLT_FUSED_MINBLOCKS 4
+#endif
+constexpr int KLT_FUSED_THREADS = KLT_FUSED_THREADS_N;  // 16 lane groups per CTA
 constexpr int KLT_GPB = KLT_FUSED_THREADS / KLT_G;
 
-__global__ void __launch_bounds__(KLT_FUSED_THREADS, 4)
+__global__ void __launch_bounds__(KLT_FUSED_THREADS, KLT_FUSED_MINBLOCKS)
 klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
                long long pyrStride, KltLevels LV, int nIter, const float4* __restrict__ X0buf,
                float4* __restrict__ state, unsigned long long* __restrict__ rec,
                const int* __restrict__ waitset,
                float4* __restrict__ out, int C, KltTrackParams Plax, KltTrackParams Pstrict,
                int verBase) {
-  __shared__ float4 s_tile[KLT_GPB][KLT_TW * KLT_TW];  // one tile per lane group
+  __shared__ float4 s_tile[KLT_GPB][KLT_TW * KLT_TP];  // one tile per lane group
   const int gl = threadIdx.x & (KLT_G - 1), grpBase = threadIdx.x & (32 - KLT_G);
   const int grpInBlock = threadIdx.x / KLT_G;
   const int q = blockIdx.x * KLT_GPB + grpInBlock;
@@ -255,7 +292,7 @@ klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
   const int F = Plax.F;
   const int T = C * F;
   const int hw = Plax.halfWidth, fwid = 2 * hw + 1, npx = fwid * fwid;
-  const bool fast = (npx <= KLT_G * KLT_ROUNDS) && (2 * hw + 2 + 2 <= KLT_TW);
+  const bool fast = (npx <= KLT_G * KLT_ROUNDS) && (2 * hw + 2 + 2 <= KLT_TW) && (2 * hw + 2 <= 8);
   const float halfW = 0.5f * (float)Plax.W, halfH = 0.5f * (float)Plax.H;
   float4* tile = s_tile[grpInBlock];
   // all groups of a warp must execute the same number of outer iterations (full-mask shuffles)
@@ -273,13 +310,19 @@ klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
   for (int r = 0; r < KLT_ROUNDS; ++r) {
     const int p = min(gl + KLT_G * r, npx - 1);
     const int py = p / fwid, px = p - py * fwid;
-    toff[r] = (py - hw) * KLT_TW + (px - hw);
+    toff[r] = (py - hw) * KLT_TP + (px - hw);
   }
   float3 I0r[KLT_ROUNDS];
   float f0 = 0.f;  // group sum of klt_d2_term of the resident item at the current level
   float4 cur0 = make_float4(-1.f, -1.f, -1.f, 0.f);
   int tx0 = 0, ty0 = 0;
 
+#if KLT_EXP_CLOCK
+  long long ck[6] = {0, 0, 0, 0, 0, 0};
+  const long long ckStart = clock64();
+  unsigned long long gt0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt0));
+#endif
   int pass = 0;
   for (int li = 0; li < LV.n; ++li) {
     const int w = LV.w[li], h = LV.h[li];
@@ -289,6 +332,7 @@ klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
       const bool strict = (it == nIter) && (it != 1);
       const int rd = (pass - 1) & 1, wr = pass & 1;
       for (int own = 0; own < nOwn; ++own) {
+        KLT_CLK(c0);
         const bool staged = fast && (own == 0);
         int item = item0, cam = cam0, wsA = wsA0, wsB = wsB0;
         bool active = active0;
@@ -303,91 +347,116 @@ klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
           wsA = waitset[slot * 16 + gl];
           wsB = waitset[slot * 16 + 8 + gl];
         }
+        // own state; the neighbours' gains are needed only after the pixel loop (klt_gain_finish)
         float4 cur;
-        float bn;
-        if (pass == 1) {
+        if (pass == 1)
           cur = make_float4(x0.x, x0.y, 1.0f, 0.f);  // X1 <- X0, gain cleared to 1 (:223-227)
-          bn = 1.0f;
-        } else {
-          // wait for the pass-(p-1) records of everything this slot reads or is read by; the
-          // first 8 entries also deliver the neighbour gains
-          bn = -1.0f;
-          if (active) {
-            const unsigned long long* rb = rec + (size_t)rd * T + (size_t)cam * F;
-            const int need = verBase + pass - 1;
-            // wsA is always a valid slot (neighbour lists are clamped), wsB may be -1
-            const unsigned long long* ra = rb + wsA;
-            const unsigned long long* rbp = rb + (wsB >= 0 ? wsB : wsA);
-            unsigned long long va = ld_relaxed_u64(ra), vb = ld_relaxed_u64(rbp);
-            while ((int)(va >> 32) < need) {
-              __nanosleep(20);
-              va = ld_relaxed_u64(ra);
-            }
-            while ((int)(vb >> 32) < need) {
-              __nanosleep(20);
-              vb = ld_relaxed_u64(rbp);
-            }
-            bn = __uint_as_float((unsigned)va);
-          }
-          __syncwarp();
+        else
           cur = (staged) ? cur0 : __ldcg(&state[item]);
-        }
+        // records of pass p-1 of everything this slot reads (first 8 entries: they also deliver
+        // the neighbour gains) or is read by (last 8, may be -1); wsA is always a valid slot
+        const unsigned long long* ra = rec + (size_t)rd * T + (size_t)cam * F + wsA;
+        const unsigned long long* rb = rec + (size_t)rd * T + (size_t)cam * F + (wsB >= 0 ? wsB : wsA);
+        const int need = verBase + pass - 1;
+        unsigned long long va = 0, vb = 0;  // version 0 < need for every pass >= 2
+        KLT_CLK(c1k);
         const float beta = cur.z;
-        const float nbterm = klt_nbterm(bn, beta, gl, grpBase);
         const bool pre_invalid = (cur.x < 0.f) || (x0.x < 0.f);
         const KltCentre c1 = klt_centre(w, h, cur.x, cur.y);
-        // ---- per-level staging (first iteration of a level): I0 samples + I1 tile
+        // ---- per-level staging (first iteration of a level): I0 samples + I1 tile.
+        // Three memory round trips with all loads of a trip in flight together: (A) the 8x8 texels
+        // under the I0 window and the upper half of the I1 tile, (B) the I0 samples interpolated
+        // from shared memory (the I0 texels borrow the lower tile rows), (C) the lower tile half.
         if (staged && it == 1) {
           const float4* L0 = pyr0 + (size_t)cam * pyrStride + LV.off[li];
           const float4* L1 = pyr1 + (size_t)cam * pyrStride + LV.off[li];
           const KltCentre c0 = klt_centre(w, h, x0.x, x0.y);
-          float d2 = 0.f;
-#pragma unroll
-          for (int r = 0; r < KLT_ROUNDS; ++r) {
-            const int p = gl + KLT_G * r;
-            const int py = p / fwid, px = p - py * fwid;
-            I0r[r] = (p < npx && !pre_invalid)
-                         ? klt_fetch_global(L0, w, h, c0.xi + px - hw, c0.yi + py - hw, c0.ax, c0.ay)
-                         : make_float3(0.f, 0.f, 0.f);
-            if (p < npx) d2 = __fadd_rn(d2, klt_d2_term(I0r[r], Plax.lambda, Plax.delta));
-          }
-          f0 = grp_sum(d2);
+          constexpr int NLD = KLT_TW * KLT_TW / KLT_G / 2;  // 9 tile texels per lane and half
+          constexpr int I0B = (KLT_TW / 2) * KLT_TP;        // I0 texels: tile rows 6.., pitch 8
+          static_assert(I0B + 64 <= KLT_TW * KLT_TP, "I0 staging area must fit the lower tile half");
           tx0 = c1.xi - hw - 2;
           ty0 = c1.yi - hw - 2;
+          // every __syncwarp below is executed by the whole warp: only the memory operations are
+          // predicated on the slot being alive (the four slots of a warp differ in that)
+          float d2 = 0.f;
           if (!pre_invalid) {
-            constexpr int NLD = KLT_TW * KLT_TW / KLT_G;  // 18 texels per lane, two batches of 9
+            float4 t0[8], tv[NLD];
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              float4 tv[NLD / 2];
+            for (int u = 0; u < 8; ++u)  // lane gl loads column gl of the 8x8 block
+              t0[u] = __ldg(&L0[(size_t)clampi(c0.yi - hw + u, 0, h - 1) * w + clampi(c0.xi - hw + gl, 0, w - 1)]);
 #pragma unroll
-              for (int u = 0; u < NLD / 2; ++u) {  // all loads of a batch in flight first
-                const int i = gl + KLT_G * (u + half * (NLD / 2));
-                const int b = i / KLT_TW, a = i - b * KLT_TW;
-                tv[u] = __ldg(&L1[(size_t)clampi(ty0 + b, 0, h - 1) * w + clampi(tx0 + a, 0, w - 1)]);
-              }
+            for (int u = 0; u < NLD; ++u) {
+              const int i = gl + KLT_G * u;
+              const int b = i / KLT_TW, a = i - b * KLT_TW;
+              tv[u] = __ldg(&L1[(size_t)clampi(ty0 + b, 0, h - 1) * w + clampi(tx0 + a, 0, w - 1)]);
+            }
 #pragma unroll
-              for (int u = 0; u < NLD / 2; ++u) tile[gl + KLT_G * (u + half * (NLD / 2))] = tv[u];
+            for (int u = 0; u < 8; ++u) tile[I0B + u * 8 + gl] = t0[u];
+#pragma unroll
+            for (int u = 0; u < NLD; ++u) {
+              const int i = gl + KLT_G * u;
+              const int b = i / KLT_TW, a = i - b * KLT_TW;
+              tile[b * KLT_TP + a] = tv[u];
             }
           }
           __syncwarp();
+          if (!pre_invalid) {
+#pragma unroll
+            for (int r = 0; r < KLT_ROUNDS; ++r) {
+              const int p = gl + KLT_G * r;
+              if (p < npx) {
+                const int py = p / fwid, px = p - py * fwid;
+                const float4* t4 = tile + I0B + py * 8 + px;
+                I0r[r] = klt_lerp4(t4[0], t4[1], t4[8], t4[9], c0.ax, c0.ay);
+                d2 = __fadd_rn(d2, klt_d2_term(I0r[r], Plax.lambda, Plax.delta));
+              } else {
+                I0r[r] = make_float3(0.f, 0.f, 0.f);
+              }
+            }
+          }
+          __syncwarp();
+          if (!pre_invalid) {
+            float4 tw[NLD];
+#pragma unroll
+            for (int u = 0; u < NLD; ++u) {
+              const int i = gl + KLT_G * (u + NLD);
+              const int b = i / KLT_TW, a = i - b * KLT_TW;
+              tw[u] = __ldg(&L1[(size_t)clampi(ty0 + b, 0, h - 1) * w + clampi(tx0 + a, 0, w - 1)]);
+            }
+#pragma unroll
+            for (int u = 0; u < NLD; ++u) {
+              const int i = gl + KLT_G * (u + NLD);
+              const int b = i / KLT_TW, a = i - b * KLT_TW;
+              tile[b * KLT_TP + a] = tw[u];
+            }
+          }
+          f0 = grp_sum(d2);
+          __syncwarp();
         }
         // ---- the iteration
+        KLT_CLK(c2k);
         KltAcc A = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         float f = f0;
         if (!pre_invalid) {
-          // tile[b * KLT_TW + a] == level[clamp(ty0 + b)][clamp(tx0 + a)]: indexing with the
+          // tile[b * KLT_TP + a] == level[clamp(ty0 + b)][clamp(tx0 + a)]: indexing with the
           // unclamped tap coordinates reproduces the clamped fetches exactly
           const int a0 = c1.xi - tx0, b0 = c1.yi - ty0;
           const bool inTile = staged && (a0 - hw >= 0) && (a0 + hw + 1 < KLT_TW) && (b0 - hw >= 0) &&
                               (b0 + hw + 1 < KLT_TW);
           if (inTile) {
-            const float4* tc = tile + b0 * KLT_TW + a0;
+            const float4* tc = tile + b0 * KLT_TP + a0;
 #pragma unroll
             for (int r = 0; r < KLT_ROUNDS; ++r) {
+              if (r == KLT_ROUNDS / 2 && pass > 1 && active) {
+                // early, non-binding look at the records: usually published by now, and the L2
+                // round trip overlaps the remaining rounds
+                va = ld_hint_u64(ra);
+                vb = ld_hint_u64(rb);
+              }
               if (gl + KLT_G * r < npx) {
                 const float4* t4 = tc + toff[r];
-                const float3 I1 = klt_lerp4(t4[0], t4[1], t4[KLT_TW], t4[KLT_TW + 1], c1.ax, c1.ay);
-                klt_acc_pixel(A, I0r[r], I1, beta, nbterm, halfW, halfH, Plax.lambda, Plax.delta);
+                const float3 I1 = klt_lerp4(t4[0], t4[1], t4[KLT_TP], t4[KLT_TP + 1], c1.ax, c1.ay);
+                klt_acc_pixel(A, I0r[r], I1, beta, halfW, halfH, Plax.lambda);
               }
             }
           } else if (staged) {
@@ -403,7 +472,7 @@ klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
 #pragma unroll
                 for (int k = 1; k < KLT_ROUNDS; ++k)
                   if (r == k) I0 = I0r[k];
-                klt_acc_pixel(A, I0, I1, beta, nbterm, halfW, halfH, Plax.lambda, Plax.delta);
+                klt_acc_pixel(A, I0, I1, beta, halfW, halfH, Plax.lambda);
               }
             }
           } else {
@@ -417,13 +486,36 @@ klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
               const float3 I0 = klt_fetch_global(L0, w, h, c0.xi + dx, c0.yi + dy, c0.ax, c0.ay);
               const float3 I1 = klt_fetch_global(L1, w, h, c1.xi + dx, c1.yi + dy, c1.ax, c1.ay);
               d2 = __fadd_rn(d2, klt_d2_term(I0, Plax.lambda, Plax.delta));
-              klt_acc_pixel(A, I0, I1, beta, nbterm, halfW, halfH, Plax.lambda, Plax.delta);
+              klt_acc_pixel(A, I0, I1, beta, halfW, halfH, Plax.lambda);
             }
             f = d2;
           }
         }
+        KLT_CLK(c3k);
         if (!staged) f = grp_sum(f);  // warp-uniform branch: staged depends on own only
-        float4 res = klt_gain_finish(A, f, cur.x, cur.y, beta, strict ? Pstrict : Plax);
+        // ---- wait for the pass-(p-1) records, get the neighbour gains with the poll itself
+        float bn = 1.0f;
+        if (pass > 1) {
+          bn = -1.0f;
+          if (active) {
+            while ((int)(va >> 32) < need) {
+              va = ld_relaxed_u64(ra);
+              if ((int)(va >> 32) >= need) break;
+              __nanosleep(20);
+            }
+            while ((int)(vb >> 32) < need) {
+              vb = ld_relaxed_u64(rb);
+              if ((int)(vb >> 32) >= need) break;
+              __nanosleep(20);
+            }
+            bn = __uint_as_float((unsigned)va);
+          }
+          __syncwarp();
+        }
+        KLT_CLK(c3p);
+        const float nbterm = klt_nbterm(bn, beta, gl, grpBase);
+        float4 res = klt_gain_finish(A, f, nbterm, (float)npx, cur.x, cur.y, beta,
+                                     strict ? Pstrict : Plax);
         if (pre_invalid) res = make_float4(-1.f, -1.f, -1.f, 0.f);
         if (staged) cur0 = res;
         if (gl == 0 && active) {
@@ -434,9 +526,26 @@ klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
                              (unsigned long long)__float_as_uint(res.z));
         }
         __syncwarp();
+#if KLT_EXP_CLOCK
+        const long long c4k = clock64();
+        ck[0] += c3p - c3k;
+        ck[1] += c2k - c0;
+        ck[2] += c3k - c2k;
+        ck[3] += c4k - c3p;
+        if (it == 1) ck[4] += c2k - c1k;
+#endif
       }
     }
   }
+#if KLT_EXP_CLOCK
+  if ((threadIdx.x & 31) == 0) {
+    const int wg = (blockIdx.x * KLT_FUSED_THREADS + threadIdx.x) >> 5;
+    state[2 * wg] = make_float4((float)ck[0], (float)ck[1], (float)ck[2], (float)ck[3]);
+    unsigned long long gt1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
+    state[2 * wg + 1] = make_float4((float)ck[4], (float)(clock64() - ckStart), __uint_as_float((unsigned)(gt0 & 0xffffffffu)), __uint_as_float((unsigned)(gt1 & 0xffffffffu)));
+  }
+#endif
 }
 
 }  // namespace coslam
