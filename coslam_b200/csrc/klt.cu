@@ -37,6 +37,8 @@ struct cosl_klt {
   float4* d_present = nullptr;
   int* d_nbr = nullptr;
   unsigned long long* d_cand = nullptr;
+  unsigned* d_prelim = nullptr;  // [C][prelimCap] packed (y << 16 | x) of 3x3 local maxima
+  int prelimCap = 0;
   int* d_counters = nullptr;
   cosl_klt_feature* d_feat = nullptr;
   float* d_feedpts = nullptr;
@@ -54,6 +56,7 @@ struct cosl_klt {
   int* d_waitset = nullptr;   // [F][16]
   bool fusedOK = false;
   int fusedBlocks = 0;
+  int numSM = 148;
   int verBase = 0;
   SectionTimer timer;
   int secPyr = 0, secTrack = 0, secDetect = 0, secSelect = 0;
@@ -94,6 +97,9 @@ int alloc_group(cosl_klt* g) {
     COSL_CUDA(cudaMemcpy(*pb, init.data(), fbytes, cudaMemcpyHostToDevice));
   }
   COSL_CUDA(cudaMalloc(&g->d_cand, sizeof(unsigned long long) * (size_t)cap * C));
+  // strict 3x3 maxima cannot be 8-adjacent: at most one per 2x2 block
+  g->prelimCap = ((W + 1) / 2) * ((H + 1) / 2);
+  COSL_CUDA(cudaMalloc(&g->d_prelim, sizeof(unsigned) * (size_t)g->prelimCap * C));
   COSL_CUDA(cudaMalloc(&g->d_counters, sizeof(int) * 8 * C));
   COSL_CUDA(cudaMemset(g->d_counters, 0, sizeof(int) * 8 * C));
   COSL_CUDA(cudaMalloc(&g->d_feat, sizeof(cosl_klt_feature) * (size_t)F * C));
@@ -144,6 +150,7 @@ int alloc_group(cosl_klt* g) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    g->numSM = std::max(1, nsm);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, klt_gain_fused, KLT_FUSED_THREADS, 0);
     g->fusedOK = ok && coop && perSM > 0 && !(g->cfg.compat & COSL_KLT_PASS_KERNELS);
     const int T = F * C;
@@ -160,11 +167,6 @@ int alloc_group(cosl_klt* g) {
                                  (int)sizeof(FrontSmem)));
   COSL_CUDA(cudaFuncSetAttribute(klt_select_refill, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  g->smemKeys * (int)sizeof(unsigned long long)));
-  const int TS = NM_T + 2 * r;
-  const int nmBytes = (3 * TS * TS + TS * NM_T) * (int)sizeof(float);
-  if (nmBytes > 48 * 1024)
-    COSL_CUDA(cudaFuncSetAttribute(klt_nonmax_compact, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   nmBytes));
   g->secPyr = g->timer.section("klt_pyramid");
   g->secTrack = g->timer.section("klt_track");
   g->secDetect = g->timer.section("klt_detect");
@@ -190,6 +192,7 @@ void free_group(cosl_klt* g) {
   cudaFree(g->d_present);
   cudaFree(g->d_nbr);
   cudaFree(g->d_cand);
+  cudaFree(g->d_prelim);
   cudaFree(g->d_counters);
   cudaFree(g->d_feat);
   cudaFree(g->d_feedpts);
@@ -401,11 +404,12 @@ int run_detector(cosl_klt* g, int mode, int nPresentExt) {
                 g->W, g->H);
   }
   const int r = std::max(1, g->cfg.minDistance);
-  const int TS = NM_T + 2 * r;
-  const int nmBytes = (3 * TS * TS + TS * NM_T) * (int)sizeof(float);
-  dim3 gn(div_up(g->W, NM_T), div_up(g->H, NM_T), g->C);
-  COSL_LAUNCH(klt_nonmax_compact, gn, 256, nmBytes, g->stream, g->d_corn, g->W, g->H, r, g->d_cand,
-              g->candCap, g->d_counters);
+  dim3 gp(div_up(g->W, 32), div_up(g->H, 8), g->C);
+  COSL_LAUNCH(klt_nm_prefilter, gp, 256, 0, g->stream, g->d_corn, g->W, g->H, g->d_prelim,
+              g->prelimCap, g->d_counters);
+  dim3 gv(2 * g->numSM, g->C);
+  COSL_LAUNCH(klt_nm_verify, gv, 256, 0, g->stream, g->d_corn, g->W, g->H, r, g->d_prelim,
+              g->prelimCap, g->d_cand, g->candCap, g->d_counters);
   g->timer.end(g->stream);
   g->timer.begin(g->secSelect, g->stream);
   COSL_LAUNCH(klt_select_refill, g->C, 1024, g->smemKeys * sizeof(unsigned long long), g->stream,

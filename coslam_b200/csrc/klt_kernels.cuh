@@ -365,135 +365,86 @@ __global__ void klt_suppress(const float4* __restrict__ pts, int n, int ptsStrid
 }
 
 // ------------------------------------------------------------------------------------------
-// Separable non-max suppression (klt_detector_nonmax.cg:12-26, horizontal then vertical) fused
-// with stream compaction (replaces discriminator + HistoPyramid build/traverse,
-// klt_detector_discriminator.cg / build_histpyr.cg / traverse_histpyr.cg): survivors are appended
-// to the per-camera candidate list as sortable 64-bit keys with a warp-aggregated atomic.
-// Tile 32 x 32 outputs, halo r = minDistance in dynamic shared memory.
-// counters[cam*8 + 1] = number of candidates.
+// Non-max suppression + compaction (klt_detector_nonmax.cg:12-26, run by the reference as a
+// horizontal then a vertical pass with the sign trick "m = c if |c| > max|n| else -max|n|").
+// The two passes leave a positive value exactly at pixels with c > 0 whose value is STRICTLY
+// larger than |v| of every other texel v of their (2r+1)^2 window (klt_suppress marks live points
+// with -1e30, which therefore clears their whole neighbourhood), the window being read with
+// CLAMP_TO_EDGE (so a pixel on the image border, whose window contains a clamped copy of itself,
+// never survives).  That predicate is evaluated directly, candidate driven:
+//   klt_nm_prefilter  one streaming pass: pixels with c > 0 that beat |.| of their 8 neighbours
+//                     (necessary condition; at most one per 2x2 block) -> prelim list
+//   klt_nm_verify     one warp per prelim pixel checks the remaining window texels (L2 resident)
+//                     and appends the survivors' sort keys
+// The cornerness map is mostly zero after thresholding, so the second kernel touches a few
+// percent of the pixels; the map is read from HBM once (4 B/px).
+// counters[cam*8+4] = prelim count, counters[cam*8+1] = candidate count.
 // ------------------------------------------------------------------------------------------
-constexpr int NM_T = 32;
-
-// exclusive window maximum over [x-r, x-1] U [x+1, x+r] from block prefix / suffix maxima
-// (van Herk / Gil-Werman with block size r): a window of length r spans at most two r-blocks.
-__device__ __forceinline__ float nm_excl_max(const float* __restrict__ P, const float* __restrict__ S,
-                                            int x, int r, int stride) {
-  const float left = fmaxf(S[(x - r) * stride], P[(x - 1) * stride]);
-  const float right = fmaxf(S[(x + 1) * stride], P[(x + r) * stride]);
-  return fmaxf(left, right);
+__global__ void __launch_bounds__(256)
+klt_nm_prefilter(const float* __restrict__ corn, int W, int H, unsigned* __restrict__ prelim,
+                 int prelimCap, int* __restrict__ counters) {
+  const int cam = blockIdx.z;
+  const float* cm = corn + (size_t)cam * W * H;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const bool in = (x < W) && (y < H);
+  const float c = in ? __ldg(&cm[(size_t)y * W + x]) : 0.f;
+  bool cand = c > 0.f;
+  if (!__any_sync(0xffffffffu, cand)) return;
+  if (cand) {
+    const int xm = max(x - 1, 0), xp = min(x + 1, W - 1);
+    const float* r0 = cm + (size_t)max(y - 1, 0) * W;
+    const float* r1 = cm + (size_t)y * W;
+    const float* r2 = cm + (size_t)min(y + 1, H - 1) * W;
+    const float m0 = fmaxf(fmaxf(fabsf(__ldg(&r0[xm])), fabsf(__ldg(&r0[x]))), fabsf(__ldg(&r0[xp])));
+    const float m1 = fmaxf(fabsf(__ldg(&r1[xm])), fabsf(__ldg(&r1[xp])));
+    const float m2 = fmaxf(fmaxf(fabsf(__ldg(&r2[xm])), fabsf(__ldg(&r2[x]))), fabsf(__ldg(&r2[xp])));
+    cand = c > fmaxf(fmaxf(m0, m1), m2);
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, cand);
+  if (m) {
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&counters[cam * 8 + 4], __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (cand) {
+      const int idx = base + __popc(m & ((1u << lane) - 1));
+      if (idx < prelimCap) prelim[(size_t)cam * prelimCap + idx] = ((unsigned)y << 16) | (unsigned)x;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256)
-klt_nonmax_compact(const float* __restrict__ corn, int W, int H, int r,
-                   unsigned long long* __restrict__ cand, int candCap,
-                   int* __restrict__ counters) {
-  extern __shared__ float s_nm[];
-  const int TS = NM_T + 2 * r;            // tile side incl. halo
-  float* s_c = s_nm;                      // [TS][TS] signed cornerness
-  float* s_p = s_c + TS * TS;             // [TS][TS] prefix maxima of |.| inside r-blocks
-  float* s_s = s_p + TS * TS;             // [TS][TS] suffix maxima
-  float* s_h = s_s + TS * TS;             // [TS][NM_T] horizontal pass result (signed)
-  const int cam = blockIdx.z;
+klt_nm_verify(const float* __restrict__ corn, int W, int H, int r,
+              const unsigned* __restrict__ prelim, int prelimCap,
+              unsigned long long* __restrict__ cand, int candCap, int* __restrict__ counters) {
+  const int cam = blockIdx.y;
   const float* cm = corn + (size_t)cam * W * H;
-  const int x0 = blockIdx.x * NM_T, y0 = blockIdx.y * NM_T;
-  const int tid = threadIdx.x;
-  int anyPos = 0;
-  // stage the tile with up to 12 independent loads in flight per thread (one memory round trip)
-  for (int base = 0; base < TS * TS; base += 256 * 12) {
-    float v[12];
-#pragma unroll
-    for (int u = 0; u < 12; ++u) {
-      const int i = base + tid + 256 * u;
-      if (i < TS * TS) {
-        const int ty = i / TS, tx = i - ty * TS;
-        const int gy = clampi(y0 + ty - r, 0, H - 1), gx = clampi(x0 + tx - r, 0, W - 1);
-        v[u] = __ldg(&cm[(size_t)gy * W + gx]);
-      }
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int nwarps = gridDim.x * (blockDim.x >> 5);
+  const int n = min(counters[cam * 8 + 4], prelimCap);
+  const int side = 2 * r + 1, nwin = side * side, centre = r * side + r;
+  for (int i = warp; i < n; i += nwarps) {
+    const unsigned p = prelim[(size_t)cam * prelimCap + i];
+    const int x = (int)(p & 0xffffu), y = (int)(p >> 16);
+    const float c = __ldg(&cm[(size_t)y * W + x]);
+    bool beaten = false;
+    for (int k = lane; k < nwin; k += 32) {
+      const int dy = k / side, dx = k - dy * side;
+      const float v = __ldg(&cm[(size_t)clampi(y + dy - r, 0, H - 1) * W + clampi(x + dx - r, 0, W - 1)]);
+      beaten |= (k != centre) && !(c > fabsf(v));
     }
-#pragma unroll
-    for (int u = 0; u < 12; ++u) {
-      const int i = base + tid + 256 * u;
-      if (i < TS * TS) {
-        const int ty = i / TS, tx = i - ty * TS;
-        s_c[i] = v[u];
-        // only the inner tile can produce candidates
-        if (v[u] > 0.f && ty >= r && ty < r + NM_T && tx >= r && tx < r + NM_T) anyPos = 1;
-      }
-    }
-  }
-  if (!__syncthreads_or(anyPos)) return;  // nothing positive in the inner tile: no survivor
-  // ---- horizontal pass (klt_detector_nonmax.cg:12-26 with ds = (1/W, 0)): the sequential
-  // "if |n| >= |m| then m = -|n|" scan equals: m = c if |c| > max|n| else -max|n|
-  const int nbk = (TS + r - 1) / r;
-  for (int i = tid; i < TS * nbk; i += 256) {
-    const int row = i / nbk, b = i - row * nbk;
-    const int xs = b * r, xe = min(TS, xs + r);
-    float m = 0.f;
-    for (int x = xs; x < xe; ++x) {
-      m = fmaxf(m, fabsf(s_c[row * TS + x]));
-      s_p[row * TS + x] = m;
-    }
-    m = 0.f;
-    for (int x = xe - 1; x >= xs; --x) {
-      m = fmaxf(m, fabsf(s_c[row * TS + x]));
-      s_s[row * TS + x] = m;
-    }
-  }
-  __syncthreads();
-  for (int i = tid; i < TS * NM_T; i += 256) {
-    const int ty = i / NM_T, tx = i - ty * NM_T;
-    const int x = tx + r;
-    const float c = s_c[ty * TS + x];
-    const float ex = nm_excl_max(s_p + ty * TS, s_s + ty * TS, x, r, 1);
-    s_h[i] = (fabsf(c) > ex) ? c : -ex;
-  }
-  __syncthreads();
-  // ---- vertical pass on the horizontal result
-  float* v_p = s_p;  // reuse: [TS][NM_T]
-  float* v_s = s_s;
-  for (int i = tid; i < NM_T * nbk; i += 256) {
-    const int col = i % NM_T, b = i / NM_T;
-    const int ys = b * r, ye = min(TS, ys + r);
-    float m = 0.f;
-    for (int y = ys; y < ye; ++y) {
-      m = fmaxf(m, fabsf(s_h[y * NM_T + col]));
-      v_p[y * NM_T + col] = m;
-    }
-    m = 0.f;
-    for (int y = ye - 1; y >= ys; --y) {
-      m = fmaxf(m, fabsf(s_h[y * NM_T + col]));
-      v_s[y * NM_T + col] = m;
-    }
-  }
-  __syncthreads();
-  for (int i = tid; i < NM_T * NM_T; i += 256) {
-    const int ty = i / NM_T, tx = i - ty * NM_T;
-    const int gx = x0 + tx, gy = y0 + ty;
-    const int y = ty + r;
-    const float c = s_h[y * NM_T + tx];
-    const float ex = nm_excl_max(v_p + tx, v_s + tx, y, r, NM_T);
-    const float mx = (fabsf(c) > ex) ? c : -ex;
-    const bool surv = (gx < W && gy < H && mx > 0.f);
-    const unsigned m = __ballot_sync(0xffffffffu, surv);
-    if (m) {
-      const int lane = tid & 31;
-      int base = 0;
-      if (lane == 0) base = atomicAdd(&counters[cam * 8 + 1], __popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (surv) {
-        const int idx = base + __popc(m & ((1u << lane) - 1));
-        if (idx < candCap) {
-          const unsigned cb = ~__float_as_uint(mx);
-          cand[(size_t)cam * candCap + idx] =
-              ((unsigned long long)cb << 32) | ((unsigned long long)gy << 16) | (unsigned long long)gx;
-        }
+    if (!__any_sync(0xffffffffu, beaten) && lane == 0) {
+      const int idx = atomicAdd(&counters[cam * 8 + 1], 1);
+      if (idx < candCap) {
+        const unsigned cb = ~__float_as_uint(c);
+        cand[(size_t)cam * candCap + idx] =
+            ((unsigned long long)cb << 32) | ((unsigned long long)y << 16) | (unsigned long long)x;
       }
     }
   }
 }
-
-// Note on the clamped halo at image borders: the reference's texture fetches clamp to the edge
-// texel, so a border pixel compares against (copies of) edge pixels exactly as s_c holds them.
 
 // ------------------------------------------------------------------------------------------
 // Single-CTA per camera: sort the candidate keys (bitonic, shared memory when they fit), then do
