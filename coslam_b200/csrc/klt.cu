@@ -57,12 +57,35 @@ struct cosl_klt {
   bool fusedOK = false;
   int fusedBlocks = 0;
   int numSM = 148;
+  int detXlo = 0, detXhi = -1, detYlo = 0, detYhi = -1;  // detector window in pixels
   int verBase = 0;
   SectionTimer timer;
   int secPyr = 0, secTrack = 0, secDetect = 0, secSelect = 0;
 };
 
 namespace {
+
+// Detector window (klt_detector_pass2.cg: the pixel centre (i + 0.5) / n must lie inside
+// [margin / n, 1 - margin / n]); evaluated with the same fp32 expressions the stand-alone
+// cornerness kernel evaluates per pixel, so the integer bounds select exactly the same pixels.
+static void update_detect_window(cosl_klt* g) {
+  const float mg = g->detectMargin;
+  auto bounds = [](int n, float lo, float hi, int& i0, int& i1) {
+    const float nf = (float)n;
+    i0 = n;
+    i1 = -1;
+    for (int i = 0; i < n; ++i) {
+      const float sc = ((float)i + 0.5f) / nf;
+      if (sc >= lo && sc <= hi) {
+        i0 = std::min(i0, i);
+        i1 = std::max(i1, i);
+      }
+    }
+  };
+  const float Wf = (float)g->W, Hf = (float)g->H;
+  bounds(g->W, mg / Wf, 1.0f - mg / Wf, g->detXlo, g->detXhi);
+  bounds(g->H, mg / Hf, 1.0f - mg / Hf, g->detYlo, g->detYhi);
+}
 
 int alloc_group(cosl_klt* g) {
   const int C = g->C, W = g->W, H = g->H, F = g->F;
@@ -163,10 +186,9 @@ int alloc_group(cosl_klt* g) {
     g->verBase = 0;
   }
   // dynamic shared memory opt-ins
-  COSL_CUDA(cudaFuncSetAttribute(klt_front, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)sizeof(FrontSmem)));
   COSL_CUDA(cudaFuncSetAttribute(klt_select_refill, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  g->smemKeys * (int)sizeof(unsigned long long)));
+  update_detect_window(g);
   g->secPyr = g->timer.section("klt_pyramid");
   g->secTrack = g->timer.section("klt_track");
   g->secDetect = g->timer.section("klt_detect");
@@ -221,12 +243,27 @@ int build_pyramid(cosl_klt* g, bool wantCorn) {
   float4* P = g->d_pyr[g->cur];
   g->timer.begin(g->secPyr, g->stream);
   // level 0 + level 1 + (optionally) the detector's cornerness map in one pass over the image
-  const float Wf = (float)g->W, Hf = (float)g->H, mg = g->detectMargin;
-  dim3 g0(div_up(g->W, FR_TW), div_up(g->H, FR_TH), g->C);
-  COSL_LAUNCH(klt_front, g0, 256, sizeof(FrontSmem), g->stream, g->d_img, g->imgPitch, g->imgStride,
-              P, g->pyrStride, g->L > 1 ? g->lvOff[1] : 0, g->d_corn, g->W, g->H, g->L > 1 ? 1 : 0,
-              wantCorn ? 1 : 0, g->cfg.minCornerness, mg / Wf, mg / Hf, 1.0f - mg / Wf,
-              1.0f - mg / Hf);
+  FrontParams fp;
+  fp.img = g->d_img;
+  fp.imgPitch = g->imgPitch;
+  fp.imgStride = g->imgStride;
+  fp.pyr = P;
+  fp.pyrStride = g->pyrStride;
+  fp.lv1Off = g->L > 1 ? g->lvOff[1] : 0;
+  fp.corn = g->d_corn;
+  fp.W = g->W;
+  fp.H = g->H;
+  fp.nStrips = div_up(g->W, FS_SW);
+  fp.nChunks = div_up(g->H, FS_R);
+  fp.wantL1 = g->L > 1 ? 1 : 0;
+  fp.wantCorn = wantCorn ? 1 : 0;
+  fp.minC = g->cfg.minCornerness;
+  fp.ixlo = g->detXlo;
+  fp.ixhi = g->detXhi;
+  fp.iylo = g->detYlo;
+  fp.iyhi = g->detYhi;
+  dim3 g0(div_up(fp.nStrips * fp.nChunks, FS_WARPS), g->C);
+  COSL_LAUNCH(klt_front, g0, 32 * FS_WARPS, 0, g->stream, fp);
   g->cornValid = wantCorn;
   for (int l = 2; l < g->L; ++l) {
     dim3 gl(div_up(g->lvW[l], PD_TW), div_up(g->lvH[l], PD_TH), g->C);
@@ -404,8 +441,8 @@ int run_detector(cosl_klt* g, int mode, int nPresentExt) {
                 g->W, g->H);
   }
   const int r = std::max(1, g->cfg.minDistance);
-  dim3 gp(div_up(g->W, 32), div_up(g->H, 8), g->C);
-  COSL_LAUNCH(klt_nm_prefilter, gp, 256, 0, g->stream, g->d_corn, g->W, g->H, g->d_prelim,
+  dim3 gp(div_up(g->W, NP_COLS), div_up(g->H, 8 * NP_ROWS), g->C);
+  COSL_LAUNCH(klt_nm_prefilter, gp, 256, 0, g->stream, g->d_corn, g->W, g->H, r, g->d_prelim,
               g->prelimCap, g->d_counters);
   dim3 gv(2 * g->numSM, g->C);
   COSL_LAUNCH(klt_nm_verify, gv, 256, 0, g->stream, g->d_corn, g->W, g->H, r, g->d_prelim,
@@ -649,6 +686,7 @@ int cosl_klt_set_margin(cosl_klt* h, float m) {  // tracker AND detector (v3d_gp
   KLT_ENTER(h)
   h->trackMargin = m;
   h->detectMargin = m;
+  update_detect_window(h);
   return COSL_OK;
 }
 int cosl_klt_set_conv(cosl_klt* h, float t) {

@@ -372,47 +372,91 @@ __global__ void klt_suppress(const float4* __restrict__ pts, int n, int ptsStrid
 // with -1e30, which therefore clears their whole neighbourhood), the window being read with
 // CLAMP_TO_EDGE (so a pixel on the image border, whose window contains a clamped copy of itself,
 // never survives).  That predicate is evaluated directly, candidate driven:
-//   klt_nm_prefilter  one streaming pass: pixels with c > 0 that beat |.| of their 8 neighbours
-//                     (necessary condition; at most one per 2x2 block) -> prelim list
+//   klt_nm_prefilter  one streaming pass: pixels with c > 0 that beat |.| of their 5x5 (3x3 when
+//                     r == 1) neighbourhood -- a necessary condition, at most one pixel per 2x2
+//                     block passes -> prelim list
 //   klt_nm_verify     one warp per prelim pixel checks the remaining window texels (L2 resident)
 //                     and appends the survivors' sort keys
 // The cornerness map is mostly zero after thresholding, so the second kernel touches a few
 // percent of the pixels; the map is read from HBM once (4 B/px).
 // counters[cam*8+4] = prelim count, counters[cam*8+1] = candidate count.
 // ------------------------------------------------------------------------------------------
+constexpr int NP_ROWS = 16;  // rows per warp in klt_nm_prefilter
+constexpr int NP_COLS = 28;  // output columns per warp (lanes 2..29; two halo lanes either side)
+
 __global__ void __launch_bounds__(256)
-klt_nm_prefilter(const float* __restrict__ corn, int W, int H, unsigned* __restrict__ prelim,
+klt_nm_prefilter(const float* __restrict__ corn, int W, int H, int r, unsigned* __restrict__ prelim,
                  int prelimCap, int* __restrict__ counters) {
   const int cam = blockIdx.z;
   const float* cm = corn + (size_t)cam * W * H;
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
-  const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  const bool in = (x < W) && (y < H);
-  const float c = in ? __ldg(&cm[(size_t)y * W + x]) : 0.f;
-  bool cand = c > 0.f;
-  if (!__any_sync(0xffffffffu, cand)) return;
-  if (cand) {
-    const int xm = max(x - 1, 0), xp = min(x + 1, W - 1);
-    const float* r0 = cm + (size_t)max(y - 1, 0) * W;
-    const float* r1 = cm + (size_t)y * W;
-    const float* r2 = cm + (size_t)min(y + 1, H - 1) * W;
-    const float m0 = fmaxf(fmaxf(fabsf(__ldg(&r0[xm])), fabsf(__ldg(&r0[x]))), fabsf(__ldg(&r0[xp])));
-    const float m1 = fmaxf(fabsf(__ldg(&r1[xm])), fabsf(__ldg(&r1[xp])));
-    const float m2 = fmaxf(fmaxf(fabsf(__ldg(&r2[xm])), fabsf(__ldg(&r2[x]))), fabsf(__ldg(&r2[xp])));
-    cand = c > fmaxf(fmaxf(m0, m1), m2);
-  }
-  const unsigned m = __ballot_sync(0xffffffffu, cand);
-  if (m) {
-    const int lane = threadIdx.x & 31;
-    int base = 0;
-    if (lane == 0) base = atomicAdd(&counters[cam * 8 + 4], __popc(m));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (cand) {
-      const int idx = base + __popc(m & ((1u << lane) - 1));
-      if (idx < prelimCap) prelim[(size_t)cam * prelimCap + idx] = ((unsigned)y << 16) | (unsigned)x;
+  const int lane = threadIdx.x & 31;
+  const int x = blockIdx.x * NP_COLS - 2 + lane;                       // unclamped column
+  const int y0 = (blockIdx.y * 8 + (threadIdx.x >> 5)) * NP_ROWS;      // first output row
+  if (y0 >= H) return;
+  const int cx = clampi(x, 0, W - 1);
+  // all NP_ROWS + 4 rows of this column in flight at once
+  float v[NP_ROWS + 4];
+#pragma unroll
+  for (int k = 0; k < NP_ROWS + 4; ++k)
+    v[k] = fabsf(__ldg(&cm[(size_t)clampi(y0 - 2 + k, 0, H - 1) * W + cx]));
+  // The clamped loads make the 5x5 window of a pixel near the image border contain copies of the
+  // edge texels, which is exactly what the reference's CLAMP_TO_EDGE window contains there.
+  const bool colOK = (lane >= 2) && (lane < 2 + NP_COLS) && (x < W);
+  // horizontal maxima of |.| over columns x-2 .. x+2 (x-1 .. x+1 when r == 1): with the centre (incl)
+  // and without it (excl)
+  const bool two = r >= 2;
+  auto hmax = [&](float c, float& incl, float& excl) {
+    const float l1 = __shfl_up_sync(0xffffffffu, c, 1), r1 = __shfl_down_sync(0xffffffffu, c, 1);
+    float l2 = __shfl_up_sync(0xffffffffu, c, 2), r2 = __shfl_down_sync(0xffffffffu, c, 2);
+    if (!two) l2 = r2 = 0.f;  // |.| >= 0: neutral
+    excl = fmaxf(fmaxf(l1, l2), fmaxf(r1, r2));
+    incl = fmaxf(excl, c);
+  };
+  float hm[5], hx[5];  // rows y-2 .. y+2 of the row under test
+  hmax(v[0], hm[1], hx[1]);
+  hmax(v[1], hm[2], hx[2]);
+  hmax(v[2], hm[3], hx[3]);
+  hmax(v[3], hm[4], hx[4]);
+  unsigned mine = 0;  // bit k: this lane's pixel of row y0 + k is a preliminary candidate
+#pragma unroll
+  for (int k = 0; k < NP_ROWS; ++k) {
+    // rows y-2 .. y+2 are v[k] .. v[k+4]: slide, then add the new bottom row
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      hm[q] = hm[q + 1];
+      hx[q] = hx[q + 1];
     }
+    hmax(v[k + 4], hm[4], hx[4]);
+    const int y = y0 + k;
+    // |c| == c for a positive candidate; a suppressed centre (-1e30) has |c| = 1e30 and passes here,
+    // but klt_nm_verify re-reads the signed value and drops it
+    const float c = v[k + 2];
+    const float far = two ? fmaxf(hm[0], hm[4]) : 0.f;
+    const float others = fmaxf(fmaxf(fmaxf(hm[1], hm[3]), far), hx[2]);
+    if (colOK && (y < H) && (c > 0.f) && (c > others)) mine |= 1u << k;
+  }
+  // one atomic per warp: exclusive prefix of the per-lane counts, then every lane writes its own
+  if (!__any_sync(0xffffffffu, mine != 0)) return;
+  const int cnt = __popc(mine);
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  int base = 0;
+  if (lane == 31) base = atomicAdd(&counters[cam * 8 + 4], incl);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  int idx = base + incl - cnt;
+  while (mine) {
+    const int k = __ffs(mine) - 1;
+    mine &= mine - 1;
+    if (idx < prelimCap) prelim[(size_t)cam * prelimCap + idx] = ((unsigned)(y0 + k) << 16) | (unsigned)x;
+    ++idx;
   }
 }
+
+constexpr int NV_BATCH = 4;  // candidates a warp examines together (independent loads in flight)
 
 __global__ void __launch_bounds__(256)
 klt_nm_verify(const float* __restrict__ corn, int W, int H, int r,
@@ -424,23 +468,43 @@ klt_nm_verify(const float* __restrict__ corn, int W, int H, int r,
   const int warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * (blockDim.x >> 5);
   const int n = min(counters[cam * 8 + 4], prelimCap);
-  const int side = 2 * r + 1, nwin = side * side, centre = r * side + r;
-  for (int i = warp; i < n; i += nwarps) {
-    const unsigned p = prelim[(size_t)cam * prelimCap + i];
-    const int x = (int)(p & 0xffffu), y = (int)(p >> 16);
-    const float c = __ldg(&cm[(size_t)y * W + x]);
-    bool beaten = false;
-    for (int k = lane; k < nwin; k += 32) {
-      const int dy = k / side, dx = k - dy * side;
-      const float v = __ldg(&cm[(size_t)clampi(y + dy - r, 0, H - 1) * W + clampi(x + dx - r, 0, W - 1)]);
-      beaten |= (k != centre) && !(c > fabsf(v));
-    }
-    if (!__any_sync(0xffffffffu, beaten) && lane == 0) {
-      const int idx = atomicAdd(&counters[cam * 8 + 1], 1);
-      if (idx < candCap) {
-        const unsigned cb = ~__float_as_uint(c);
-        cand[(size_t)cam * candCap + idx] =
-            ((unsigned long long)cb << 32) | ((unsigned long long)y << 16) | (unsigned long long)x;
+  const int side = 2 * r + 1, nwin = side * side;
+  // window texel k (rows from the centre outwards: 0, -1, +1, -2, ...)
+  auto beaten_by = [&](int k, int x, int y, float c) -> bool {
+    if (k >= nwin) return false;
+    const int ri = k / side, dx = k - ri * side - r;
+    const int dy = (ri & 1) ? -((ri + 1) >> 1) : (ri >> 1);
+    const float v = __ldg(&cm[(size_t)clampi(y + dy, 0, H - 1) * W + clampi(x + dx, 0, W - 1)]);
+    return ((dx | dy) != 0) && !(c > fabsf(v));
+  };
+  for (int i0 = warp * NV_BATCH; i0 < n; i0 += nwarps * NV_BATCH) {
+    unsigned p[NV_BATCH];
+    float c[NV_BATCH];
+    bool b[NV_BATCH];
+#pragma unroll
+    for (int j = 0; j < NV_BATCH; ++j) p[j] = (i0 + j < n) ? prelim[(size_t)cam * prelimCap + i0 + j] : 0u;
+#pragma unroll
+    for (int j = 0; j < NV_BATCH; ++j)  // signed value: negative if suppressed meanwhile
+      c[j] = (i0 + j < n) ? __ldg(&cm[(size_t)(p[j] >> 16) * W + (p[j] & 0xffffu)]) : -1.0f;
+    // first 32 texels (the centre row and most of the one above) of every candidate of the batch in
+    // one memory round trip; the few candidates that are still unbeaten walk the rest of their
+    // window 32 texels at a time and leave at the first larger value (reading whole windows
+    // unconditionally was measured slower: the kernel is bound by L1 requests, not by latency)
+#pragma unroll
+    for (int j = 0; j < NV_BATCH; ++j) b[j] = beaten_by(lane, (int)(p[j] & 0xffffu), (int)(p[j] >> 16), c[j]);
+#pragma unroll
+    for (int j = 0; j < NV_BATCH; ++j) {
+      bool beaten = !(c[j] > 0.f) || __any_sync(0xffffffffu, b[j]);
+      const int x = (int)(p[j] & 0xffffu), y = (int)(p[j] >> 16);
+      for (int k0 = 32; k0 < nwin && !beaten; k0 += 32)
+        beaten = __any_sync(0xffffffffu, beaten_by(k0 + lane, x, y, c[j]));
+      if (!beaten && lane == 0) {
+        const int idx = atomicAdd(&counters[cam * 8 + 1], 1);
+        if (idx < candCap) {
+          const unsigned cb = ~__float_as_uint(c[j]);
+          cand[(size_t)cam * candCap + idx] =
+              ((unsigned long long)cb << 32) | ((unsigned long long)y << 16) | (unsigned long long)x;
+        }
       }
     }
   }
