@@ -41,29 +41,71 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML from a polling thread
+    (about 1 kHz), nvidia-smi one-shot queries if NVML is not importable."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.gpu, self.sm, self.mx, self.reasons = gpu_index, [], [], set()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu_index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if gpu_index < len(ids) and ids[gpu_index].isdigit():
+                    phys = int(ids[gpu_index])
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def start(self):
-        # one-shot queries from a polling thread (a looping nvidia-smi block-buffers its pipe)
         self.stop_flag = False
-        self.t = threading.Thread(target=self._poll, daemon=True)
+        self.t = threading.Thread(target=self._poll_nvml if self.nvml else self._poll_smi, daemon=True)
         self.t.start()
 
-    def _poll(self):
+    def _poll_nvml(self):
+        n = self.nvml
+        bits = {"hw_slowdown": getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        try:
+            self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM)))
+        except Exception:
+            pass
+        while not self.stop_flag:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)))
+                r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for nm, b in bits.items():
+                    if r & b:
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            time.sleep(0.001)
+
+    def _poll_smi(self):
         cmd = ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
                str(self.gpu)]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         while not self.stop_flag:
             try:
                 out = subprocess.run(cmd, capture_output=True, text=True, timeout=5).stdout
                 for line in out.strip().splitlines():
-                    self.rows.append(line.strip().split(", "))
+                    r = line.strip().split(", ")
+                    self.sm.append(float(r[1]))
+                    self.mx.append(float(r[2]))
+                    for k, nm in enumerate(names):
+                        if r[5 + k].strip().lower().startswith("active"):
+                            self.reasons.add(nm)
             except Exception:
                 pass
             time.sleep(0.05)
@@ -71,20 +113,10 @@ class ClockSampler:
     def stop(self):
         self.stop_flag = True
         self.t.join(timeout=6)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-                for k, nm in enumerate(names):
-                    if r[5 + k].strip().lower().startswith("active"):
-                        reasons.add(nm)
-            except Exception:
-                pass
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(max(mx)) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+                "sm_max_mhz": float(max(self.mx)) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def dist_env():

@@ -10,8 +10,13 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <mutex>
 #include <new>
+#include <sched.h>
+#include <thread>
 #include <vector>
 
 #include "ba_kernels.cuh"
@@ -174,10 +179,54 @@ void quat_mul(const double a[4], const double b[4], double p[4]) {
   p[3] = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
 }
 
+// Solver buffers come from the device's stream-ordered memory pool with an unlimited release
+// threshold: cosl_ba_solve creates and destroys a solver per call, and after the first call the
+// ~30 buffers (0.7 GB at c4) are handed out again without touching the driver's allocator.
+static void pool_keep(int device) {
+  static std::mutex mu;
+  static bool done[64] = {};
+  std::lock_guard<std::mutex> lk(mu);
+  if (device < 0 || device >= 64 || done[device]) return;
+  done[device] = true;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    unsigned long long keep = ~0ull;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+}
+
 template <typename T>
-int dev_alloc(T** p, size_t count) {
-  COSL_CUDA(cudaMalloc((void**)p, sizeof(T) * (count ? count : 1)));
+int dev_alloc(cudaStream_t st, T** p, size_t count) {
+  COSL_CUDA(cudaMallocAsync((void**)p, sizeof(T) * (count ? count : 1), st));
   return COSL_OK;
+}
+
+// worker threads for host-side index building: affinity and cgroup quota, at most 16
+static int host_threads() {
+  static const int n = [] {
+    int c = 1;
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) c = CPU_COUNT(&set);
+    if (FILE* f = std::fopen("/sys/fs/cgroup/cpu.max", "r")) {
+      char q[64];
+      long long per = 0;
+      if (std::fscanf(f, "%63s %lld", q, &per) == 2 && std::strcmp(q, "max") != 0 && per > 0) {
+        const long long quota = std::atoll(q);
+        if (quota > 0) c = std::min<long long>(c, (quota + per - 1) / per);
+      }
+      std::fclose(f);
+    }
+    return std::max(1, std::min(c, 16));
+  }();
+  return n;
+}
+
+static bool ba_timing() {
+  static const bool on = std::getenv("COSL_BA_TIMING") != nullptr;
+  return on;
+}
+static double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
 int upload_params(cosl_ba_solver* s, const cosl_ba_problem* p) {
@@ -210,7 +259,9 @@ void free_solver(cosl_ba_solver* s) {
                   s->d_items, s->d_entries, s->d_Linv, s->d_firstBlk, s->d_rowEnd, s->d_envOff,
                   s->d_envBuf};
   if (s->solveGraph) cudaGraphExecDestroy(s->solveGraph);
-  for (void* b : bufs) cudaFree(b);
+  for (void* b : bufs)
+    if (b) cudaFreeAsync(b, s->stream);
+  if (s->stream) cudaStreamSynchronize(s->stream);
   if (s->h_sc) cudaFreeHost(s->h_sc);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -256,39 +307,49 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   // pair lists of the Schur contraction: for every free point, every pair (a <= b) of its
   // free-camera observations, bucketed by camera pair (counting sort)
   const int mf = s->mf;
+  const double tPair0 = now_s();
   std::vector<long long> pcount((size_t)mf * mf + 1, 0);
-  for (int i = ncon; i < n; ++i) {
-    for (long long a = p->ptr[i]; a < p->ptr[i + 1]; ++a) {
-      if (cam[a] < mcon) continue;
-      for (long long b = a; b < p->ptr[i + 1]; ++b) {
-        if (cam[b] < mcon) continue;
-        int ja = cam[a] - mcon, jb = cam[b] - mcon;
-        if (ja > jb) std::swap(ja, jb);
-        pcount[(size_t)ja * mf + jb + 1]++;
-      }
-    }
-  }
-  for (size_t k = 0; k < (size_t)mf * mf; ++k) pcount[k + 1] += pcount[k];
-  const long long nEntries = pcount[(size_t)mf * mf];
-  s->nEntries = nEntries;
-  std::vector<int2> entries((size_t)nEntries);
+  std::vector<int2> entries;
+  long long nEntries = 0;
   {
-    std::vector<long long> fill(pcount.begin(), pcount.end() - 1);
-    for (int i = ncon; i < n; ++i)
-      for (long long a = p->ptr[i]; a < p->ptr[i + 1]; ++a) {
-        if (cam[a] < mcon) continue;
-        for (long long b = a; b < p->ptr[i + 1]; ++b) {
-          if (cam[b] < mcon) continue;
-          int ja = cam[a] - mcon, jb = cam[b] - mcon;
-          long long oa = a, ob = b;
-          if (ja > jb) {
-            std::swap(ja, jb);
-            std::swap(oa, ob);
+    // Worker t owns the camera pairs whose smaller camera lies in its range, so counting and
+    // filling need no synchronisation and the entry order inside a bucket (by point index) does
+    // not depend on the number of workers.
+    const int T = (mf >= 64) ? host_threads() : 1;
+    auto for_pairs = [&](int t, auto&& emit) {
+      const int ja0 = (int)((long long)mf * t / T), ja1 = (int)((long long)mf * (t + 1) / T);
+      for (int i = ncon; i < n; ++i) {
+        const long long o0 = p->ptr[i], o1 = p->ptr[i + 1];
+        for (long long a = o0; a < o1; ++a) {
+          const int ja = cam[a] - mcon;
+          if (ja < ja0 || ja >= ja1) continue;
+          for (long long b = o0; b < o1; ++b) {
+            const int jb = cam[b] - mcon;
+            if (jb > ja || (jb == ja && b >= a)) emit((size_t)ja * mf + jb, a, b);
           }
-          entries[fill[(size_t)ja * mf + jb]++] = make_int2((int)oa, (int)ob);
         }
       }
+    };
+    auto run = [&](auto&& body) {
+      std::vector<std::thread> th;
+      for (int t = 1; t < T; ++t) th.emplace_back(body, t);
+      body(0);
+      for (auto& x : th) x.join();
+    };
+    run([&](int t) { for_pairs(t, [&](size_t bucket, long long, long long) { pcount[bucket + 1]++; }); });
+    for (size_t k = 0; k < (size_t)mf * mf; ++k) pcount[k + 1] += pcount[k];
+    nEntries = pcount[(size_t)mf * mf];
+    entries.resize((size_t)nEntries);
+    std::vector<long long> fill(pcount.begin(), pcount.end() - 1);
+    run([&](int t) {
+      for_pairs(t, [&](size_t bucket, long long a, long long b) {
+        entries[fill[bucket]++] = make_int2((int)a, (int)b);
+      });
+    });
   }
+  s->nEntries = nEntries;
+  if (ba_timing()) std::fprintf(stderr, "[ba timing] pair lists %.1f ms (%lld entries, %d threads)\n",
+                                1e3 * (now_s() - tPair0), nEntries, host_threads());
   std::vector<BaPairItem> items;
   const int chunk = 512;
   for (int ja = 0; ja < mf; ++ja)
@@ -315,30 +376,30 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
     camK[5 * j + 4] = K[5];
   }
   // device allocations
-  COSL_TRY(dev_alloc(&s->d_camK, (size_t)m * 5));
-  COSL_TRY(dev_alloc(&s->d_camR0, (size_t)m * 9));
-  COSL_TRY(dev_alloc(&s->d_pa, (size_t)m * 6));
-  COSL_TRY(dev_alloc(&s->d_na, (size_t)m * 6));
-  COSL_TRY(dev_alloc(&s->d_dpa, (size_t)m * 6));
-  COSL_TRY(dev_alloc(&s->d_pb, (size_t)n * 3));
-  COSL_TRY(dev_alloc(&s->d_nb, (size_t)n * 3));
-  COSL_TRY(dev_alloc(&s->d_dpb, (size_t)n * 3));
-  COSL_TRY(dev_alloc(&s->d_cam, (size_t)N));
-  COSL_TRY(dev_alloc(&s->d_pt, (size_t)N));
-  COSL_TRY(dev_alloc(&s->d_cobs, (size_t)Nc));
-  COSL_TRY(dev_alloc(&s->d_ccam, (size_t)Nc));
-  COSL_TRY(dev_alloc(&s->d_xy, (size_t)N * 2));
-  COSL_TRY(dev_alloc(&s->d_wgt, (size_t)N));
-  COSL_TRY(dev_alloc(&s->d_ptr, (size_t)n + 1));
-  COSL_TRY(dev_alloc(&s->d_W, (size_t)N * 18));
-  COSL_TRY(dev_alloc(&s->d_V, (size_t)n * 6));
-  COSL_TRY(dev_alloc(&s->d_eb, (size_t)n * 3));
-  COSL_TRY(dev_alloc(&s->d_Uea, (size_t)m * 27));
+  COSL_TRY(dev_alloc(s->stream, &s->d_camK, (size_t)m * 5));
+  COSL_TRY(dev_alloc(s->stream, &s->d_camR0, (size_t)m * 9));
+  COSL_TRY(dev_alloc(s->stream, &s->d_pa, (size_t)m * 6));
+  COSL_TRY(dev_alloc(s->stream, &s->d_na, (size_t)m * 6));
+  COSL_TRY(dev_alloc(s->stream, &s->d_dpa, (size_t)m * 6));
+  COSL_TRY(dev_alloc(s->stream, &s->d_pb, (size_t)n * 3));
+  COSL_TRY(dev_alloc(s->stream, &s->d_nb, (size_t)n * 3));
+  COSL_TRY(dev_alloc(s->stream, &s->d_dpb, (size_t)n * 3));
+  COSL_TRY(dev_alloc(s->stream, &s->d_cam, (size_t)N));
+  COSL_TRY(dev_alloc(s->stream, &s->d_pt, (size_t)N));
+  COSL_TRY(dev_alloc(s->stream, &s->d_cobs, (size_t)Nc));
+  COSL_TRY(dev_alloc(s->stream, &s->d_ccam, (size_t)Nc));
+  COSL_TRY(dev_alloc(s->stream, &s->d_xy, (size_t)N * 2));
+  COSL_TRY(dev_alloc(s->stream, &s->d_wgt, (size_t)N));
+  COSL_TRY(dev_alloc(s->stream, &s->d_ptr, (size_t)n + 1));
+  COSL_TRY(dev_alloc(s->stream, &s->d_W, (size_t)N * 18));
+  COSL_TRY(dev_alloc(s->stream, &s->d_V, (size_t)n * 6));
+  COSL_TRY(dev_alloc(s->stream, &s->d_eb, (size_t)n * 3));
+  COSL_TRY(dev_alloc(s->stream, &s->d_Uea, (size_t)m * 27));
   s->ld = ((s->ns + 1 + 15) / 16) * 16;
   s->nb = (s->ns + CB - 1) / CB;
-  COSL_TRY(dev_alloc(&s->d_Srhs, (size_t)s->ld * (s->ns ? s->ns : 1)));
-  COSL_TRY(dev_alloc(&s->d_Linv, (size_t)std::max(1, s->nb) * CB * CB));
-  COSL_TRY(dev_alloc(&s->d_firstBlk, (size_t)std::max(1, s->nb)));
+  COSL_TRY(dev_alloc(s->stream, &s->d_Srhs, (size_t)s->ld * (s->ns ? s->ns : 1)));
+  COSL_TRY(dev_alloc(s->stream, &s->d_Linv, (size_t)std::max(1, s->nb) * CB * CB));
+  COSL_TRY(dev_alloc(s->stream, &s->d_firstBlk, (size_t)std::max(1, s->nb)));
   {
     // block-row envelope from the camera co-visibility (pair counts): pair (ja <= jb) puts
     // entries at rows of jb, columns of ja of the lower factor
@@ -369,21 +430,21 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
       envOff[J + 1] = envOff[J] + (long long)std::min(CB, s->ns - J * CB) * (rowEnd[J] - J * CB);
     }
     s->envCount = envOff[nbk] + s->ns;
-    COSL_TRY(dev_alloc(&s->d_rowEnd, (size_t)std::max(1, nbk)));
-    COSL_TRY(dev_alloc(&s->d_envOff, (size_t)nbk + 2));
-    COSL_TRY(dev_alloc(&s->d_envBuf, (size_t)std::max<long long>(1, s->envCount)));
+    COSL_TRY(dev_alloc(s->stream, &s->d_rowEnd, (size_t)std::max(1, nbk)));
+    COSL_TRY(dev_alloc(s->stream, &s->d_envOff, (size_t)nbk + 2));
+    COSL_TRY(dev_alloc(s->stream, &s->d_envBuf, (size_t)std::max<long long>(1, s->envCount)));
     COSL_CUDA(cudaMemcpy(s->d_rowEnd, rowEnd.data(), sizeof(int) * std::max(1, nbk),
                          cudaMemcpyHostToDevice));
     COSL_CUDA(cudaMemcpy(s->d_envOff, envOff.data(), sizeof(long long) * (nbk + 1),
                          cudaMemcpyHostToDevice));
     COSL_CUDA(cudaMemset(s->d_Srhs, 0, sizeof(double) * (size_t)s->ld * (s->ns ? s->ns : 1)));
   }
-  COSL_TRY(dev_alloc(&s->d_y, (size_t)s->ns));
-  COSL_TRY(dev_alloc(&s->d_x, (size_t)s->ns));
-  COSL_TRY(dev_alloc(&s->d_sc, (size_t)SC_NTOT));
-  COSL_TRY(dev_alloc(&s->d_outlier, (size_t)N));
-  COSL_TRY(dev_alloc(&s->d_items, items.size()));
-  COSL_TRY(dev_alloc(&s->d_entries, (size_t)nEntries));
+  COSL_TRY(dev_alloc(s->stream, &s->d_y, (size_t)s->ns));
+  COSL_TRY(dev_alloc(s->stream, &s->d_x, (size_t)s->ns));
+  COSL_TRY(dev_alloc(s->stream, &s->d_sc, (size_t)SC_NTOT));
+  COSL_TRY(dev_alloc(s->stream, &s->d_outlier, (size_t)N));
+  COSL_TRY(dev_alloc(s->stream, &s->d_items, items.size()));
+  COSL_TRY(dev_alloc(s->stream, &s->d_entries, (size_t)nEntries));
   COSL_CUDA(cudaMallocHost(&s->h_sc, sizeof(double) * SC_NTOT));
 #define UP(dst, src, bytes) \
   COSL_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s->stream))
@@ -911,7 +972,10 @@ int cosl_ba_solver_create(const cosl_ba_problem* prob, const cosl_ba_options* op
     delete s;
     return set_error(COSL_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
   }
+  pool_keep(opt->device);
+  const double tBuild0 = now_s();
   const int rc = build_solver(s, prob);
+  if (ba_timing()) std::fprintf(stderr, "[ba timing] build_solver %.1f ms\n", 1e3 * (now_s() - tBuild0));
   if (rc != COSL_OK) {
     free_solver(s);
     return rc;
@@ -977,15 +1041,22 @@ const char* cosl_ba_solver_timer(cosl_ba_solver* s, int idx, double* ms, int* ca
 int cosl_ba_solve(cosl_ba_problem* prob, const cosl_ba_options* opt,
                   double info[COSL_BA_INFOSZ]) {
   cosl_ba_solver* s = nullptr;
+  const double t0 = now_s();
   COSL_TRY(cosl_ba_solver_create(prob, opt, nullptr, &s));
+  const double t1 = now_s();
   int rc = run_robust(s, 0, info);
+  const double t2 = now_s();
   if (rc == COSL_OK) rc = download(s, prob);
+  const double t3 = now_s();
   if (rc == COSL_OK && info && prob->outlier) {
     long long c = 0;
     for (long long o = 0; o < prob->nobs; ++o) c += prob->outlier[o] ? 1 : 0;
     info[13] = (double)c;
   }
   free_solver(s);
+  if (ba_timing())
+    std::fprintf(stderr, "[ba timing] cosl_ba_solve: create %.1f  run %.1f  download %.1f  destroy %.1f ms\n",
+                 1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2), 1e3 * (now_s() - t3));
   return rc;
 }
 

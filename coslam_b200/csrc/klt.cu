@@ -22,6 +22,12 @@ struct cosl_klt {
   int levelSkip = 1, halfWidth = 3;
   float trackMargin = 4.f, conv = 0.1f, ssd = 5000.f, detectMargin = 10.f;
   cudaStream_t stream = nullptr;
+  // host uploads run on their own stream, one event per camera, so that klt_front of camera c
+  // overlaps the copy of camera c+1 (cosl_klt_group_next path)
+  cudaStream_t copyStream = nullptr;
+  cudaEvent_t evImg[64] = {};
+  cudaEvent_t evFront = nullptr;
+  bool imgPerCam = false, frontRecorded = false;
   // geometry
   int lvW[8], lvH[8];
   long long lvOff[8];
@@ -57,6 +63,9 @@ struct cosl_klt {
   bool fusedOK = false;
   int fusedBlocks = 0;
   int numSM = 148;
+  // launch folding on the combined next() path
+  bool wantTail = false, statusDone = false, suppressDone = false;
+  bool foldAdvance = false, advanceDone = false;
   int detXlo = 0, detXhi = -1, detYlo = 0, detYhi = -1;  // detector window in pixels
   int verBase = 0;
   SectionTimer timer;
@@ -213,6 +222,10 @@ void free_group(cosl_klt* g) {
   cudaFree(g->d_res);
   cudaFree(g->d_present);
   cudaFree(g->d_nbr);
+  if (g->copyStream) cudaStreamDestroy(g->copyStream);
+  if (g->evFront) cudaEventDestroy(g->evFront);
+  for (int c = 0; c < 64; ++c)
+    if (g->evImg[c]) cudaEventDestroy(g->evImg[c]);
   cudaFree(g->d_cand);
   cudaFree(g->d_prelim);
   cudaFree(g->d_counters);
@@ -232,6 +245,17 @@ void free_group(cosl_klt* g) {
 // ---- stages (all asynchronous on g->stream) ----
 
 int upload_images(cosl_klt* g, const uint8_t* const* imgs, size_t pitch, cudaMemcpyKind kind) {
+  if (kind == cudaMemcpyHostToDevice && g->C > 1 && g->copyStream) {
+    // the previous frame's front pass must have consumed d_img before it is overwritten
+    if (g->frontRecorded) COSL_CUDA(cudaStreamWaitEvent(g->copyStream, g->evFront, 0));
+    for (int c = 0; c < g->C; ++c) {
+      COSL_CUDA(cudaMemcpy2DAsync(g->d_img + (size_t)c * g->imgStride, g->imgPitch, imgs[c], pitch,
+                                  g->W, g->H, kind, g->copyStream));
+      COSL_CUDA(cudaEventRecord(g->evImg[c], g->copyStream));
+    }
+    g->imgPerCam = true;
+    return COSL_OK;
+  }
   for (int c = 0; c < g->C; ++c)
     COSL_CUDA(cudaMemcpy2DAsync(g->d_img + (size_t)c * g->imgStride, g->imgPitch, imgs[c], pitch,
                                 g->W, g->H, kind, g->stream));
@@ -262,8 +286,27 @@ int build_pyramid(cosl_klt* g, bool wantCorn) {
   fp.ixhi = g->detXhi;
   fp.iylo = g->detYlo;
   fp.iyhi = g->detYhi;
-  dim3 g0(div_up(fp.nStrips * fp.nChunks, FS_WARPS), g->C);
-  COSL_LAUNCH(klt_front, g0, 32 * FS_WARPS, 0, g->stream, fp);
+  if (g->imgPerCam) {
+    // two half-groups: the front pass of the first half overlaps the upload of the second (a launch
+    // per camera would leave the SMs mostly empty: 500 warps per 1280x720 camera)
+    g->imgPerCam = false;
+    const int half = (g->C + 1) / 2;
+    for (int c0 = 0; c0 < g->C; c0 += half) {
+      const int nc = std::min(half, g->C - c0);
+      COSL_CUDA(cudaStreamWaitEvent(g->stream, g->evImg[c0 + nc - 1], 0));
+      fp.camBase = c0;
+      dim3 g1(div_up(fp.nStrips * fp.nChunks, FS_WARPS), nc);
+      COSL_LAUNCH(klt_front, g1, 32 * FS_WARPS, 0, g->stream, fp);
+    }
+  } else {
+    fp.camBase = 0;
+    dim3 g0(div_up(fp.nStrips * fp.nChunks, FS_WARPS), g->C);
+    COSL_LAUNCH(klt_front, g0, 32 * FS_WARPS, 0, g->stream, fp);
+  }
+  if (g->evFront) {
+    COSL_CUDA(cudaEventRecord(g->evFront, g->stream));
+    g->frontRecorded = true;
+  }
   g->cornValid = wantCorn;
   for (int l = 2; l < g->L; ++l) {
     dim3 gl(div_up(g->lvW[l], PD_TW), div_up(g->lvH[l], PD_TH), g->C);
@@ -332,10 +375,21 @@ int run_tracker(cosl_klt* g) {
     long long pyrStride = g->pyrStride;
     KltTrackParams Plax = track_params(g, false), Pstrict = track_params(g, true);
     int verBase = g->verBase;
+    KltTail tail = {nullptr, nullptr, nullptr, 0, 0, 0};
+    if (g->wantTail) {
+      tail.dest = g->d_feat;
+      tail.counters = g->d_counters;
+      tail.corn = g->d_corn;
+      tail.W = g->W;
+      tail.H = g->H;
+      tail.suppress = g->cornValid ? 1 : 0;  // only a map of THIS frame may be marked
+      g->statusDone = true;
+      g->suppressDone = tail.suppress != 0;
+    }
     void* args[] = {(void*)&P0,          (void*)&P1,     (void*)&pyrStride, (void*)&LV,
                     (void*)&nIter,       (void*)&g->d_src, (void*)&g->d_state, (void*)&g->d_ver,
                     (void*)&g->d_waitset, (void*)&g->d_res, (void*)&C,        (void*)&Plax,
-                    (void*)&Pstrict,     (void*)&verBase};
+                    (void*)&Pstrict,     (void*)&verBase, (void*)&tail};
     COSL_CUDA(cudaLaunchCooperativeKernel((const void*)klt_gain_fused, dim3(g->fusedBlocks),
                                           dim3(KLT_FUSED_THREADS), args, 0, g->stream));
     g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -432,7 +486,9 @@ int run_detector(cosl_klt* g, int mode, int nPresentExt) {
                 g->W, g->H, g->cfg.minCornerness, mg / Wf, mg / Hf, 1.0f - mg / Wf, 1.0f - mg / Hf);
   }
   g->cornValid = false;  // the suppression below modifies the map
-  if (mode == 1) {
+  if (mode == 1 && g->suppressDone) {
+    g->suppressDone = false;  // the tracker's last pass already marked the live tracks
+  } else if (mode == 1) {
     dim3 gs(div_up(g->F, 256), g->C);
     COSL_LAUNCH(klt_suppress, gs, 256, 0, g->stream, g->d_res, g->F, g->F, g->d_corn, g->W, g->H);
   } else if (nPresentExt > 0) {
@@ -450,9 +506,11 @@ int run_detector(cosl_klt* g, int mode, int nPresentExt) {
   g->timer.end(g->stream);
   g->timer.begin(g->secSelect, g->stream);
   COSL_LAUNCH(klt_select_refill, g->C, 1024, g->smemKeys * sizeof(unsigned long long), g->stream,
-              g->d_cand, g->candCap, g->plCap, g->d_counters, g->d_feat, g->d_dst, g->d_present,
+              g->d_cand, g->candCap, g->plCap, g->d_counters, g->d_feat, g->d_dst,
+              g->foldAdvance ? g->d_src : (float4*)nullptr, g->d_present,
               nPresentExt, g->F, g->W, g->H, mode, g->cfg.trackWithGain ? 1 : 0, g->smemKeys);
   g->timer.end(g->stream);
+  g->advanceDone = g->foldAdvance;
   COSL_CUDA(cudaGetLastError());
   return COSL_OK;
 }
@@ -470,16 +528,22 @@ int advance(cosl_klt* g) {
   // swapFeatureBuffers + swap pyramids (v3d_gpuklt.h:252-259); the feature buffer is copied, not
   // swapped, so a later feed() still sees the provided set (see DESIGN.md, quirk list)
   const size_t n = (size_t)g->F * g->C;
-  COSL_LAUNCH(klt_copy_f4, (unsigned)div_up64(n, 256), 256, 0, g->stream, g->d_dst, g->d_src, n);
+  if (g->advanceDone)
+    g->advanceDone = false;  // klt_select_refill already wrote the provided set to both buffers
+  else
+    COSL_LAUNCH(klt_copy_f4, (unsigned)div_up64(n, 256), 256, 0, g->stream, g->d_dst, g->d_src, n);
   g->cur = 1 - g->cur;
   return COSL_OK;
 }
 
 int do_track(cosl_klt* g, bool wantCorn = false) {
   COSL_TRY(build_pyramid(g, wantCorn));
-  COSL_TRY(run_tracker(g));
   COSL_TRY(zero_counters(g));
-  COSL_TRY(run_status(g));
+  g->statusDone = g->suppressDone = false;
+  g->wantTail = true;  // the persistent gain tracker writes the feature table itself
+  COSL_TRY(run_tracker(g));
+  g->wantTail = false;
+  if (!g->statusDone) COSL_TRY(run_status(g));
   return COSL_OK;
 }
 
@@ -564,6 +628,17 @@ int cosl_klt_group_create(const cosl_klt_config* cfg, int nCams, int width, int 
   if (e != cudaSuccess) {
     delete g;
     return set_error(COSL_E_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+  }
+  if (cudaStreamCreateWithFlags(&g->copyStream, cudaStreamNonBlocking) == cudaSuccess) {
+    bool ok = cudaEventCreateWithFlags(&g->evFront, cudaEventDisableTiming) == cudaSuccess;
+    for (int c = 0; c < g->C && ok; ++c)
+      ok = cudaEventCreateWithFlags(&g->evImg[c], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {  // fall back to uploads on the compute stream
+      cudaStreamDestroy(g->copyStream);
+      g->copyStream = nullptr;
+    }
+  } else {
+    g->copyStream = nullptr;
   }
   int rc = alloc_group(g);
   if (rc != COSL_OK) {
@@ -705,7 +780,10 @@ int cosl_klt_group_first(cosl_klt* h, const uint8_t* const* imgs, size_t pitch,
   KLT_ENTER(h)
   if (!imgs || pitch < (size_t)h->W) return set_error(COSL_E_INVALID, "group_first: bad argument");
   COSL_TRY(upload_images(h, imgs, pitch, cudaMemcpyHostToDevice));
-  COSL_TRY(do_detect(h, 0));
+  h->foldAdvance = true;  // the provided set goes to both feature buffers in one launch
+  const int rcDet = do_detect(h, 0);
+  h->foldAdvance = false;
+  if (rcDet != COSL_OK) return rcDet;
   COSL_TRY(advance(h));
   COSL_TRY(fetch_results(h));
   for (int c = 0; c < h->C; ++c) {
@@ -720,7 +798,10 @@ int cosl_klt_group_next(cosl_klt* h, const uint8_t* const* imgs, size_t pitch,
   KLT_ENTER(h)
   if (!imgs || pitch < (size_t)h->W) return set_error(COSL_E_INVALID, "group_next: bad argument");
   COSL_TRY(upload_images(h, imgs, pitch, cudaMemcpyHostToDevice));
-  COSL_TRY(do_redetect(h));
+  h->foldAdvance = true;  // the provided set goes to both feature buffers in one launch
+  const int rcDet = do_redetect(h);
+  h->foldAdvance = false;
+  if (rcDet != COSL_OK) return rcDet;
   COSL_TRY(advance(h));
   COSL_TRY(fetch_results(h));
   for (int c = 0; c < h->C; ++c) {
@@ -735,7 +816,10 @@ int cosl_klt_group_next_dev(cosl_klt* h, const uint8_t* const* dimgs, size_t pit
   if (!dimgs || pitch < (size_t)h->W)
     return set_error(COSL_E_INVALID, "group_next_dev: bad argument");
   COSL_TRY(upload_images(h, dimgs, pitch, cudaMemcpyDeviceToDevice));
-  COSL_TRY(do_redetect(h));
+  h->foldAdvance = true;  // the provided set goes to both feature buffers in one launch
+  const int rcDet = do_redetect(h);
+  h->foldAdvance = false;
+  if (rcDet != COSL_OK) return rcDet;
   COSL_TRY(advance(h));
   return COSL_OK;
 }

@@ -45,6 +45,7 @@ struct FrontParams {
   long long pyrStride, lv1Off;
   float* corn;
   int W, H, nStrips, nChunks, wantL1, wantCorn;
+  int camBase;  // first camera of this launch (per-camera launches pipeline with the uploads)
   float minC;
   int ixlo, ixhi, iylo, iyhi;  // detector window (pixels whose centre lies inside the margins)
 };
@@ -54,7 +55,7 @@ klt_front(const FrontParams P) {
   const int lane = threadIdx.x & 31;
   const int wid = blockIdx.x * FS_WARPS + (threadIdx.x >> 5);
   if (wid >= P.nStrips * P.nChunks) return;
-  const int cam = blockIdx.y;
+  const int cam = blockIdx.y + P.camBase;
   const int chunk = wid / P.nStrips, strip = wid - chunk * P.nStrips;
   const int W = P.W, H = P.H;
   const int X0 = strip * FS_SW - FS_HL;

@@ -540,7 +540,8 @@ __device__ __forceinline__ void bitonic_sort(unsigned long long* k, int n2) {
 __global__ void __launch_bounds__(1024)
 klt_select_refill(unsigned long long* __restrict__ cand, int candCap, int plCap,
                   int* __restrict__ counters, cosl_klt_feature* __restrict__ dest,
-                  float4* __restrict__ dstbuf, const float4* __restrict__ present, int nPresentExt,
+                  float4* __restrict__ dstbuf, float4* __restrict__ alsoSrc,
+                  const float4* __restrict__ present, int nPresentExt,
                   int F, int W, int H, int mode, int withGain, int smemKeys) {
   extern __shared__ unsigned long long s_keys[];
   __shared__ int s_scan[1024];
@@ -565,6 +566,7 @@ klt_select_refill(unsigned long long* __restrict__ cand, int candCap, int plCap,
   const float Wf = (float)W, Hf = (float)H;
   cosl_klt_feature* d = dest + (size_t)cam * F;
   float4* pb = dstbuf + (size_t)cam * F;
+  float4* ps = alsoSrc ? alsoSrc + (size_t)cam * F : nullptr;  // advanceFrame copy folded in
   if (mode == 0) {
     const int nDet = max(0, min(min(nCand, plCap), F - nPresentExt));
     for (int i = threadIdx.x; i < F; i += blockDim.x) {
@@ -597,6 +599,7 @@ klt_select_refill(unsigned long long* __restrict__ cand, int candCap, int plCap,
       }
       d[i] = f;
       pb[i] = p;
+      if (ps) ps[i] = p;
     }
     if (threadIdx.x == 0) {
       cnt[2] = nDet + nPresentExt;
@@ -653,6 +656,7 @@ klt_select_refill(unsigned long long* __restrict__ cand, int candCap, int plCap,
           p = make_float4(f.pos[0], f.pos[1], 1.0f, 0.f);
         }
         pb[i] = p;
+        if (ps) ps[i] = p;
       }
       __syncthreads();
       if (threadIdx.x == 0) s_base += s_scan[32];

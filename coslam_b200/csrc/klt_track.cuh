@@ -274,6 +274,15 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned l
 #ifndef KLT_FUSED_MINBLOCKS
 #define KLT_FUSED_MINBLOCKS 4
 #endif
+// Optional tail of the last pass: what klt_status (feature table + live count) and klt_suppress
+// (-1e30 at the pixel of every live track) would do in two more launches.  dest == nullptr: off.
+struct KltTail {
+  cosl_klt_feature* dest;
+  int* counters;
+  float* corn;
+  int W, H, suppress;
+};
+
 constexpr int KLT_FUSED_THREADS = KLT_FUSED_THREADS_N;  // 16 lane groups per CTA
 constexpr int KLT_GPB = KLT_FUSED_THREADS / KLT_G;
 
@@ -283,7 +292,7 @@ klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
                float4* __restrict__ state, unsigned long long* __restrict__ rec,
                const int* __restrict__ waitset,
                float4* __restrict__ out, int C, KltTrackParams Plax, KltTrackParams Pstrict,
-               int verBase) {
+               int verBase, KltTail tail) {
   __shared__ float4 s_tile[KLT_GPB][KLT_TW * KLT_TP];  // one tile per lane group
   const int gl = threadIdx.x & (KLT_G - 1), grpBase = threadIdx.x & (32 - KLT_G);
   const int grpInBlock = threadIdx.x / KLT_G;
@@ -519,7 +528,28 @@ klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
         if (pre_invalid) res = make_float4(-1.f, -1.f, -1.f, 0.f);
         if (staged) cur0 = res;
         if (gl == 0 && active) {
-          if (pass == LV.n * nIter) out[item] = res;
+          if (pass == LV.n * nIter) {
+            out[item] = res;
+            if (tail.dest) {  // v3d_gpuklt.cpp:872-888 and :475-500, see klt_status / klt_suppress
+              cosl_klt_feature f;
+              const bool live = res.x >= 0.f;
+              f.status = live ? 0 : -1;
+              f.pos[0] = live ? res.x : -1.0f;
+              f.pos[1] = live ? res.y : -1.0f;
+              f.gain = live ? res.z : 1.0f;
+              f.fed = -1;
+              tail.dest[item] = f;
+              if (live) {
+                atomicAdd(&tail.counters[cam * 8 + 0], 1);
+                if (tail.suppress && res.x < 1.0f && res.y >= 0.0f && res.y < 1.0f) {
+                  const int ix = (int)floorf(__fmul_rn(res.x, (float)tail.W));
+                  const int iy = (int)floorf(__fmul_rn(res.y, (float)tail.H));
+                  if (ix >= 0 && ix < tail.W && iy >= 0 && iy < tail.H)
+                    tail.corn[(size_t)cam * tail.W * tail.H + (size_t)iy * tail.W + ix] = -1e30f;
+                }
+              }
+            }
+          }
           if (!staged) __stcg(&state[item], res);
           st_relaxed_u64(rec + (size_t)wr * T + item,
                          ((unsigned long long)(unsigned)(verBase + pass) << 32) |
