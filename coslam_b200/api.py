@@ -79,6 +79,7 @@ def _load():
     L.cosl_ba_solver_timer.argtypes = [vp, ci, C.POINTER(cd), pint]
     L.cosl_ba_solver_timer.restype = C.c_char_p
     L.cosl_ba_solver_profile_enable.argtypes = [vp, ci]
+    L.cosl_ba_solver_stats.argtypes = [vp, C.POINTER(cd)]
     return L
 
 

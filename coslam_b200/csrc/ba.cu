@@ -99,6 +99,7 @@ struct cosl_ba_solver {
   long long* d_envOff = nullptr;  // [nb + 1] packed offsets for the enveloped all-reduce
   double* d_envBuf = nullptr;
   long long envCount = 0;
+  double factorFlops = 0.0;
   double* d_sc = nullptr;
   unsigned char* d_outlier = nullptr;
   BaPairItem* d_items = nullptr;
@@ -430,6 +431,11 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
       envOff[J + 1] = envOff[J] + (long long)std::min(CB, s->ns - J * CB) * (rowEnd[J] - J * CB);
     }
     s->envCount = envOff[nbk] + s->ns;
+    s->factorFlops = 0.0;
+    for (int j = 0; j < s->ns; ++j) {
+      const double hgt = (double)(rowEnd[j / CB] - j);
+      s->factorFlops += hgt * hgt;
+    }
     COSL_TRY(dev_alloc(s->stream, &s->d_rowEnd, (size_t)std::max(1, nbk)));
     COSL_TRY(dev_alloc(s->stream, &s->d_envOff, (size_t)nbk + 2));
     COSL_TRY(dev_alloc(s->stream, &s->d_envBuf, (size_t)std::max<long long>(1, s->envCount)));
@@ -1019,6 +1025,17 @@ int cosl_ba_solver_destroy(cosl_ba_solver* s) {
 }
 
 void* cosl_ba_solver_stream(cosl_ba_solver* s) { return s ? (void*)s->stream : nullptr; }
+
+int cosl_ba_solver_stats(cosl_ba_solver* s, double out[8]) {
+  if (!s || !out) return set_error(COSL_E_INVALID, "cosl_ba_solver_stats: null argument");
+  for (int k = 0; k < 8; ++k) out[k] = 0.0;
+  out[0] = (double)s->ns;
+  out[1] = (double)s->envCount;
+  out[2] = s->smallSolve ? (double)s->ns * s->ns * s->ns / 3.0 : s->factorFlops;
+  out[3] = (double)s->nEntries;
+  out[4] = (double)s->nItems;
+  return COSL_OK;
+}
 
 int cosl_ba_solver_profile_enable(cosl_ba_solver* s, int on) {
   BA_ENTER(s)

@@ -274,6 +274,11 @@ void* cosl_ba_solver_stream(cosl_ba_solver* s);
 const char* cosl_ba_solver_timer(cosl_ba_solver* s, int idx, double* ms, int* calls);
 /* enable(1) resets and starts accumulating the per-kernel-class timers above. */
 int cosl_ba_solver_profile_enable(cosl_ba_solver* s, int on);
+/* Structure of the reduced camera system, for the roofline arithmetic of bench.py:
+ * out[0] = order ns, out[1] = doubles inside the block envelope (what is cleared, all-reduced and
+ * factored), out[2] = flops of the skyline Cholesky (sum over columns of height^2; ns^3/3 when
+ * dense), out[3] = Schur pair entries, out[4] = pair work items, out[5..7] reserved (0). */
+int cosl_ba_solver_stats(cosl_ba_solver* s, double out[8]);
 
 #ifdef __cplusplus
 }
