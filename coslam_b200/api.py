@@ -230,6 +230,17 @@ class KltGroup:
         _ck(LIB.cosl_klt_group_next(self.h, arr, pitch, self._dest, _ptr(self.counts)))
         return self.feats, self.counts
 
+    def host_ptrs(self, imgs):
+        """Pre-built argument for next_raw(): the per-camera pointer array of a set of host frames
+        (the caller keeps the frames alive)."""
+        return self._imgs(imgs)
+
+    def next_raw(self, ptrs_pitch):
+        """cosl_klt_group_next with a pointer array from host_ptrs(): no per-call marshalling."""
+        _ck(LIB.cosl_klt_group_next(self.h, ptrs_pitch[0], ptrs_pitch[1], self._dest,
+                                    _ptr(self.counts)))
+        return self.feats, self.counts
+
     def next_dev(self, dev_ptrs, pitch):
         arr = (C.c_void_p * self.C)(*dev_ptrs)
         _ck(LIB.cosl_klt_group_next_dev(self.h, arr, pitch))

@@ -90,3 +90,26 @@ def test_group_with_a_blank_camera(api):
             assert ng[c] == nr
             assert np.array_equal(fg[c]["status"], fr["status"])
             assert np.array_equal(_bits(fg[c]["pos"]), _bits(fr["pos"]))
+
+
+def test_fused_tracker_with_more_slots_than_resident_groups(api):
+    """7 cameras x 2048 slots = 14 336 items exceed the lane groups a B200 keeps resident (148 SMs x
+    4 CTAs x 16), so part of the items take the non-resident path of klt_gain_fused (state in
+    global memory, clamped global window loads); results must still equal the per-pass launches
+    bit for bit."""
+    W, H, C = 320, 240, 7
+    s = [seq(H, W, 60 + c, n=3) for c in range(C)]
+    cfg_f = live_cfg(gain=True, min_corner=300.0)
+    cfg_p = live_cfg(gain=True, min_corner=300.0)
+    cfg_p.compat |= 2  # COSL_KLT_PASS_KERNELS
+    cfg_f.minDistance = cfg_p.minDistance = 3
+    a = api.KltGroup(cfg_f, C, W, H, 4, 64, 32)
+    b = api.KltGroup(cfg_p, C, W, H, 4, 64, 32)
+    fa, na = a.first([q.frames[0] for q in s])
+    fb, nb = b.first([q.frames[0] for q in s])
+    assert fa.tobytes() == fb.tobytes() and int(na.sum()) > 2000
+    for k in (1, 2):
+        fa, na = a.next([q.frames[k] for q in s])
+        fb, nb = b.next([q.frames[k] for q in s])
+        assert np.array_equal(na, nb) and fa.tobytes() == fb.tobytes(), f"frame {k}"
+        assert (fa["status"] == 0).sum() > 1500
