@@ -384,6 +384,12 @@ class BaSolver:
     def stream(self):
         return LIB.cosl_ba_solver_stream(self.h)
 
+    def stats(self):
+        out = (C.c_double * 8)()
+        _ck(LIB.cosl_ba_solver_stats(self.h, out))
+        return {"ns": int(out[0]), "envelope_doubles": out[1], "factor_flops": out[2],
+                "pair_entries": out[3], "pair_items": out[4]}
+
     def profile_enable(self, on=True):
         _ck(LIB.cosl_ba_solver_profile_enable(self.h, 1 if on else 0))
 

@@ -96,6 +96,17 @@ ba_chol_small(double* __restrict__ S, int ld, int ns, double* __restrict__ xout,
 //   inverse: thread (c = tid >> 2, gg = tid & 3) owns X[p][c], p == gg (mod 4); row by row forward
 //            substitution with a 4-lane shuffle reduction.
 // ------------------------------------------------------------------------------------------
+// 1/sqrt(d) for the pivots: single-precision MUFU seed + two Newton steps in fp64 (full double
+// accuracy for d inside the float range, which Gauss-Newton diagonals always are).  The library
+// rsqrt() is ~3x longer, and this value sits on the pivot-to-pivot critical path of the whole solve.
+__device__ __forceinline__ double ba_rsqrt(double d) {
+  double y = (double)rsqrtf((float)d);
+  const double h = 0.5 * d;
+  y = __fma_rn(y, __fma_rn(-h * y, y, 0.5), y);
+  y = __fma_rn(y, __fma_rn(-h * y, y, 0.5), y);
+  return y;
+}
+
 __global__ void __launch_bounds__(256)
 ba_chol_potf2_inv(double* __restrict__ S, int ld, int k0, int bs, double* __restrict__ Linv,
                   double* __restrict__ sc, int scFail) {
@@ -123,7 +134,7 @@ ba_chol_potf2_inv(double* __restrict__ S, int ld, int k0, int bs, double* __rest
         if (tid == 0) s_fail = 1;
         d = 1.0;
       }
-      const double rs = rsqrt(d);
+      const double rs = ba_rsqrt(d);
       const double li = colraw[buf][i] * rs;  // L(i, k) for i > k; sqrt(d) for i == k
       if (g == gk) Lm[i][k] = (i >= k) ? li : 0.0;
       if (tid == k) rdiag[k] = rs;
@@ -148,12 +159,14 @@ ba_chol_potf2_inv(double* __restrict__ S, int ld, int k0, int bs, double* __rest
     for (int q = 0; q < 16; ++q) x[q] = 0.0;
 #pragma unroll
     for (int r = 0; r < CB; ++r) {
-      double s = 0.0;
+      // four independent partial sums: the dot product is on the row-to-row critical path
+      double sp[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
       for (int q = 0; q <= ((r - 1) >> 2); ++q) {
         const int p = gg + 4 * q;
-        if (r > 0 && p < r) s += Lm[r][p] * x[q];
+        if (r > 0 && p < r) sp[q & 3] = __fma_rn(Lm[r][p], x[q], sp[q & 3]);
       }
+      double s = (sp[0] + sp[1]) + (sp[2] + sp[3]);
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
       const double xr = (((r == c) ? 1.0 : 0.0) - s) * rdiag[r];

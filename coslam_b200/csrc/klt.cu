@@ -497,9 +497,19 @@ int run_detector(cosl_klt* g, int mode, int nPresentExt) {
                 g->W, g->H);
   }
   const int r = std::max(1, g->cfg.minDistance);
-  dim3 gp(div_up(g->W, NP_COLS), div_up(g->H, 8 * NP_ROWS), g->C);
-  COSL_LAUNCH(klt_nm_prefilter, gp, 256, 0, g->stream, g->d_corn, g->W, g->H, r, g->d_prelim,
-              g->prelimCap, g->d_counters);
+  {
+    const int pr = std::min(r, 3);
+    dim3 gp(div_up(g->W, 32 - 2 * pr), div_up(g->H, 8 * NP_ROWS), g->C);
+    if (pr == 3)
+      COSL_LAUNCH(klt_nm_prefilter<3>, gp, 256, 0, g->stream, g->d_corn, g->W, g->H, g->d_prelim,
+                  g->prelimCap, g->d_counters);
+    else if (pr == 2)
+      COSL_LAUNCH(klt_nm_prefilter<2>, gp, 256, 0, g->stream, g->d_corn, g->W, g->H, g->d_prelim,
+                  g->prelimCap, g->d_counters);
+    else
+      COSL_LAUNCH(klt_nm_prefilter<1>, gp, 256, 0, g->stream, g->d_corn, g->W, g->H, g->d_prelim,
+                  g->prelimCap, g->d_counters);
+  }
   dim3 gv(2 * g->numSM, g->C);
   COSL_LAUNCH(klt_nm_verify, gv, 256, 0, g->stream, g->d_corn, g->W, g->H, r, g->d_prelim,
               g->prelimCap, g->d_cand, g->candCap, g->d_counters);

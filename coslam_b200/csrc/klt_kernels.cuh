@@ -372,9 +372,9 @@ __global__ void klt_suppress(const float4* __restrict__ pts, int n, int ptsStrid
 // with -1e30, which therefore clears their whole neighbourhood), the window being read with
 // CLAMP_TO_EDGE (so a pixel on the image border, whose window contains a clamped copy of itself,
 // never survives).  That predicate is evaluated directly, candidate driven:
-//   klt_nm_prefilter  one streaming pass: pixels with c > 0 that beat |.| of their 5x5 (3x3 when
-//                     r == 1) neighbourhood -- a necessary condition, at most one pixel per 2x2
-//                     block passes -> prelim list
+//   klt_nm_prefilter  one streaming pass: pixels with c > 0 that beat |.| of their (2p+1)^2
+//                     neighbourhood, p = min(r, 3) -- a necessary condition, at most one pixel per
+//                     2x2 block passes -> prelim list
 //   klt_nm_verify     one warp per prelim pixel checks the remaining window texels (L2 resident)
 //                     and appends the survivors' sort keys
 // The cornerness map is mostly zero after thresholding, so the second kernel touches a few
@@ -382,57 +382,58 @@ __global__ void klt_suppress(const float4* __restrict__ pts, int n, int ptsStrid
 // counters[cam*8+4] = prelim count, counters[cam*8+1] = candidate count.
 // ------------------------------------------------------------------------------------------
 constexpr int NP_ROWS = 16;  // rows per warp in klt_nm_prefilter
-constexpr int NP_COLS = 28;  // output columns per warp (lanes 2..29; two halo lanes either side)
 
+// PR = prefilter radius (1..3, <= the suppression radius r): lanes PR .. 31-PR produce outputs.
+template <int PR>
 __global__ void __launch_bounds__(256)
-klt_nm_prefilter(const float* __restrict__ corn, int W, int H, int r, unsigned* __restrict__ prelim,
+klt_nm_prefilter(const float* __restrict__ corn, int W, int H, unsigned* __restrict__ prelim,
                  int prelimCap, int* __restrict__ counters) {
+  constexpr int NCOLS = 32 - 2 * PR, NR = 2 * PR + 1;
   const int cam = blockIdx.z;
   const float* cm = corn + (size_t)cam * W * H;
   const int lane = threadIdx.x & 31;
-  const int x = blockIdx.x * NP_COLS - 2 + lane;                       // unclamped column
+  const int x = blockIdx.x * NCOLS - PR + lane;                        // unclamped column
   const int y0 = (blockIdx.y * 8 + (threadIdx.x >> 5)) * NP_ROWS;      // first output row
   if (y0 >= H) return;
   const int cx = clampi(x, 0, W - 1);
-  // all NP_ROWS + 4 rows of this column in flight at once
-  float v[NP_ROWS + 4];
+  // all NP_ROWS + 2 PR rows of this column in flight at once
+  float v[NP_ROWS + 2 * PR];
 #pragma unroll
-  for (int k = 0; k < NP_ROWS + 4; ++k)
-    v[k] = fabsf(__ldg(&cm[(size_t)clampi(y0 - 2 + k, 0, H - 1) * W + cx]));
-  // The clamped loads make the 5x5 window of a pixel near the image border contain copies of the
-  // edge texels, which is exactly what the reference's CLAMP_TO_EDGE window contains there.
-  const bool colOK = (lane >= 2) && (lane < 2 + NP_COLS) && (x < W);
-  // horizontal maxima of |.| over columns x-2 .. x+2 (x-1 .. x+1 when r == 1): with the centre (incl)
-  // and without it (excl)
-  const bool two = r >= 2;
+  for (int k = 0; k < NP_ROWS + 2 * PR; ++k)
+    v[k] = fabsf(__ldg(&cm[(size_t)clampi(y0 - PR + k, 0, H - 1) * W + cx]));
+  // The clamped loads make the window of a pixel near the image border contain copies of the edge
+  // texels, which is exactly what the reference's CLAMP_TO_EDGE window contains there.
+  const bool colOK = (lane >= PR) && (lane < PR + NCOLS) && (x < W);
+  // horizontal maxima of |.| over columns x-PR .. x+PR: with the centre (incl) and without (excl)
   auto hmax = [&](float c, float& incl, float& excl) {
-    const float l1 = __shfl_up_sync(0xffffffffu, c, 1), r1 = __shfl_down_sync(0xffffffffu, c, 1);
-    float l2 = __shfl_up_sync(0xffffffffu, c, 2), r2 = __shfl_down_sync(0xffffffffu, c, 2);
-    if (!two) l2 = r2 = 0.f;  // |.| >= 0: neutral
-    excl = fmaxf(fmaxf(l1, l2), fmaxf(r1, r2));
-    incl = fmaxf(excl, c);
+    float m = 0.f;  // |.| >= 0: neutral
+#pragma unroll
+    for (int d = 1; d <= PR; ++d)
+      m = fmaxf(m, fmaxf(__shfl_up_sync(0xffffffffu, c, d), __shfl_down_sync(0xffffffffu, c, d)));
+    excl = m;
+    incl = fmaxf(m, c);
   };
-  float hm[5], hx[5];  // rows y-2 .. y+2 of the row under test
-  hmax(v[0], hm[1], hx[1]);
-  hmax(v[1], hm[2], hx[2]);
-  hmax(v[2], hm[3], hx[3]);
-  hmax(v[3], hm[4], hx[4]);
+  float hm[NR], hx[NR];  // rows y-PR .. y+PR of the row under test
+#pragma unroll
+  for (int q = 1; q < NR; ++q) hmax(v[q - 1], hm[q], hx[q]);
   unsigned mine = 0;  // bit k: this lane's pixel of row y0 + k is a preliminary candidate
 #pragma unroll
   for (int k = 0; k < NP_ROWS; ++k) {
-    // rows y-2 .. y+2 are v[k] .. v[k+4]: slide, then add the new bottom row
+    // rows y-PR .. y+PR are v[k] .. v[k+2PR]: slide, then add the new bottom row
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q + 1 < NR; ++q) {
       hm[q] = hm[q + 1];
       hx[q] = hx[q + 1];
     }
-    hmax(v[k + 4], hm[4], hx[4]);
+    hmax(v[k + 2 * PR], hm[NR - 1], hx[NR - 1]);
     const int y = y0 + k;
     // |c| == c for a positive candidate; a suppressed centre (-1e30) has |c| = 1e30 and passes here,
     // but klt_nm_verify re-reads the signed value and drops it
-    const float c = v[k + 2];
-    const float far = two ? fmaxf(hm[0], hm[4]) : 0.f;
-    const float others = fmaxf(fmaxf(fmaxf(hm[1], hm[3]), far), hx[2]);
+    const float c = v[k + PR];
+    float others = hx[PR];
+#pragma unroll
+    for (int q = 0; q < NR; ++q)
+      if (q != PR) others = fmaxf(others, hm[q]);
     if (colOK && (y < H) && (c > 0.f) && (c > others)) mine |= 1u << k;
   }
   // one atomic per warp: exclusive prefix of the per-lane counts, then every lane writes its own
