@@ -400,17 +400,23 @@ int run_tracker(cosl_klt* g) {
       if (++calls == 50) {
         cudaStreamSynchronize(g->stream);
         const int nw = g->fusedBlocks * KLT_FUSED_THREADS / 32;
-        std::vector<float> hs((size_t)nw * 8);
+        std::vector<float> hs((size_t)nw * 12);
         cudaMemcpy(hs.data(), g->d_state, sizeof(float) * hs.size(), cudaMemcpyDeviceToHost);
         double acc[6] = {0, 0, 0, 0, 0, 0}, mx = 0;
         unsigned s0 = ~0u, s1 = 0, e0 = ~0u, e1 = 0;
         for (int i = 0; i < nw; ++i) {
-          for (int k = 0; k < 6; ++k) acc[k] += hs[(size_t)i * 8 + k];
-          mx = std::max(mx, (double)hs[(size_t)i * 8 + 5]);
+          for (int k = 0; k < 6; ++k) acc[k] += hs[(size_t)i * 12 + k];
+          mx = std::max(mx, (double)hs[(size_t)i * 12 + 5]);
           unsigned a, b;
-          memcpy(&a, &hs[(size_t)i * 8 + 6], 4);
-          memcpy(&b, &hs[(size_t)i * 8 + 7], 4);
+          memcpy(&a, &hs[(size_t)i * 12 + 6], 4);
+          memcpy(&b, &hs[(size_t)i * 12 + 7], 4);
           s0 = std::min(s0, a); s1 = std::max(s1, a); e0 = std::min(e0, b); e1 = std::max(e1, b);
+        }
+        if (const char* dump = std::getenv("COSL_KLT_CLOCK_DUMP")) {
+          if (FILE* f = fopen(dump, "wb")) {
+            fwrite(hs.data(), sizeof(float), hs.size(), f);
+            fclose(f);
+          }
         }
         fprintf(stderr, "[klt clock] globaltimer ns: start spread %u, end spread %u, first start -> last end %u, last start -> first end %u\n", s1 - s0, e1 - e0, e1 - s0, e0 - s1);
         fprintf(stderr, "[klt clock] warps %d  mean cycles: poll %.0f  pre+stage %.0f  loop %.0f  finish %.0f  (stage-only %.0f)  total %.0f max %.0f\n", nw,

@@ -55,14 +55,14 @@ struct KltCentre {
 };
 
 __device__ __forceinline__ KltCentre klt_centre(int w, int h, float s, float t) {
-  float u = s * (float)w - 0.5f;
-  float v = t * (float)h - 0.5f;
+  float u = __fmaf_rn(s, (float)w, -0.5f);
+  float v = __fmaf_rn(t, (float)h, -0.5f);
   u = fminf(fmaxf(u, -2.0f), (float)w + 1.0f);
   v = fminf(fmaxf(v, -2.0f), (float)h + 1.0f);
   const float fu = floorf(u), fv = floorf(v);
   KltCentre p;
-  p.ax = u - fu;
-  p.ay = v - fv;
+  p.ax = __fsub_rn(u, fu);
+  p.ay = __fsub_rn(v, fv);
   p.xi = (int)fu;
   p.yi = (int)fv;
   return p;
@@ -446,12 +446,46 @@ klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
         KLT_CLK(c2k);
         KltAcc A = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         float f = f0;
+        // tile[b * KLT_TP + a] == level[clamp(ty0 + b)][clamp(tx0 + a)]: indexing with the
+        // unclamped tap coordinates reproduces the clamped fetches exactly
+        int a0 = c1.xi - tx0, b0 = c1.yi - ty0;
+        bool inTile = staged && (a0 - hw >= 0) && (a0 + hw + 1 < KLT_TW) && (b0 - hw >= 0) &&
+                      (b0 + hw + 1 < KLT_TW);
+        // A window that drifted out of its tile gets the tile re-centred (two batches of loads)
+        // rather than paying clamped global loads for the rest of the level; the slow warp would
+        // otherwise hold up every slot that waits on it.
+        if (staged && it != 1) {
+          const bool need = !pre_invalid && !inTile;
+          if (__any_sync(0xffffffffu, need)) {
+            if (need) {
+              const float4* L1 = pyr1 + (size_t)cam * pyrStride + LV.off[li];
+              tx0 = c1.xi - hw - 2;
+              ty0 = c1.yi - hw - 2;
+              constexpr int NLD = KLT_TW * KLT_TW / KLT_G / 2;
+#pragma unroll
+              for (int half = 0; half < 2; ++half) {
+                float4 tv[NLD];
+#pragma unroll
+                for (int u = 0; u < NLD; ++u) {
+                  const int i = gl + KLT_G * (u + half * NLD);
+                  const int b = i / KLT_TW, a = i - b * KLT_TW;
+                  tv[u] = __ldg(&L1[(size_t)clampi(ty0 + b, 0, h - 1) * w + clampi(tx0 + a, 0, w - 1)]);
+                }
+#pragma unroll
+                for (int u = 0; u < NLD; ++u) {
+                  const int i = gl + KLT_G * (u + half * NLD);
+                  const int b = i / KLT_TW, a = i - b * KLT_TW;
+                  tile[b * KLT_TP + a] = tv[u];
+                }
+              }
+              a0 = c1.xi - tx0;
+              b0 = c1.yi - ty0;
+              inTile = true;  // 2 * hw + 2 + 2 <= KLT_TW on the staged path
+            }
+            __syncwarp();
+          }
+        }
         if (!pre_invalid) {
-          // tile[b * KLT_TP + a] == level[clamp(ty0 + b)][clamp(tx0 + a)]: indexing with the
-          // unclamped tap coordinates reproduces the clamped fetches exactly
-          const int a0 = c1.xi - tx0, b0 = c1.yi - ty0;
-          const bool inTile = staged && (a0 - hw >= 0) && (a0 + hw + 1 < KLT_TW) && (b0 - hw >= 0) &&
-                              (b0 + hw + 1 < KLT_TW);
           if (inTile) {
             const float4* tc = tile + b0 * KLT_TP + a0;
 #pragma unroll
@@ -570,10 +604,14 @@ klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
 #if KLT_EXP_CLOCK
   if ((threadIdx.x & 31) == 0) {
     const int wg = (blockIdx.x * KLT_FUSED_THREADS + threadIdx.x) >> 5;
-    state[2 * wg] = make_float4((float)ck[0], (float)ck[1], (float)ck[2], (float)ck[3]);
     unsigned long long gt1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt1));
-    state[2 * wg + 1] = make_float4((float)ck[4], (float)(clock64() - ckStart), __uint_as_float((unsigned)(gt0 & 0xffffffffu)), __uint_as_float((unsigned)(gt1 & 0xffffffffu)));
+    unsigned smid, warpid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(warpid));
+    state[3 * wg] = make_float4((float)ck[0], (float)ck[1], (float)ck[2], (float)ck[3]);
+    state[3 * wg + 1] = make_float4((float)ck[4], (float)(clock64() - ckStart), __uint_as_float((unsigned)(gt0 & 0xffffffffu)), __uint_as_float((unsigned)(gt1 & 0xffffffffu)));
+    state[3 * wg + 2] = make_float4((float)smid, (float)warpid, (float)blockIdx.x, 0.f);
   }
 #endif
 }
