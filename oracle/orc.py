@@ -15,6 +15,22 @@ from coslam_b200.ctypes_defs import (COSL_BA_INFOSZ, FEAT_DTYPE, BaOptions, BaPr
 # libgomp spin-waiting fights with OpenBLAS' own worker threads (10x slowdowns measured)
 os.environ.setdefault("OMP_WAIT_POLICY", "passive")
 
+
+def _quota_threads():
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, -(-int(q) // int(per))))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+# OpenBLAS (dlopen'ed below for dpotrf) starts one worker per LOGICAL cpu unless told otherwise; on a
+# box with 128 cpus and a 16-cpu quota its idle workers alone eat the quota.
+os.environ.setdefault("OPENBLAS_NUM_THREADS", str(_quota_threads()))
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
