@@ -202,7 +202,8 @@ int dev_alloc(cudaStream_t st, T** p, size_t count) {
   return COSL_OK;
 }
 
-// worker threads for host-side index building: affinity and cgroup quota, at most 16
+// worker threads for host-side index building: affinity and cgroup quota (shared between the
+// local ranks), at most 16; COSLAM_B200_THREADS overrides
 static int host_threads() {
   static const int n = [] {
     int c = 1;
@@ -216,6 +217,15 @@ static int host_threads() {
         if (quota > 0) c = std::min<long long>(c, (quota + per - 1) / per);
       }
       std::fclose(f);
+    }
+    // several ranks on one host (torchrun exports LOCAL_WORLD_SIZE) share the quota
+    if (const char* lws = std::getenv("LOCAL_WORLD_SIZE")) {
+      const int n = std::atoi(lws);
+      if (n > 1) c = std::max(1, c / n);
+    }
+    if (const char* ov = std::getenv("COSLAM_B200_THREADS")) {
+      const int n = std::atoi(ov);
+      if (n >= 1) c = n;
     }
     return std::max(1, std::min(c, 16));
   }();

@@ -28,6 +28,12 @@ struct cosl_klt {
   cudaEvent_t evImg[64] = {};
   cudaEvent_t evFront = nullptr;
   bool imgPerCam = false, frontRecorded = false;
+  // the detector's prefilter needs only the cornerness map: on the re-detect path it runs on a side
+  // stream next to the coarse pyramid levels and the tracker (valid on the unsuppressed map: the
+  // suppression marks can only remove candidates, and klt_nm_verify reads the marked map)
+  cudaStream_t auxStream = nullptr;
+  cudaEvent_t evPre = nullptr;
+  bool earlyPrefilter = false, prefilterDone = false;
   // geometry
   int lvW[8], lvH[8];
   long long lvOff[8];
@@ -222,6 +228,8 @@ void free_group(cosl_klt* g) {
   cudaFree(g->d_res);
   cudaFree(g->d_present);
   cudaFree(g->d_nbr);
+  if (g->auxStream) cudaStreamDestroy(g->auxStream);
+  if (g->evPre) cudaEventDestroy(g->evPre);
   if (g->copyStream) cudaStreamDestroy(g->copyStream);
   if (g->evFront) cudaEventDestroy(g->evFront);
   for (int c = 0; c < 64; ++c)
@@ -260,6 +268,21 @@ int upload_images(cosl_klt* g, const uint8_t* const* imgs, size_t pitch, cudaMem
     COSL_CUDA(cudaMemcpy2DAsync(g->d_img + (size_t)c * g->imgStride, g->imgPitch, imgs[c], pitch,
                                 g->W, g->H, kind, g->stream));
   return COSL_OK;
+}
+
+// klt_nm_prefilter on `st` (prefilter radius = min(minDistance, 3))
+static void launch_prefilter(cosl_klt* g, cudaStream_t st) {
+  const int pr = std::min(std::max(1, g->cfg.minDistance), 3);
+  dim3 gp(div_up(g->W, 32 - 2 * pr), div_up(g->H, 8 * NP_ROWS), g->C);
+  if (pr == 3)
+    COSL_LAUNCH(klt_nm_prefilter<3>, gp, 256, 0, st, g->d_corn, g->W, g->H, g->d_prelim,
+                g->prelimCap, g->d_counters);
+  else if (pr == 2)
+    COSL_LAUNCH(klt_nm_prefilter<2>, gp, 256, 0, st, g->d_corn, g->W, g->H, g->d_prelim,
+                g->prelimCap, g->d_counters);
+  else
+    COSL_LAUNCH(klt_nm_prefilter<1>, gp, 256, 0, st, g->d_corn, g->W, g->H, g->d_prelim,
+                g->prelimCap, g->d_counters);
 }
 
 // PyramidWithDerivativesCreator::buildPyramidForGrayscaleImage (v3d_gpupyramid.cpp:366-429)
@@ -306,6 +329,12 @@ int build_pyramid(cosl_klt* g, bool wantCorn) {
   if (g->evFront) {
     COSL_CUDA(cudaEventRecord(g->evFront, g->stream));
     g->frontRecorded = true;
+  }
+  if (g->earlyPrefilter && wantCorn && g->auxStream && g->evFront && g->evPre) {
+    COSL_CUDA(cudaStreamWaitEvent(g->auxStream, g->evFront, 0));
+    launch_prefilter(g, g->auxStream);
+    COSL_CUDA(cudaEventRecord(g->evPre, g->auxStream));
+    g->prefilterDone = true;
   }
   g->cornValid = wantCorn;
   for (int l = 2; l < g->L; ++l) {
@@ -503,18 +532,11 @@ int run_detector(cosl_klt* g, int mode, int nPresentExt) {
                 g->W, g->H);
   }
   const int r = std::max(1, g->cfg.minDistance);
-  {
-    const int pr = std::min(r, 3);
-    dim3 gp(div_up(g->W, 32 - 2 * pr), div_up(g->H, 8 * NP_ROWS), g->C);
-    if (pr == 3)
-      COSL_LAUNCH(klt_nm_prefilter<3>, gp, 256, 0, g->stream, g->d_corn, g->W, g->H, g->d_prelim,
-                  g->prelimCap, g->d_counters);
-    else if (pr == 2)
-      COSL_LAUNCH(klt_nm_prefilter<2>, gp, 256, 0, g->stream, g->d_corn, g->W, g->H, g->d_prelim,
-                  g->prelimCap, g->d_counters);
-    else
-      COSL_LAUNCH(klt_nm_prefilter<1>, gp, 256, 0, g->stream, g->d_corn, g->W, g->H, g->d_prelim,
-                  g->prelimCap, g->d_counters);
+  if (g->prefilterDone) {
+    g->prefilterDone = false;
+    COSL_CUDA(cudaStreamWaitEvent(g->stream, g->evPre, 0));
+  } else {
+    launch_prefilter(g, g->stream);
   }
   dim3 gv(2 * g->numSM, g->C);
   COSL_LAUNCH(klt_nm_verify, gv, 256, 0, g->stream, g->d_corn, g->W, g->H, r, g->d_prelim,
@@ -553,8 +575,8 @@ int advance(cosl_klt* g) {
 }
 
 int do_track(cosl_klt* g, bool wantCorn = false) {
+  COSL_TRY(zero_counters(g));  // before the front pass: the early prefilter counts into them
   COSL_TRY(build_pyramid(g, wantCorn));
-  COSL_TRY(zero_counters(g));
   g->statusDone = g->suppressDone = false;
   g->wantTail = true;  // the persistent gain tracker writes the feature table itself
   COSL_TRY(run_tracker(g));
@@ -564,7 +586,10 @@ int do_track(cosl_klt* g, bool wantCorn = false) {
 }
 
 int do_redetect(cosl_klt* g) {
-  COSL_TRY(do_track(g, true));
+  g->earlyPrefilter = true;
+  const int rcTrack = do_track(g, true);
+  g->earlyPrefilter = false;
+  if (rcTrack != COSL_OK) return rcTrack;
   COSL_TRY(run_detector(g, 1, 0));
   return COSL_OK;
 }
@@ -655,6 +680,11 @@ int cosl_klt_group_create(const cosl_klt_config* cfg, int nCams, int width, int 
     }
   } else {
     g->copyStream = nullptr;
+  }
+  if (cudaStreamCreateWithFlags(&g->auxStream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&g->evPre, cudaEventDisableTiming) != cudaSuccess) {
+    if (g->auxStream) cudaStreamDestroy(g->auxStream);
+    g->auxStream = nullptr;
   }
   int rc = alloc_group(g);
   if (rc != COSL_OK) {
