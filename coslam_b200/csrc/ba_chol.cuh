@@ -100,6 +100,7 @@ ba_chol_small(double* __restrict__ S, int ld, int ns, double* __restrict__ xout,
 // accuracy for d inside the float range, which Gauss-Newton diagonals always are).  The library
 // rsqrt() is ~3x longer, and this value sits on the pivot-to-pivot critical path of the whole solve.
 __device__ __forceinline__ double ba_rsqrt(double d) {
+  if (d < 1e-30 || d > 1e30) return rsqrt(d);  // outside the float range of the seed
   double y = (double)rsqrtf((float)d);
   const double h = 0.5 * d;
   y = __fma_rn(y, __fma_rn(-h * y, y, 0.5), y);

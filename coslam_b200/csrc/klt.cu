@@ -256,9 +256,14 @@ int upload_images(cosl_klt* g, const uint8_t* const* imgs, size_t pitch, cudaMem
   if (kind == cudaMemcpyHostToDevice && g->C > 1 && g->copyStream) {
     // the previous frame's front pass must have consumed d_img before it is overwritten
     if (g->frontRecorded) COSL_CUDA(cudaStreamWaitEvent(g->copyStream, g->evFront, 0));
+    const bool flat = (pitch == (size_t)g->W) && (g->imgPitch == (size_t)g->W);  // one contiguous block
     for (int c = 0; c < g->C; ++c) {
-      COSL_CUDA(cudaMemcpy2DAsync(g->d_img + (size_t)c * g->imgStride, g->imgPitch, imgs[c], pitch,
-                                  g->W, g->H, kind, g->copyStream));
+      if (flat)
+        COSL_CUDA(cudaMemcpyAsync(g->d_img + (size_t)c * g->imgStride, imgs[c], (size_t)g->W * g->H,
+                                  kind, g->copyStream));
+      else
+        COSL_CUDA(cudaMemcpy2DAsync(g->d_img + (size_t)c * g->imgStride, g->imgPitch, imgs[c],
+                                    pitch, g->W, g->H, kind, g->copyStream));
       COSL_CUDA(cudaEventRecord(g->evImg[c], g->copyStream));
     }
     g->imgPerCam = true;
