@@ -323,6 +323,35 @@ def run_cuda(args):
     clk = clocks.stop()  # sampled across the device-resident, profiled and end-to-end regions
     barrier()
     klt_value = world * KLT_C * F * K / (ms_val * 1e-3)
+    # ---- the same frame with the plain 2x2 tracker (north_star's kernel; CoSLAM's live default is
+    # the 3x3 gain tracker measured above): device-resident frames, value only
+    klt2 = None
+    if rank == 0:
+        from coslam_b200.ctypes_defs import KltConfig
+        g2 = api.KltGroup(KltConfig.coslam_live(with_gain=False), KLT_C, KLT_W, KLT_H, KLT_L, KLT_FW,
+                          KLT_FH, device=local)
+        s2 = torch.cuda.ExternalStream(g2.stream(), device=local)
+        g2.first([host[0][c].numpy() for c in range(KLT_C)])
+        j = 1
+        for _ in range(Wm):
+            g2.next_dev([t.data_ptr() for t in dev[fidx(j)]], KLT_W)
+            j += 1
+        g2.sync()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(s2)
+        for _ in range(K):
+            g2.next_dev([t.data_ptr() for t in dev[fidx(j)]], KLT_W)
+            j += 1
+        a1.record(s2)
+        g2.sync()
+        ms2 = a0.elapsed_time(a1)
+        f2, _ = g2.fetch()
+        klt2 = {"metric": "klt_features_per_s", "value": KLT_C * F * K / (ms2 * 1e-3),
+                "unit": "features/s", "ms_per_step": ms2 / K,
+                "tracked_fraction": float(np.mean([(f2[c]["status"] == 0).mean() for c in range(KLT_C)])),
+                "config": {"workload": "c3 with trackWithGain = false (2x2 LK, levels 5/3/1 x 5 iterations: the "
+                                       "reference build always runs 5, v3d_gpuklt.cpp quirk kept), frames resident in HBM"}}
+        g2.close()
     klt_e2e = world * KLT_C * F * K / (ms_e2e * 1e-3)
 
     # ------------------------------------------------------------------ pose (latency, rank 0)
@@ -385,6 +414,8 @@ def run_cuda(args):
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if klt2 is not None:
+            line["klt_2x2"] = klt2
         if ba is not None:
             line["ba"] = ba
         if pose is not None:
