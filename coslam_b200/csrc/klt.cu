@@ -496,8 +496,17 @@ int run_tracker(cosl_klt* g) {
       ++LV.n;
     }
     const int nIter = (g->cfg.compat & COSL_KLT_COMPAT_ITER5) ? 5 : g->cfg.nIterations;
-    COSL_LAUNCH(klt_track_2x2, grid, wpb * 32, 0, g->stream, P0, P1, g->pyrStride, LV, g->d_src,
-                g->d_res, track_params(g, true), nIter);
+    const int hw2 = g->halfWidth, npx2 = (2 * hw2 + 1) * (2 * hw2 + 1);
+    const bool tiled = (npx2 <= KLT_G * KLT_ROUNDS) && (2 * hw2 + 4 <= KLT_TW) && (2 * hw2 + 2 <= 8) &&
+                       !(g->cfg.compat & COSL_KLT_PASS_KERNELS);
+    if (tiled) {
+      dim3 gt(div_up(g->F, 16), g->C);
+      COSL_LAUNCH(klt_track_2x2_tiled, gt, 128, 0, g->stream, P0, P1, g->pyrStride, LV, g->d_src,
+                  g->d_res, track_params(g, true), nIter);
+    } else {
+      COSL_LAUNCH(klt_track_2x2, grid, wpb * 32, 0, g->stream, P0, P1, g->pyrStride, LV, g->d_src,
+                  g->d_res, track_params(g, true), nIter);
+    }
   }
   g->timer.end(g->stream);
   COSL_CUDA(cudaGetLastError());

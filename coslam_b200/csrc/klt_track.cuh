@@ -617,3 +617,184 @@ klt_gain_fused(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
 }
 
 }  // namespace coslam
+
+namespace coslam {
+
+// ------------------------------------------------------------------------------------------
+// 2x2 LK (klt_tracker.cg:35-131, host loop v3d_gpuklt.cpp:99-161) with the memory structure of
+// klt_gain_fused: 8 lanes per slot, per level the I0 samples in registers and a 12x12 tile of the
+// current frame in shared memory (re-centred if the window leaves it).  Slots do not interact, so
+// this is a plain launch: grid = (ceil(F / 16), cameras), 128 threads.  Same control flow as
+// klt_track_2x2 (thresholds from the last iteration of every level, validity region at the end);
+// used when the window fits the tile (hw <= 3), klt_track_2x2 otherwise.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+klt_track_2x2_tiled(const float4* __restrict__ pyr0, const float4* __restrict__ pyr1,
+                    long long pyrStride, KltLevels LV, const float4* __restrict__ X0buf,
+                    float4* __restrict__ out, KltTrackParams P, int nIter) {
+  __shared__ float4 s_tile[16][KLT_TW * KLT_TP];
+  const int gl = threadIdx.x & (KLT_G - 1);
+  const int grp = threadIdx.x / KLT_G;
+  const int cam = blockIdx.y;
+  int slot = blockIdx.x * 16 + grp;
+  const bool active = slot < P.F;
+  if (!active) slot = P.F - 1;  // keep the warp complete for the shuffles
+  float4* tile = s_tile[grp];
+  const size_t fb = (size_t)cam * P.F;
+  const float4 x0 = X0buf[fb + slot];
+  float X1x = x0.x, X1y = x0.y;
+  bool invalid = (x0.x < 0.f);
+  const bool dead = invalid;  // no samples are fetched for a dead slot
+  const int hw = P.halfWidth, fwid = 2 * hw + 1, npx = fwid * fwid;
+  const float halfW = 0.5f * (float)P.W, halfH = 0.5f * (float)P.H;
+  int toff[KLT_ROUNDS];
+#pragma unroll
+  for (int r = 0; r < KLT_ROUNDS; ++r) {
+    const int p = min(gl + KLT_G * r, npx - 1);
+    const int py = p / fwid, px = p - py * fwid;
+    toff[r] = (py - hw) * KLT_TP + (px - hw);
+  }
+  float3 I0r[KLT_ROUNDS];
+  float sqrLen = 0.f, ssd = 0.f;
+  for (int li = 0; li < LV.n; ++li) {
+    const int w = LV.w[li], h = LV.h[li];
+    const float4* L0 = pyr0 + (size_t)cam * pyrStride + LV.off[li];
+    const float4* L1 = pyr1 + (size_t)cam * pyrStride + LV.off[li];
+    constexpr int NLD = KLT_TW * KLT_TW / KLT_G / 2;
+    constexpr int I0B = (KLT_TW / 2) * KLT_TP;
+    int tx0, ty0;
+    {
+      // ---- staging, as in klt_gain_fused: I0 block + upper tile half, I0 samples, lower tile half
+      const KltCentre c0 = klt_centre(w, h, x0.x, x0.y);
+      const KltCentre c1 = klt_centre(w, h, X1x, X1y);
+      tx0 = c1.xi - hw - 2;
+      ty0 = c1.yi - hw - 2;
+      if (!dead) {
+        float4 t0[8], tv[NLD];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          t0[u] = __ldg(&L0[(size_t)clampi(c0.yi - hw + u, 0, h - 1) * w + clampi(c0.xi - hw + gl, 0, w - 1)]);
+#pragma unroll
+        for (int u = 0; u < NLD; ++u) {
+          const int i = gl + KLT_G * u;
+          const int b = i / KLT_TW, a = i - b * KLT_TW;
+          tv[u] = __ldg(&L1[(size_t)clampi(ty0 + b, 0, h - 1) * w + clampi(tx0 + a, 0, w - 1)]);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) tile[I0B + u * 8 + gl] = t0[u];
+#pragma unroll
+        for (int u = 0; u < NLD; ++u) {
+          const int i = gl + KLT_G * u;
+          const int b = i / KLT_TW, a = i - b * KLT_TW;
+          tile[b * KLT_TP + a] = tv[u];
+        }
+      }
+      __syncwarp();
+      if (!dead) {
+#pragma unroll
+        for (int r = 0; r < KLT_ROUNDS; ++r) {
+          const int p = gl + KLT_G * r;
+          if (p < npx) {
+            const int py = p / fwid, px = p - py * fwid;
+            const float4* t4 = tile + I0B + py * 8 + px;
+            I0r[r] = klt_lerp4(t4[0], t4[1], t4[8], t4[9], c0.ax, c0.ay);
+          } else {
+            I0r[r] = make_float3(0.f, 0.f, 0.f);
+          }
+        }
+      }
+      __syncwarp();
+      if (!dead) {
+        float4 tw[NLD];
+#pragma unroll
+        for (int u = 0; u < NLD; ++u) {
+          const int i = gl + KLT_G * (u + NLD);
+          const int b = i / KLT_TW, a = i - b * KLT_TW;
+          tw[u] = __ldg(&L1[(size_t)clampi(ty0 + b, 0, h - 1) * w + clampi(tx0 + a, 0, w - 1)]);
+        }
+#pragma unroll
+        for (int u = 0; u < NLD; ++u) {
+          const int i = gl + KLT_G * (u + NLD);
+          const int b = i / KLT_TW, a = i - b * KLT_TW;
+          tile[b * KLT_TP + a] = tw[u];
+        }
+      }
+      __syncwarp();
+    }
+    for (int it = 0; it < nIter; ++it) {
+      const KltCentre c1 = klt_centre(w, h, X1x, X1y);
+      int a0 = c1.xi - tx0, b0 = c1.yi - ty0;
+      const bool inTile = (a0 - hw >= 0) && (a0 + hw + 1 < KLT_TW) && (b0 - hw >= 0) && (b0 + hw + 1 < KLT_TW);
+      const bool need = !dead && !inTile;
+      if (__any_sync(0xffffffffu, need)) {  // re-centre the tile (warp-uniform branch)
+        if (need) {
+          tx0 = c1.xi - hw - 2;
+          ty0 = c1.yi - hw - 2;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float4 tv[NLD];
+#pragma unroll
+            for (int u = 0; u < NLD; ++u) {
+              const int i = gl + KLT_G * (u + half * NLD);
+              const int b = i / KLT_TW, a = i - b * KLT_TW;
+              tv[u] = __ldg(&L1[(size_t)clampi(ty0 + b, 0, h - 1) * w + clampi(tx0 + a, 0, w - 1)]);
+            }
+#pragma unroll
+            for (int u = 0; u < NLD; ++u) {
+              const int i = gl + KLT_G * (u + half * NLD);
+              const int b = i / KLT_TW, a = i - b * KLT_TW;
+              tile[b * KLT_TP + a] = tv[u];
+            }
+          }
+          a0 = c1.xi - tx0;
+          b0 = c1.yi - ty0;
+        }
+        __syncwarp();
+      }
+      float a = 0.f, b = 0.f, c = 0.f, r0 = 0.f, r1 = 0.f, sd = 0.f;
+      if (!dead) {
+        const float4* tc = tile + b0 * KLT_TP + a0;
+#pragma unroll
+        for (int r = 0; r < KLT_ROUNDS; ++r) {
+          if (gl + KLT_G * r < npx) {
+            const float4* t4 = tc + toff[r];
+            const float3 I1 = klt_lerp4(t4[0], t4[1], t4[KLT_TP], t4[KLT_TP + 1], c1.ax, c1.ay);
+            const float3 I0 = I0r[r];
+            const float e = __fsub_rn(I0.x, I1.x);
+            const float Jx = __fmul_rn(__fadd_rn(I0.y, I1.y), halfW);
+            const float Jy = __fmul_rn(__fadd_rn(I0.z, I1.z), halfH);
+            a = __fmaf_rn(Jx, Jx, a);
+            b = __fmaf_rn(Jx, Jy, b);
+            c = __fmaf_rn(Jy, Jy, c);
+            r0 = __fmaf_rn(e, Jx, r0);
+            r1 = __fmaf_rn(e, Jy, r1);
+            sd = __fmaf_rn(e, e, sd);
+          }
+        }
+      }
+      a = grp_sum(a);
+      b = grp_sum(b);
+      c = grp_sum(c);
+      r0 = grp_sum(r0);
+      r1 = grp_sum(r1);
+      ssd = grp_sum(sd);
+      const float det = __fmaf_rn(a, c, -__fmul_rn(b, b));
+      invalid = invalid || (det < 0.00001f);
+      const float rdet = __fdividef(1.0f, det);
+      float ux = __fmul_rn(rdet, __fmaf_rn(c, r0, -__fmul_rn(b, r1)));
+      float uy = __fmul_rn(rdet, __fmaf_rn(a, r1, -__fmul_rn(b, r0)));
+      X1x = __fadd_rn(X1x, ux);
+      X1y = __fadd_rn(X1y, uy);
+      ux = __fmul_rn(ux, (float)P.W);
+      uy = __fmul_rn(uy, (float)P.H);
+      sqrLen = __fmaf_rn(ux, ux, __fmul_rn(uy, uy));
+    }
+    invalid = invalid || (sqrLen > P.sqrConv);
+    invalid = invalid || (ssd > P.ssdThr);
+  }
+  invalid = invalid || (X1x < P.vr0 || X1y < P.vr1) || (X1x > P.vr2 || X1y > P.vr3);
+  if (gl == 0 && active)
+    out[fb + slot] = invalid ? make_float4(-1.f, -1.f, -1.f, 0.f) : make_float4(X1x, X1y, x0.x, 0.f);
+}
+
+}  // namespace coslam

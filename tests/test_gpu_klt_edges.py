@@ -113,3 +113,27 @@ def test_fused_tracker_with_more_slots_than_resident_groups(api):
         fb, nb = b.next([q.frames[k] for q in s])
         assert np.array_equal(na, nb) and fa.tobytes() == fb.tobytes(), f"frame {k}"
         assert (fa["status"] == 0).sum() > 1500
+
+
+def test_tiled_2x2_tracker_matches_the_plain_kernel(api, orc):
+    """klt_track_2x2_tiled (shared-memory tile, 8 lanes per slot) against klt_track_2x2 (selected by
+    the PASS_KERNELS compat bit) and against the oracle: same tolerance as every LK parity test."""
+    W, H = 640, 480
+    s = seq(H, W, 77, n=4)
+    cfg_t = live_cfg(gain=False, min_corner=1200.0)
+    cfg_p = live_cfg(gain=False, min_corner=1200.0)
+    cfg_p.compat |= 2
+    a = api.KltTracker(cfg_t, W, H, 6, 32, 32)
+    b = api.KltTracker(cfg_p, W, H, 6, 32, 32)
+    o = orc.OracleKlt(cfg_t, W, H, 6, 32, 32)
+    fa, na = a.first(s.frames[0])
+    fb, nb = b.first(s.frames[0])
+    fo, no = o.first(s.frames[0])
+    assert na == nb == no and fa.tobytes() == fb.tobytes()
+    for k in range(1, 4):
+        fa, na = a.next(s.frames[k])
+        fb, nb = b.next(s.frames[k])
+        fo, no = o.next(s.frames[k])
+        compare_features(fb, fa, W, H)
+        compare_features(fo, fa, W, H)
+        assert (fa["status"] == 0).sum() > 500
