@@ -303,6 +303,16 @@ def run_cuda(args):
             "frame_total": {"algorithmic_bytes": grp.algorithmic_bytes(),
                             "achieved": grp.algorithmic_bytes() / (ms_val / K * 1e-3) / 1e9,
                             "frac": grp.algorithmic_bytes() / (ms_val / K * 1e-3) / 1e9 / hbm_peak}}
+    # SURVEY 8(d) lists the LK solve as FP32-SIMT co-bound: 123 kflop per feature (70 w^2 flops per
+    # window evaluation, 36 evaluations).  No measured fp32 peak exists in MEASURED_PEAKS.json, so the
+    # denominator is the nominal 148 SMs x 128 FMA lanes x 2 flop at 1.965 GHz, labelled as such.
+    if top == "klt_track":
+        lk_flops = 123.0e3 * KLT_C * F
+        fp32_nominal = 148 * 128 * 2 * 1.965e9 / 1e12
+        roof["fp32_co_bound"] = {"algorithmic_flops_per_step": lk_flops,
+                                 "achieved_tflops": lk_flops / (top_ms * 1e-3) / 1e12,
+                                 "peak_tflops": fp32_nominal, "peak_source": "nominal",
+                                 "frac": lk_flops / (top_ms * 1e-3) / 1e12 / fp32_nominal}
     # ---- e2e: host buffers through the public C-ABI call, H2D + D2H inside the timed region
     host_np = [[h.numpy() for h in row] for row in host]
     host_args = [grp.host_ptrs(row) for row in host_np]  # pointer arrays built once per frame
