@@ -86,3 +86,21 @@ def test_bad_arguments_return_error_codes():
     assert rc == -1 and b"geometry" in api.LIB.cosl_last_error()
     assert api.LIB.cosl_klt_advance(None) == -1
     assert api.LIB.cosl_ba_solver_run(None, None) == -1
+
+
+def test_product_tree_does_not_reach_into_the_oracle():
+    """oracle/ is test infrastructure: nothing under coslam_b200/ may import, include or load it,
+    and the shared library must not be linked against it."""
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r"^\s*(#\s*include\s*[\"<][^\">]*oracle|from\s+oracle|import\s+oracle|.*liboracle)",
+                     re.M)
+    for dirpath, _, files in os.walk(os.path.join(root, "coslam_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert not pat.search(text), os.path.join(dirpath, f)
+    lib = os.path.join(root, "coslam_b200", "libcoslam_b200.so")
+    deps = subprocess.run(["ldd", lib], capture_output=True, text=True).stdout
+    assert "oracle" not in deps
