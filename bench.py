@@ -443,7 +443,7 @@ def cpu_baseline_klt(cfg, seqs):
     trk = [orc.OracleKlt(cfg, KLT_W, KLT_H, KLT_L, KLT_FW, KLT_FH) for _ in range(KLT_C)]
     for c in range(KLT_C):
         trk[c].first(seqs[c].frame(0))
-    nfr = 6
+    nfr = 16  # ~1 s of wall time on 16 threads (~15 core-seconds)
     t0 = time.perf_counter()
     for k in range(1, 1 + nfr):
         for c in range(KLT_C):
