@@ -32,3 +32,15 @@ def test_shims_run_on_gpu(tmp_path):
     out = subprocess.run([exe, "run"], capture_output=True, text=True)
     assert out.returncode == 0, f"rc={out.returncode}\n{out.stdout}{out.stderr}"
     assert "klt:" in out.stdout and "pose: ok 1" in out.stdout and "ba:" in out.stdout
+
+
+def test_ba_shim_host_logic_with_a_mock_abi(tmp_path):
+    """CPU: bundleAdjustRobust's flattening (CSR by point), option forwarding, write-back of R/t/X
+    and outlier flags, and the exception on failure -- against a mock of the C-ABI."""
+    exe = os.path.join(str(tmp_path), "mock_ba_shim")
+    src = os.path.join(ROOT, "tests", "stubs", "mock_ba_shim.cpp")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-I", os.path.join(ROOT, "tests", "stubs"),
+                           "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(ROOT, "coslam_b200", "shim"), src, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "MOCK_BA_SHIM_OK" in out.stdout, out.stdout + out.stderr
