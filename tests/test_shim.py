@@ -44,3 +44,14 @@ def test_ba_shim_host_logic_with_a_mock_abi(tmp_path):
                            "-I", os.path.join(ROOT, "coslam_b200", "shim"), src, "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and "MOCK_BA_SHIM_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_klt_shim_host_logic_with_a_mock_abi(tmp_path):
+    """CPU: V3D_GPU::KLT_SequenceTracker forwards configuration, geometry, image pitch, feature
+    buffers and counts to the C-ABI exactly as the reference's class receives them."""
+    exe = os.path.join(str(tmp_path), "mock_klt_shim")
+    src = os.path.join(ROOT, "tests", "stubs", "mock_klt_shim.cpp")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(ROOT, "coslam_b200", "shim"), src, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "MOCK_KLT_SHIM_OK" in out.stdout, out.stdout + out.stderr
