@@ -55,3 +55,14 @@ def test_klt_shim_host_logic_with_a_mock_abi(tmp_path):
                            "-I", os.path.join(ROOT, "coslam_b200", "shim"), src, "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and "MOCK_KLT_SHIM_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_pose_shim_host_logic_with_a_mock_abi(tmp_path):
+    """CPU: intraCamEstimate forwards the option fields, copies the diagnostics back and maps the
+    two failure modes to `false`."""
+    exe = os.path.join(str(tmp_path), "mock_pose_shim")
+    src = os.path.join(ROOT, "tests", "stubs", "mock_pose_shim.cpp")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(ROOT, "coslam_b200", "shim"), src, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "MOCK_POSE_SHIM_OK" in out.stdout, out.stdout + out.stderr
