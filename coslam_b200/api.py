@@ -80,6 +80,8 @@ def _load():
     L.cosl_ba_solver_timer.restype = C.c_char_p
     L.cosl_ba_solver_profile_enable.argtypes = [vp, ci]
     L.cosl_ba_solver_stats.argtypes = [vp, C.POINTER(cd)]
+    L.cosl_ba_solver_plan_info.argtypes = [vp, pint]
+    L.cosl_ba_solver_trace.argtypes = [vp, ci, vp, vp, ci]
     return L
 
 
@@ -387,8 +389,27 @@ class BaSolver:
     def stats(self):
         out = (C.c_double * 8)()
         _ck(LIB.cosl_ba_solver_stats(self.h, out))
-        return {"ns": int(out[0]), "envelope_doubles": out[1], "factor_flops": out[2],
-                "pair_entries": out[3], "pair_items": out[4]}
+        return {"ns": int(out[0]), "reduce_doubles": out[1], "factor_flops": out[2],
+                "pair_entries": out[3], "pair_items": out[4], "blocks": int(out[5]),
+                "tiles": int(out[6]), "tasks": int(out[7])}
+
+    def plan_info(self):
+        out = (C.c_int * 8)()
+        _ck(LIB.cosl_ba_solver_plan_info(self.h, out))
+        keys = ("blocks", "tiles_schur", "tiles", "tasks", "nd_depth", "critical_tasks", "grid",
+                "small_solve")
+        return dict(zip(keys, [int(v) for v in out]))
+
+    def trace_arm(self):
+        return int(LIB.cosl_ba_solver_trace(self.h, 1, None, None, 0))
+
+    def trace_get(self):
+        """Timeline of the last persistent solve: (times [n,4] uint64, meta [n,3] int32)."""
+        n = self.plan_info()["tasks"]
+        tm = np.zeros((n, 4), np.uint64)
+        meta = np.zeros((n, 3), np.int32)
+        LIB.cosl_ba_solver_trace(self.h, 0, _ptr(tm), _ptr(meta), n)
+        return tm, meta
 
     def profile_enable(self, on=True):
         _ck(LIB.cosl_ba_solver_profile_enable(self.h, 1 if on else 0))

@@ -20,7 +20,7 @@
 #include <vector>
 
 #include "ba_kernels.cuh"
-#include "ba_chol.cuh"
+#include "ba_tile.cuh"
 #include "common.cuh"
 
 using namespace coslam;
@@ -30,7 +30,7 @@ namespace {
 
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
-enum { ncclSum = 0, ncclMax = 2, ncclFloat64 = 8 };
+enum { ncclSum = 0, ncclMax = 2, ncclUint8 = 1, ncclFloat64 = 8 };
 
 struct NcclApi {
   void* handle = nullptr;
@@ -90,15 +90,20 @@ struct cosl_ba_solver {
   long long* d_ptr = nullptr;
   double *d_W = nullptr, *d_V = nullptr, *d_eb = nullptr;
   double* d_Uea = nullptr;   // [U (m x 21) | ea (m x 6)] contiguous for one all-reduce
-  double* d_Srhs = nullptr;  // (ns+1) x ns trapezoid [S ; rhs^T], leading dimension ld, one all-reduce
-  int ld = 0, nb = 0;
-  double *d_y = nullptr, *d_x = nullptr;
-  double* d_Linv = nullptr;   // [nb][64*64] inverses of the diagonal Cholesky blocks
-  int* d_firstBlk = nullptr;
-  int* d_rowEnd = nullptr;        // [nb] end row (exclusive) of block column J's envelope
-  long long* d_envOff = nullptr;  // [nb + 1] packed offsets for the enveloped all-reduce
-  double* d_envBuf = nullptr;
-  long long envCount = 0;
+  // reduced camera system: [rhs (nb*64) | tiles]; the leading part [rhs | Schur-structure tiles]
+  // is the payload of the one all-reduce per LM trial (ba_tile.cuh)
+  BaPlan plan;
+  double* d_S = nullptr;
+  long long reduceCount = 0;  // doubles in the all-reduce payload
+  double *d_Linv = nullptr, *d_y = nullptr, *d_x = nullptr;
+  int* d_cnt = nullptr;
+  BaTask* d_tasks = nullptr;
+  BaBwdEntry* d_bwd = nullptr;
+  int *d_blkRows = nullptr, *d_blkRow0 = nullptr, *d_tileIdx = nullptr, *d_diagBlk = nullptr,
+      *d_blkCam0 = nullptr, *d_order = nullptr, *d_solIdx = nullptr;
+  BaTileDev td;
+  unsigned long long* d_trace = nullptr;
+  int solveGrid = 1;
   double factorFlops = 0.0;
   double* d_sc = nullptr;
   unsigned char* d_outlier = nullptr;
@@ -108,12 +113,6 @@ struct cosl_ba_solver {
   long long nEntries = 0;
   double* h_sc = nullptr;  // pinned
   bool smallSolve = true;
-  // block envelope (skyline) of the reduced camera system for the blocked factorisation: block row
-  // I has its first structurally non-zero block column at firstBlk[I]; panel k only touches block
-  // rows (k, lastBlk[k]].  Dense co-visibility gives firstBlk == 0 everywhere (== dense algorithm).
-  std::vector<int> firstBlk, lastBlk;
-  cudaGraphExec_t solveGraph = nullptr;
-  int solveGraphNodes = 0;
   SectionTimer timer;
   int secLin = 0, secSchur = 0, secSolve = 0, secBack = 0, secCost = 0, secComm = 0;
   // statistics
@@ -266,10 +265,10 @@ void free_solver(cosl_ba_solver* s) {
   s->timer.destroy();
   void* bufs[] = {s->d_camK, s->d_camR0, s->d_pa, s->d_na, s->d_dpa, s->d_pb, s->d_nb, s->d_dpb,
                   s->d_cam, s->d_pt, s->d_cobs, s->d_ccam, s->d_xy, s->d_wgt, s->d_ptr, s->d_W,
-                  s->d_V, s->d_eb, s->d_Uea, s->d_Srhs, s->d_y, s->d_x, s->d_sc, s->d_outlier,
-                  s->d_items, s->d_entries, s->d_Linv, s->d_firstBlk, s->d_rowEnd, s->d_envOff,
-                  s->d_envBuf};
-  if (s->solveGraph) cudaGraphExecDestroy(s->solveGraph);
+                  s->d_V, s->d_eb, s->d_Uea, s->d_S, s->d_y, s->d_x, s->d_sc, s->d_outlier,
+                  s->d_items, s->d_entries, s->d_Linv, s->d_cnt, s->d_tasks, s->d_bwd, s->d_blkRows,
+                  s->d_blkRow0, s->d_tileIdx, s->d_diagBlk, s->d_blkCam0, s->d_order, s->d_solIdx,
+                  s->d_trace};
   for (void* b : bufs)
     if (b) cudaFreeAsync(b, s->stream);
   if (s->stream) cudaStreamSynchronize(s->stream);
@@ -361,15 +360,52 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   s->nEntries = nEntries;
   if (ba_timing()) std::fprintf(stderr, "[ba timing] pair lists %.1f ms (%lld entries, %d threads)\n",
                                 1e3 * (now_s() - tPair0), nEntries, host_threads());
+  // camera co-visibility -> plan of the reduced-system solve (ordering, tiles, task DAG).  In the
+  // multi-GPU case every rank must derive the SAME structure although it only sees the pairs of
+  // its own point shard: the presence bitmap is all-reduced (max) first.
+  std::vector<uint8_t> adj((size_t)mf * mf, 0);
+  for (int ja = 0; ja < mf; ++ja)
+    for (int jb = ja; jb < mf; ++jb)
+      if (pcount[(size_t)ja * mf + jb + 1] > pcount[(size_t)ja * mf + jb])
+        adj[(size_t)ja * mf + jb] = adj[(size_t)jb * mf + ja] = 1;
+  if (s->comm && s->comm->nranks > 1 && mf > 0) {
+    uint8_t* d_adj = nullptr;
+    COSL_TRY(dev_alloc(s->stream, &d_adj, adj.size()));
+    COSL_CUDA(cudaMemcpyAsync(d_adj, adj.data(), adj.size(), cudaMemcpyHostToDevice, s->stream));
+    const int rc = nccl().AllReduce(d_adj, d_adj, adj.size(), ncclUint8, ncclMax, s->comm->comm, s->stream);
+    if (rc != 0) return set_error(COSL_E_NCCL, "ncclAllReduce (co-visibility) failed (%d)", rc);
+    COSL_CUDA(cudaMemcpyAsync(adj.data(), d_adj, adj.size(), cudaMemcpyDeviceToHost, s->stream));
+    COSL_CUDA(cudaStreamSynchronize(s->stream));
+    COSL_CUDA(cudaFreeAsync(d_adj, s->stream));
+  }
+  {
+    int ndDepth = -1;
+    if (const char* e = std::getenv("COSL_BA_ND_DEPTH")) ndDepth = std::atoi(e);
+    s->plan = ba_make_plan(mf, adj, ndDepth);
+    if (s->plan.nb < 0) return set_error(COSL_E_INVALID, "solve plan: dependency cycle (internal error)");
+  }
+  const BaPlan& P = s->plan;
   std::vector<BaPairItem> items;
   const int chunk = 512;
   for (int ja = 0; ja < mf; ++ja)
     for (int jb = ja; jb < mf; ++jb) {
       const long long b0 = pcount[(size_t)ja * mf + jb], b1 = pcount[(size_t)ja * mf + jb + 1];
+      if (b1 == b0) continue;
+      BaPairItem it;
+      std::memset(&it, 0, sizeof(it));
+      it.rowCam = ja;
+      it.colCam = jb;
+      // lower triangle of the permuted system: the later camera (block, offset) gives the row
+      const int bA = P.camBlk[ja], oA = P.camOff[ja], bB = P.camBlk[jb], oB = P.camOff[jb];
+      const bool bLater = (bB > bA) || (bB == bA && oB >= oA);
+      const int tile = bLater ? P.tileIdx[(size_t)bB * P.nb + bA] : P.tileIdx[(size_t)bA * P.nb + bB];
+      if (tile < 0 || tile >= P.nTilesOrig) return set_error(COSL_E_INVALID, "solve plan: missing tile");
+      it.dst = tile * BA_TILE;
+      it.trans = bLater ? 0 : 1;
+      it.cOff = bLater ? oA : oB;
+      it.rOff = bLater ? oB : oA;
+      it.rhsIdx = bA * BA_TB + oA;
       for (long long b = b0; b < b1; b += chunk) {
-        BaPairItem it;
-        it.rowCam = ja;
-        it.colCam = jb;
         it.begin = (int)b;
         it.end = (int)std::min(b1, b + chunk);
         items.push_back(it);
@@ -406,57 +442,30 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   COSL_TRY(dev_alloc(s->stream, &s->d_V, (size_t)n * 6));
   COSL_TRY(dev_alloc(s->stream, &s->d_eb, (size_t)n * 3));
   COSL_TRY(dev_alloc(s->stream, &s->d_Uea, (size_t)m * 27));
-  s->ld = ((s->ns + 1 + 15) / 16) * 16;
-  s->nb = (s->ns + CB - 1) / CB;
-  COSL_TRY(dev_alloc(s->stream, &s->d_Srhs, (size_t)s->ld * (s->ns ? s->ns : 1)));
-  COSL_TRY(dev_alloc(s->stream, &s->d_Linv, (size_t)std::max(1, s->nb) * CB * CB));
-  COSL_TRY(dev_alloc(s->stream, &s->d_firstBlk, (size_t)std::max(1, s->nb)));
-  {
-    // block-row envelope from the camera co-visibility (pair counts): pair (ja <= jb) puts
-    // entries at rows of jb, columns of ja of the lower factor
-    const int nbk = s->nb;
-    s->firstBlk.assign(std::max(1, nbk), 0);
-    for (int I = 0; I < nbk; ++I) s->firstBlk[I] = I;
-    for (int ja = 0; ja < mf; ++ja)
-      for (int jb = ja; jb < mf; ++jb)
-        if (pcount[(size_t)ja * mf + jb + 1] > pcount[(size_t)ja * mf + jb]) {
-          const int cb0 = (6 * ja) / CB;
-          for (int rb = (6 * jb) / CB; rb <= (6 * jb + 5) / CB; ++rb)
-            s->firstBlk[rb] = std::min(s->firstBlk[rb], cb0);
-        }
-    s->lastBlk.assign(std::max(1, nbk), 0);
-    for (int k = 0; k < nbk; ++k) {
-      int last = k;
-      for (int I = k + 1; I < nbk; ++I)
-        if (s->firstBlk[I] <= k) last = I;
-      s->lastBlk[k] = last;
-    }
-    COSL_CUDA(cudaMemcpy(s->d_firstBlk, s->firstBlk.data(), sizeof(int) * std::max(1, nbk),
-                         cudaMemcpyHostToDevice));
-    // envelope of block COLUMN J: rows [J*CB, rowEnd[J]) (the small solve keeps everything dense)
-    std::vector<int> rowEnd(std::max(1, nbk), 0);
-    std::vector<long long> envOff(nbk + 2, 0);
-    for (int J = 0; J < nbk; ++J) {
-      rowEnd[J] = std::min(s->ns, (s->lastBlk[J] + 1) * CB);
-      envOff[J + 1] = envOff[J] + (long long)std::min(CB, s->ns - J * CB) * (rowEnd[J] - J * CB);
-    }
-    s->envCount = envOff[nbk] + s->ns;
-    s->factorFlops = 0.0;
-    for (int j = 0; j < s->ns; ++j) {
-      const double hgt = (double)(rowEnd[j / CB] - j);
-      s->factorFlops += hgt * hgt;
-    }
-    COSL_TRY(dev_alloc(s->stream, &s->d_rowEnd, (size_t)std::max(1, nbk)));
-    COSL_TRY(dev_alloc(s->stream, &s->d_envOff, (size_t)nbk + 2));
-    COSL_TRY(dev_alloc(s->stream, &s->d_envBuf, (size_t)std::max<long long>(1, s->envCount)));
-    COSL_CUDA(cudaMemcpy(s->d_rowEnd, rowEnd.data(), sizeof(int) * std::max(1, nbk),
-                         cudaMemcpyHostToDevice));
-    COSL_CUDA(cudaMemcpy(s->d_envOff, envOff.data(), sizeof(long long) * (nbk + 1),
-                         cudaMemcpyHostToDevice));
-    COSL_CUDA(cudaMemset(s->d_Srhs, 0, sizeof(double) * (size_t)s->ld * (s->ns ? s->ns : 1)));
+  const int nb = std::max(1, P.nb), nTiles = std::max(1, P.nTiles);
+  const size_t rhsLen = (size_t)nb * BA_TB;
+  s->reduceCount = (long long)rhsLen + (long long)P.nTilesOrig * BA_TILE;
+  s->factorFlops = P.flops;
+  COSL_TRY(dev_alloc(s->stream, &s->d_S, rhsLen + (size_t)nTiles * BA_TILE));
+  COSL_TRY(dev_alloc(s->stream, &s->d_Linv, (size_t)nb * BA_TILE));
+  COSL_TRY(dev_alloc(s->stream, &s->d_y, rhsLen));
+  COSL_TRY(dev_alloc(s->stream, &s->d_x, rhsLen));
+  COSL_TRY(dev_alloc(s->stream, &s->d_cnt, (size_t)P.nCounters + 1));
+  COSL_TRY(dev_alloc(s->stream, &s->d_tasks, P.tasks.size()));
+  COSL_TRY(dev_alloc(s->stream, &s->d_bwd, P.bwdList.size()));
+  COSL_TRY(dev_alloc(s->stream, &s->d_blkRows, (size_t)nb));
+  COSL_TRY(dev_alloc(s->stream, &s->d_blkRow0, (size_t)nb + 1));
+  COSL_TRY(dev_alloc(s->stream, &s->d_tileIdx, (size_t)nb * nb));
+  COSL_TRY(dev_alloc(s->stream, &s->d_diagBlk, (size_t)nTiles));
+  COSL_TRY(dev_alloc(s->stream, &s->d_blkCam0, (size_t)nb + 1));
+  COSL_TRY(dev_alloc(s->stream, &s->d_order, (size_t)std::max(1, mf)));
+  COSL_TRY(dev_alloc(s->stream, &s->d_solIdx, (size_t)std::max(1, mf)));
+  std::vector<int> h_blkRow0(nb + 1, 0), h_diagBlk(nTiles, -1), h_solIdx(std::max(1, mf), 0);
+  for (int k = 0; k < P.nb; ++k) {
+    h_blkRow0[k + 1] = h_blkRow0[k] + P.blkRows[k];
+    h_diagBlk[P.tileIdx[(size_t)k * P.nb + k]] = k;
   }
-  COSL_TRY(dev_alloc(s->stream, &s->d_y, (size_t)s->ns));
-  COSL_TRY(dev_alloc(s->stream, &s->d_x, (size_t)s->ns));
+  for (int j = 0; j < mf; ++j) h_solIdx[j] = P.camBlk[j] * BA_TB + P.camOff[j];
   COSL_TRY(dev_alloc(s->stream, &s->d_sc, (size_t)SC_NTOT));
   COSL_TRY(dev_alloc(s->stream, &s->d_outlier, (size_t)N));
   COSL_TRY(dev_alloc(s->stream, &s->d_items, items.size()));
@@ -475,6 +484,17 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   UP(s->d_ptr, p->ptr, sizeof(long long) * ((size_t)n + 1));
   if (!items.empty()) UP(s->d_items, items.data(), sizeof(BaPairItem) * items.size());
   if (nEntries) UP(s->d_entries, entries.data(), sizeof(int2) * (size_t)nEntries);
+  if (!P.tasks.empty()) UP(s->d_tasks, P.tasks.data(), sizeof(BaTask) * P.tasks.size());
+  if (!P.bwdList.empty()) UP(s->d_bwd, P.bwdList.data(), sizeof(BaBwdEntry) * P.bwdList.size());
+  if (P.nb) {
+    UP(s->d_blkRows, P.blkRows.data(), sizeof(int) * P.nb);
+    UP(s->d_tileIdx, P.tileIdx.data(), sizeof(int) * (size_t)P.nb * P.nb);
+    UP(s->d_blkCam0, P.blkCam0.data(), sizeof(int) * (P.nb + 1));
+    UP(s->d_order, P.order.data(), sizeof(int) * mf);
+  }
+  UP(s->d_blkRow0, h_blkRow0.data(), sizeof(int) * (nb + 1));
+  UP(s->d_diagBlk, h_diagBlk.data(), sizeof(int) * nTiles);
+  UP(s->d_solIdx, h_solIdx.data(), sizeof(int) * std::max(1, mf));
 #undef UP
   COSL_CUDA(cudaStreamSynchronize(s->stream));
   BaDev& d = s->d;
@@ -484,7 +504,6 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   d.ncon = ncon;
   d.mf = s->mf;
   d.ns = s->ns;
-  d.ld = s->ld;
   d.N = N;
   d.Nc = Nc;
   d.camK = s->d_camK;
@@ -501,26 +520,46 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   d.eb = s->d_eb;
   d.U = s->d_Uea;
   d.ea = s->d_Uea + (size_t)m * 21;
-  d.S = s->d_Srhs;
+  d.rhs = s->d_S;
+  d.tiles = s->d_S + rhsLen;
+  d.solIdx = s->d_solIdx;
   d.sc = s->d_sc;
-  // small systems are factored inside one CTA (ns*ns doubles of shared memory)
+  BaTileDev& td = s->td;
+  td.rhs = d.rhs;
+  td.tiles = d.tiles;
+  td.Linv = s->d_Linv;
+  td.y = s->d_y;
+  td.x = s->d_x;
+  td.cnt = s->d_cnt;
+  td.tasks = s->d_tasks;
+  td.bwd = s->d_bwd;
+  td.blkRows = s->d_blkRows;
+  td.nTasks = (int)P.tasks.size();
+  td.nb = P.nb;
+  td.nTiles = P.nTiles;
+  td.nCounters = P.nCounters;
+  td.sc = s->d_sc;
+  td.scFail = (int)SC_FAIL;
+  td.trace = nullptr;
+  // small systems (local BA) are factored inside one CTA (ns*ns doubles of shared memory)
   const size_t smallBytes = sizeof(double) * (size_t)s->ns * s->ns;
   s->smallSolve = (smallBytes <= 200 * 1024) && s->ns <= 1024;
+  if (std::getenv("COSL_BA_NO_SMALL")) s->smallSolve = false;
   // (the kernel also has ~8 KB of static shared memory, so opt in well below the 48 KB default)
   if (s->smallSolve && smallBytes > 32 * 1024)
-    COSL_CUDA(cudaFuncSetAttribute(ba_chol_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    COSL_CUDA(cudaFuncSetAttribute(ba_tile_small, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)smallBytes));
-  COSL_CUDA(cudaFuncSetAttribute(ba_chol_trsm, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 BA_CHOL_SMEM));
-  COSL_CUDA(cudaFuncSetAttribute(ba_chol_syrk, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 BA_CHOL_SMEM));
+  COSL_CUDA(cudaFuncSetAttribute(ba_tile_solve, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 BA_TILE_SMEM));
   {
-    const size_t bw = sizeof(double) * ((size_t)s->ns + CB * CB + CB);
-    if (!s->smallSolve && bw > 220 * 1024)
-      return set_error(COSL_E_INVALID, "reduced system too large for the backward solve (%d)", s->ns);
-    if (!s->smallSolve)
-      COSL_CUDA(cudaFuncSetAttribute(ba_chol_backward, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)bw));
+    // persistent grid: never more CTAs than can be co-resident (the ticket scheduler spins)
+    int nsm = 0, perSm = 0;
+    COSL_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, s->device));
+    COSL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, ba_tile_solve, BA_NTHREADS,
+                                                            BA_TILE_SMEM));
+    int grid = nsm * std::max(1, std::min(perSm, 1));
+    if (const char* e = std::getenv("COSL_BA_SOLVE_GRID")) grid = std::max(1, std::min(std::atoi(e), nsm * std::max(1, perSm)));
+    s->solveGrid = std::max(1, std::min(grid, td.nTasks));
   }
   s->secLin = s->timer.section("ba_linearize");
   s->secSchur = s->timer.section("ba_schur");
@@ -612,78 +651,17 @@ int linearize(cosl_ba_solver* s) {
   return COSL_OK;
 }
 
-// fine == true: per-kernel-class CUDA events (diagnostic, COSL_BA_NO_GRAPH=1), not capturable
-int launch_blocked_solve(cosl_ba_solver* s, int* nLaunch, bool fine = false) {
-  const int secP = fine ? s->timer.section("chol_potf2_inv") : 0;
-  const int secT = fine ? s->timer.section("chol_trsm") : 0;
-  const int secS = fine ? s->timer.section("chol_syrk") : 0;
-  const int secB = fine ? s->timer.section("chol_backward") : 0;
-  const int ns = s->ns, ld = s->ld, nb = s->nb, nrows = ns + 1;
-  const int extraBlk = ns / CB;  // block row that holds the right-hand-side row ns
-  int count = 0;
-  for (int k = 0; k < nb; ++k) {
-    const int k0 = k * CB, bs = std::min(CB, ns - k0);
-    double* Linv = s->d_Linv + (size_t)k * CB * CB;
-    if (fine) s->timer.begin(secP, s->stream);
-    COSL_LAUNCH(ba_chol_potf2_inv, 1, 256, 0, s->stream, s->d.S, ld, k0, bs, Linv, s->d_sc,
-                (int)SC_FAIL);
-    if (fine) s->timer.end(s->stream);
-    const int nAct = s->lastBlk[k] - k;
-    const bool extra = extraBlk > k + nAct || extraBlk == k;
-    const int nT = nAct + (extra ? 1 : 0);
-    if (nT > 0) {
-      if (fine) s->timer.begin(secT, s->stream);
-      COSL_LAUNCH(ba_chol_trsm, nT, 256, BA_CHOL_SMEM, s->stream, s->d.S, ld, nrows, k0, bs, k, nAct,
-                  extraBlk, Linv);
-      if (fine) s->timer.end(s->stream);
-      if (fine) s->timer.begin(secS, s->stream);
-      COSL_LAUNCH(ba_chol_syrk, dim3(nT, nT), 256, BA_CHOL_SMEM, s->stream, s->d.S, ld, ns, nrows, k0, bs, k,
-                  nAct, extraBlk);
-      if (fine) s->timer.end(s->stream);
-      count += 2;
-    }
-    ++count;
-  }
-  if (fine) s->timer.begin(secB, s->stream);
-  COSL_LAUNCH(ba_chol_backward, 1, 1024, sizeof(double) * ((size_t)ns + CB * CB + CB), s->stream,
-              s->d.S, ld, ns, nb, s->d_Linv, s->d_firstBlk, s->d_x);
-  if (fine) s->timer.end(s->stream);
-  *nLaunch = count + 1;
-  return COSL_OK;
-}
-
+// reduced camera system -> d_x (block padded, permuted): one persistent dataflow launch
 int dense_solve(cosl_ba_solver* s) {
   const int ns = s->ns;
   if (ns == 0) return COSL_OK;
-  static const bool noGraph = std::getenv("COSL_BA_NO_GRAPH") != nullptr;
-  if (!s->smallSolve && noGraph) {
-    int nl = 0;
-    COSL_TRY(launch_blocked_solve(s, &nl, s->timer.enabled));
-    COSL_CUDA(cudaGetLastError());
-    return COSL_OK;
-  }
   s->timer.begin(s->secSolve, s->stream);
   if (s->smallSolve) {
-    COSL_LAUNCH(ba_chol_small, 1, 256, sizeof(double) * (size_t)ns * ns, s->stream, s->d.S, s->ld,
-                ns, s->d_x, s->d_sc, (int)SC_FAIL);
+    COSL_LAUNCH(ba_tile_small, 1, 256, sizeof(double) * (size_t)ns * ns, s->stream, s->td,
+                s->d_tileIdx, s->d_blkRow0, ns);
   } else {
-    // the launch sequence only depends on the (fixed) structure: capture it once, replay after
-    if (!s->solveGraph) {
-      cudaGraph_t graph = nullptr;
-      int nl = 0;
-      const uint64_t before = g_launches.load();
-      COSL_CUDA(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
-      const int rc = launch_blocked_solve(s, &nl);
-      cudaError_t e = cudaStreamEndCapture(s->stream, &graph);
-      g_launches.store(before);
-      if (rc != COSL_OK) return rc;
-      if (e != cudaSuccess) return set_error(COSL_E_CUDA, "graph capture: %s", cudaGetErrorString(e));
-      COSL_CUDA(cudaGraphInstantiate(&s->solveGraph, graph, 0));
-      cudaGraphDestroy(graph);
-      s->solveGraphNodes = nl;
-    }
-    COSL_CUDA(cudaGraphLaunch(s->solveGraph, s->stream));
-    g_launches.fetch_add(s->solveGraphNodes, std::memory_order_relaxed);
+    COSL_CUDA(cudaMemsetAsync(s->d_cnt, 0, sizeof(int) * ((size_t)s->td.nCounters + 1), s->stream));
+    COSL_LAUNCH(ba_tile_solve, s->solveGrid, BA_NTHREADS, BA_TILE_SMEM, s->stream, s->td);
   }
   s->timer.end(s->stream);
   COSL_CUDA(cudaGetLastError());
@@ -700,20 +678,15 @@ int solve_trial(cosl_ba_solver* s, double mu, bool* solved) {
   s->timer.begin(s->secSchur, s->stream);
   const long long ns = s->ns;
   if (ns) {
-    COSL_LAUNCH(ba_init_S, s->nb, 256, 0, s->stream, s->d, mu, r0 ? 1 : 0, s->d_rowEnd);
+    COSL_LAUNCH(ba_tile_init, std::max(1, s->plan.nTiles), 256, 0, s->stream, s->d, mu, r0 ? 1 : 0,
+                s->d_diagBlk, s->d_blkCam0, s->d_order);
     if (s->nItems)
       COSL_LAUNCH(ba_schur_pairs, div_up(s->nItems, 4), 128, 0, s->stream, s->d, s->d_items,
                   s->nItems, s->d_entries, mu);
   }
   s->timer.end(s->stream);
-  if (ns && multi(s)) {
-    // only the envelope travels: pack -> one ncclAllReduce -> unpack
-    COSL_LAUNCH(ba_env_pack, s->nb + 1, 256, 0, s->stream, s->d.S, s->ld, s->ns, s->d_rowEnd,
-                s->d_envOff, s->nb, s->d_envBuf, 0, s->d.S);
-    COSL_TRY(allreduce(s, s->d_envBuf, (size_t)s->envCount, ncclSum));
-    COSL_LAUNCH(ba_env_pack, s->nb + 1, 256, 0, s->stream, s->d.S, s->ld, s->ns, s->d_rowEnd,
-                s->d_envOff, s->nb, s->d_envBuf, 1, s->d.S);
-  }
+  // the one exchange of an LM trial: [rhs | Schur-structure tiles] is contiguous, no packing
+  if (ns && multi(s)) COSL_TRY(allreduce(s, s->d_S, (size_t)s->reduceCount, ncclSum));
   COSL_TRY(dense_solve(s));
   s->timer.begin(s->secBack, s->stream);
   COSL_LAUNCH(ba_cam_update, div_up(6 * s->m, 256), 256, 0, s->stream, s->d, s->d_pa, s->d_x,
@@ -1040,11 +1013,54 @@ int cosl_ba_solver_stats(cosl_ba_solver* s, double out[8]) {
   if (!s || !out) return set_error(COSL_E_INVALID, "cosl_ba_solver_stats: null argument");
   for (int k = 0; k < 8; ++k) out[k] = 0.0;
   out[0] = (double)s->ns;
-  out[1] = (double)s->envCount;
-  out[2] = s->smallSolve ? (double)s->ns * s->ns * s->ns / 3.0 : s->factorFlops;
+  out[1] = (double)s->reduceCount;
+  out[2] = s->smallSolve ? (double)s->ns * s->ns * s->ns / 3.0 : 0.5 * s->factorFlops;
+  out[5] = (double)s->plan.nb;
+  out[6] = (double)s->plan.nTiles;
+  out[7] = (double)s->plan.tasks.size();
   out[3] = (double)s->nEntries;
   out[4] = (double)s->nItems;
   return COSL_OK;
+}
+
+int cosl_ba_solver_plan_info(cosl_ba_solver* s, int out[8]) {
+  if (!s || !out) return set_error(COSL_E_INVALID, "cosl_ba_solver_plan_info: null argument");
+  out[0] = s->plan.nb;
+  out[1] = s->plan.nTilesOrig;
+  out[2] = s->plan.nTiles;
+  out[3] = (int)s->plan.tasks.size();
+  out[4] = s->plan.ndDepth;
+  out[5] = s->plan.criticalPathTasks;
+  out[6] = s->solveGrid;
+  out[7] = s->smallSolve ? 1 : 0;
+  return COSL_OK;
+}
+
+// diagnostic: per-task timeline of the LAST persistent solve launch.  enable -> run -> get.
+// out: [nTasks][4] = sm id, globaltimer ns at ticket / operands ready / done; meta: [nTasks][3] =
+// task type, pivot block k, row block i.
+int cosl_ba_solver_trace(cosl_ba_solver* s, int enable, uint64_t* out, int32_t* meta, int cap) {
+  BA_ENTER(s)
+  const int nt = (int)s->plan.tasks.size();
+  if (enable) {
+    if (!s->d_trace) COSL_TRY(dev_alloc(s->stream, &s->d_trace, (size_t)std::max(1, nt) * 4));
+    COSL_CUDA(cudaMemsetAsync(s->d_trace, 0, sizeof(unsigned long long) * 4 * std::max(1, nt), s->stream));
+    s->td.trace = s->d_trace;
+    return nt;
+  }
+  if (out && s->d_trace) {
+    const int n = std::min(cap, nt);
+    COSL_CUDA(cudaMemcpyAsync(out, s->d_trace, sizeof(uint64_t) * 4 * n, cudaMemcpyDeviceToHost, s->stream));
+    COSL_CUDA(cudaStreamSynchronize(s->stream));
+    if (meta)
+      for (int t = 0; t < n; ++t) {
+        meta[3 * t] = s->plan.tasks[t].type;
+        meta[3 * t + 1] = s->plan.tasks[t].k;
+        meta[3 * t + 2] = s->plan.tasks[t].i;
+      }
+  }
+  s->td.trace = nullptr;
+  return nt;
 }
 
 int cosl_ba_solver_profile_enable(cosl_ba_solver* s, int on) {

@@ -11,7 +11,8 @@
 //   V[n][6], eb[n][3], U[m][21] (packed upper), ea[m][6]
 //   pair work list for the Schur contraction: items {rowCam, colCam, begin, end} over entry pairs
 //   (obsA, obsB) sorted by camera pair
-//   S[ns*ns] row-major, only blocks (j <= k) are formed (== lower triangle in column-major); rhs[ns]
+//   S: block-sparse 64x64 tiles of the permuted reduced camera system + block-padded rhs, see
+//   ba_tile.cuh / ba_plan.h
 //
 // One-observation-per-thread kernels evaluate residuals and the 2x6 / 2x3 Jacobian blocks; per-point
 // (resp. per-camera) sums are collapsed with segmented warp shuffles and only segment heads touch
@@ -24,7 +25,6 @@ namespace coslam {
 
 struct BaDev {
   int m, n, mcon, ncon, mf, ns;
-  int ld;  // leading dimension of S (>= ns + 1): column c starts at S + c*ld, row ns = rhs
   long long N, Nc;
   const double* camK;
   const double* camR0;
@@ -40,8 +40,10 @@ struct BaDev {
   double* eb;
   double* U;
   double* ea;
-  double* S;
-  double* sc;  // scalars, see BaScalar
+  double* tiles;      // reduced camera system, tile t at tiles + 4096 t (column-major 64x64)
+  double* rhs;        // block padded: block k at rhs + 64 k
+  const int* solIdx;  // per free camera: index of its first row in rhs / x
+  double* sc;         // scalars, see BaScalar
 };
 
 enum BaScalar {
@@ -339,36 +341,44 @@ __global__ void __launch_bounds__(256) ba_stats_kernel(BaDev d) {
   }
 }
 
-// S <- 0 with the damped camera blocks U*_j on the diagonal, rhs <- ea.  addU: this rank
-// contributes U/ea/mu (rank 0 only in the multi-GPU case, where U/ea are already all-reduced).
+// S <- 0 with the damped camera blocks U*_j on the diagonal tiles, rhs <- ea.  One CTA per tile
+// (blockIdx.x < nTiles) zeroes it and, if it is the diagonal tile of block k (diagBlk[t] = k), writes
+// the lower part of U_j + mu I for the cameras order[blkCam0[k] .. blkCam0[k+1]) of that block and
+// their slice of rhs.  addU: this rank contributes U/ea/mu (rank 0 only in the multi-GPU case, where
+// U/ea are already all-reduced).  Padding rows of a block stay zero (the factorisation treats them
+// as identity).
 __global__ void __launch_bounds__(256)
-ba_init_S(BaDev d, double mu, int addU, const int* __restrict__ rowEnd) {
-  // one CTA per 64-wide block column J: (re)initialise only the envelope rows [J*64, rowEnd[J])
-  // of its columns plus the right-hand-side row ns.  Everything outside the envelope is zero from
-  // the allocation-time memset and is never written (Schur terms and Cholesky fill stay inside).
-  // Memory index = c * ld + r (column c of the column-major lower factor == row c of the
-  // row-major upper Schur complement).
-  const int J = blockIdx.x;
-  const int ns = d.ns, ld = d.ld;
-  const int c0 = J * 64, ncol = min(64, ns - c0);
-  const int r0 = c0, r1 = rowEnd[J], len = r1 - r0;
-  for (int t = threadIdx.x; t < ncol * (len + 1); t += 256) {
-    const int cc = t / (len + 1), rr = t - cc * (len + 1);
-    const int c = c0 + cc;
-    const int r = (rr < len) ? (r0 + rr) : ns;
-    double v = 0;
-    if (r < ns) {
-      const int jb = c / 6, kb = r / 6;
-      if (addU && jb == kb && r >= c) {
-        const int a = c - 6 * jb, b = r - 6 * kb;
-        const int idx = a * 6 - (a * (a - 1)) / 2 + (b - a);  // packed upper index of (a, b), a<=b
-        v = d.U[21 * (size_t)(jb + d.mcon) + idx];
-        if (a == b) v += mu;
+ba_tile_init(BaDev d, double mu, int addU, const int* __restrict__ diagBlk,
+             const int* __restrict__ blkCam0, const int* __restrict__ order) {
+  const int t = blockIdx.x;
+  double2* tile = reinterpret_cast<double2*>(d.tiles + (size_t)t * 4096);
+  const double2 z = make_double2(0.0, 0.0);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) tile[threadIdx.x + 256 * u] = z;
+  const int k = diagBlk[t];
+  if (k < 0) return;
+  if (threadIdx.x < 64) d.rhs[(size_t)k * 64 + threadIdx.x] = 0.0;
+  __syncthreads();
+  if (!addU) return;
+  const int p0 = blkCam0[k], ncam = blkCam0[k + 1] - p0;
+  for (int e = threadIdx.x; e < ncam * 27; e += 256) {
+    const int c = e / 27, q = e - 27 * c;
+    const int cam = order[p0 + c] + d.mcon;
+    const int off = 6 * c;
+    if (q < 21) {
+      // packed upper index q -> (a <= b); stored at row off+b, column off+a of the lower tile
+      int a = 0, rem = q;
+      while (rem >= 6 - a) {
+        rem -= 6 - a;
+        ++a;
       }
+      const int b = a + rem;
+      double v = d.U[21 * (size_t)cam + q];
+      if (a == b) v += mu;
+      d.tiles[(size_t)t * 4096 + (off + a) * 64 + off + b] = v;
     } else {
-      v = addU ? d.ea[6 * (size_t)d.mcon + c] : 0.0;
+      d.rhs[(size_t)k * 64 + off + (q - 21)] = d.ea[6 * (size_t)cam + (q - 21)];
     }
-    d.S[(size_t)c * ld + r] = v;
   }
 }
 
@@ -381,6 +391,11 @@ ba_init_S(BaDev d, double mu, int addU, const int* __restrict__ rowEnd) {
 struct BaPairItem {
   int rowCam, colCam;  // free-camera indices (0-based in the reduced system)
   int begin, end;      // entry range
+  // destination of the 6x6 block acc(r, c) (r: row camera's parameter, c: column camera's):
+  // tiles[dst + (cOff + (trans ? c : r)) * 64 + rOff + (trans ? r : c)] -- the block lands in the
+  // LOWER triangle of the permuted system whichever of the two cameras comes first in the ordering
+  int dst, rOff, cOff, trans;
+  int rhsIdx, pad0, pad1, pad2;  // rhs index of the row camera (diagonal items only)
 };
 
 __device__ __forceinline__ void inv3sym_mu(const double* __restrict__ V, double mu, double I[6]) {
@@ -450,20 +465,21 @@ ba_schur_pairs(BaDev d, const BaPairItem* __restrict__ items, int nItems,
     for (int k = 0; k < 3; ++k) racc[k] += __shfl_xor_sync(0xffffffffu, racc[k], o);
   }
   if (lane < 2) {
-    const long long ld = d.ld;
-    const int r0 = 6 * it.rowCam, c0 = 6 * it.colCam + 3 * half;
+    double* T = d.tiles + it.dst;
 #pragma unroll
     for (int r = 0; r < 6; ++r)
 #pragma unroll
       for (int cc = 0; cc < 3; ++cc) {
-        // only the upper part (col >= row) of diagonal blocks is kept
-        if (!diag || (c0 + cc >= r0 + r))
-          atomicAdd(&d.S[(long long)(r0 + r) * ld + c0 + cc], -acc[3 * r + cc]);
+        const int c = 3 * half + cc;
+        // only the lower part (row >= col of the tile, i.e. c >= r) of diagonal blocks is kept
+        if (!diag || c >= r) {
+          const int col = it.cOff + (it.trans ? c : r), row = it.rOff + (it.trans ? r : c);
+          atomicAdd(&T[col * 64 + row], -acc[3 * r + cc]);
+        }
       }
     if (diag) {
 #pragma unroll
-      for (int rr = 0; rr < 3; ++rr)
-        atomicAdd(&d.S[(long long)(r0 + 3 * half + rr) * ld + d.ns], -racc[rr]);
+      for (int rr = 0; rr < 3; ++rr) atomicAdd(&d.rhs[it.rhsIdx + 3 * half + rr], -racc[rr]);
     }
   }
 }
@@ -554,7 +570,7 @@ ba_cam_update(BaDev d, const double* __restrict__ pa, const double* __restrict__
     const int j = t / 6, r = t - 6 * j;
     double dlt = 0;
     if (j >= d.mcon) {
-      dlt = sol[6 * (j - d.mcon) + r];
+      dlt = sol[d.solIdx[j - d.mcon] + r];
       dp2 = dlt * dlt;
       dl = dlt * (mu * dlt + d.ea[t]);
       p2 = pa[t] * pa[t];

@@ -1,0 +1,549 @@
+// ba_tile.cuh -- device side of the reduced-camera-system solve (fp64, sm_100a).
+//
+// Replaces the dense LAPACK solve inside sba_motstr_levmar_x (reference call
+// app/SL_CoSLAMBA.cpp:360-363; BA-4 step v and 8f-1 of SURVEY.md).  Planning (ordering, blocking,
+// symbolic fill, task DAG) is done once per solver on the host, see ba_plan.h.
+//
+// Storage in HBM:  S = [ rhs (nb*64, block padded) | tiles ]: tile t = 64x64 doubles, column-major
+// (element (r, c) at c*64 + r), only the structurally non-zero lower tiles of the permuted system
+// exist; the tiles the Schur contraction can write come first, so [rhs | those tiles] is one
+// contiguous buffer for the multi-GPU all-reduce.  Linv[k] (64x64, column-major), y and x are block
+// padded like rhs.
+//
+// ba_tile_solve: ONE persistent launch for factorisation + both substitutions.  Every CTA takes the
+// next task of the critical-path-first list with an atomic ticket, waits (one polling thread,
+// ld.acquire.gpu) until the per-tile counters say its operands are final, executes it on tiles
+// staged in shared memory, publishes the result (fence + red.release on the counter).  All tile
+// reads bypass L1 (ld.global.cg): tiles are rewritten by other SMs during the launch.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ba_plan.h"
+
+namespace coslam {
+
+struct BaTileDev {
+  double* rhs;    // [nb*64]
+  double* tiles;  // [nTiles][4096]
+  double* Linv;   // [nb][4096]
+  double* y;      // [nb*64]
+  double* x;      // [nb*64]
+  int* cnt;       // [nCounters + 1]; the last one is the task ticket
+  const BaTask* tasks;
+  const BaBwdEntry* bwd;
+  const int* blkRows;
+  int nTasks, nb, nTiles, nCounters;
+  double* sc;
+  int scFail;
+  unsigned long long* trace;  // optional [nTasks][4]: sm id, ns at ticket, ns when ready, ns when done
+};
+
+constexpr int BA_LDS = 68;                                   // smem leading dimension of a staged tile
+constexpr int BA_TILE_SMEM_DOUBLES = 3 * BA_TB * BA_LDS + 8 * BA_TB + 2 * BA_TB;
+constexpr int BA_TILE_SMEM = BA_TILE_SMEM_DOUBLES * (int)sizeof(double);
+constexpr int BA_NTHREADS = 256;
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ba_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void red_release_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// 1/sqrt(d): single-precision seed + two Newton steps in fp64 (full double accuracy inside the
+// float range, which Gauss-Newton pivots always are); the library rsqrt() is ~3x longer and this
+// sits on the pivot-to-pivot critical path of the whole solve.
+__device__ __forceinline__ double ba_rsqrt_fast(double d) {
+  if (d < 1e-30 || d > 1e30) return rsqrt(d);
+  double y = (double)rsqrtf((float)d);
+  const double h = 0.5 * d;
+  y = __fma_rn(y, __fma_rn(-h * y, y, 0.5), y);
+  y = __fma_rn(y, __fma_rn(-h * y, y, 0.5), y);
+  return y;
+}
+
+// global column-major 64x64 tile -> shared [col][row] with leading dimension LD; all 8 loads of a
+// thread are in flight before the first shared store (one L2 round trip per tile)
+template <int LD>
+__device__ __forceinline__ void tile_load(const double* __restrict__ g, double* __restrict__ s, int tid) {
+  double2 v[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) v[u] = __ldcg(reinterpret_cast<const double2*>(g) + tid + BA_NTHREADS * u);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int e = 2 * (tid + BA_NTHREADS * u);
+    const int c = e >> 6, r = e & 63;
+    *reinterpret_cast<double2*>(s + c * LD + r) = v[u];
+  }
+}
+
+// two tiles at once (16 loads in flight)
+template <int LD>
+__device__ __forceinline__ void tile_load2(const double* __restrict__ g0, double* __restrict__ s0,
+                                           const double* __restrict__ g1, double* __restrict__ s1, int tid) {
+  double2 v0[8], v1[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    v0[u] = __ldcg(reinterpret_cast<const double2*>(g0) + tid + BA_NTHREADS * u);
+    v1[u] = __ldcg(reinterpret_cast<const double2*>(g1) + tid + BA_NTHREADS * u);
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int e = 2 * (tid + BA_NTHREADS * u);
+    const int c = e >> 6, r = e & 63;
+    *reinterpret_cast<double2*>(s0 + c * LD + r) = v0[u];
+    *reinterpret_cast<double2*>(s1 + c * LD + r) = v1[u];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// acc(r, c) = sum_{p < kk} sA[p][r] * sB[p][c]   (both operands staged [p][row], ld = BA_LDS)
+// Tensor-core version: fp64 DMMA m8n8k4.  Warp w owns rows 16*(w&3).. (2 fragments) and columns
+// 32*(w>>2).. (4 fragments); lane l holds A(row l/4, k l%4), B(k l%4, col l/4) and
+// C(row l/4, cols 2*(l%4), 2*(l%4)+1) of each 8x8 fragment.  BA_LDS = 68 makes the fragment loads
+// conflict free (half-warp: 4*(l%4) + l/4 covers 16 distinct bank pairs).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+struct TileAcc {
+  double c[2][4][2];
+};
+
+__device__ __forceinline__ void tile_gemm_dmma(const double* __restrict__ sA, const double* __restrict__ sB,
+                                               int kk, int tid, TileAcc& acc) {
+  const int lane = tid & 31, w = tid >> 5;
+  const int mB = (w & 3) * 16 + (lane >> 2), nB = (w >> 2) * 32 + (lane >> 2), kl = lane & 3;
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni) acc.c[mi][ni][0] = acc.c[mi][ni][1] = 0.0;
+  for (int p0 = 0; p0 < kk; p0 += 4) {
+    const double* pa = sA + (p0 + kl) * BA_LDS + mB;
+    const double* pb = sB + (p0 + kl) * BA_LDS + nB;
+    const double a0 = pa[0], a1 = pa[8];
+    const double b0 = pb[0], b1 = pb[8], b2 = pb[16], b3 = pb[24];
+    dmma884(acc.c[0][0][0], acc.c[0][0][1], a0, b0);
+    dmma884(acc.c[0][1][0], acc.c[0][1][1], a0, b1);
+    dmma884(acc.c[0][2][0], acc.c[0][2][1], a0, b2);
+    dmma884(acc.c[0][3][0], acc.c[0][3][1], a0, b3);
+    dmma884(acc.c[1][0][0], acc.c[1][0][1], a1, b0);
+    dmma884(acc.c[1][1][0], acc.c[1][1][1], a1, b1);
+    dmma884(acc.c[1][2][0], acc.c[1][2][1], a1, b2);
+    dmma884(acc.c[1][3][0], acc.c[1][3][1], a1, b3);
+  }
+}
+
+// fragment element -> (row, col) inside the 64x64 tile
+__device__ __forceinline__ void tile_acc_rc(int tid, int mi, int ni, int e, int& r, int& c) {
+  const int lane = tid & 31, w = tid >> 5;
+  r = (w & 3) * 16 + 8 * mi + (lane >> 2);
+  c = (w >> 2) * 32 + 8 * ni + 2 * (lane & 3) + e;
+}
+
+// ---------------------------------------------------------------------------------------------
+// POTRF: factor the diagonal tile staged in sT (ld 65, lower part used, padding rows/cols made
+// identity), 8-column panels: the 64 row threads factor the 8x8 diagonal block redundantly in
+// registers and solve their own row of the panel (no communication inside a panel), then all 256
+// threads apply the rank-8 update to the trailing lower triangle.  2 barriers per 8 pivots.
+// ---------------------------------------------------------------------------------------------
+constexpr int BA_LDP = 65;
+
+__device__ __forceinline__ void tile_potrf(double* __restrict__ sT, int bs, int tid, int* s_fail,
+                                           double* __restrict__ sInv) {
+  for (int c0 = 0; c0 < bs; c0 += 8) {
+    if (tid < 64) {
+      const int r = tid;
+      double D[8][8], inv[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int i = j; i < 8; ++i) D[i][j] = sT[(c0 + j) * BA_LDP + c0 + i];
+      bool bad = false;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        double d = D[p][p];
+        if (!(d > 0) || !isfinite(d)) {
+          bad = true;
+          d = 1.0;
+        }
+        const double rs = ba_rsqrt_fast(d);
+        inv[p] = rs;
+        D[p][p] = d * rs;
+#pragma unroll
+        for (int i = p + 1; i < 8; ++i) D[i][p] *= rs;
+#pragma unroll
+        for (int j = p + 1; j < 8; ++j)
+#pragma unroll
+          for (int i = j; i < 8; ++i) D[i][j] = __fma_rn(-D[i][p], D[j][p], D[i][j]);
+      }
+      if (r == 0) {
+        if (bad) *s_fail = 1;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) sInv[c0 + p] = inv[p];  // 1 / L(c0+p, c0+p)
+      }
+      if (r >= c0 + 8) {
+        double x[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) x[q] = sT[(c0 + q) * BA_LDP + r];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          double s = x[q];
+#pragma unroll
+          for (int p = 0; p < q; ++p) s = __fma_rn(-x[p], D[q][p], s);
+          x[q] = s * inv[q];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sT[(c0 + q) * BA_LDP + r] = x[q];
+      } else if (r >= c0) {
+        const int a = r - c0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          double v = 0.0;
+#pragma unroll
+          for (int aa = 0; aa < 8; ++aa)
+            if (aa == a && q <= aa) v = D[aa][q];
+          sT[(c0 + q) * BA_LDP + r] = v;
+        }
+      }
+    }
+    __syncthreads();
+    if (c0 + 8 < 64) {
+      // trailing update of the lower triangle right of the panel
+      const int ti = tid & 15, tj = tid >> 4;
+      double xi[4][8], xj[4][8];
+      bool any = false;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) any = any || (tj + 16 * b >= c0 + 8);
+      if (any) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) xi[a][q] = sT[(c0 + q) * BA_LDP + ti + 16 * a];
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) xj[b][q] = sT[(c0 + q) * BA_LDP + tj + 16 * b];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            const int i = ti + 16 * a, j = tj + 16 * b;
+            if (j >= c0 + 8 && i >= j) {
+              double s = sT[j * BA_LDP + i];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) s = __fma_rn(-xi[a][q], xj[b][q], s);
+              sT[j * BA_LDP + i] = s;
+            }
+          }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Inverse of the lower-triangular factor in sT (ld 65) -> sM (ld 65, full tile, zeros above the
+// diagonal), by recursive doubling: four 16x16 diagonal blocks by forward substitution (one thread
+// per column), then M21 = -M22 (L21 M11) on the 32- and the 64-level; sW is scratch (ld 65).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_trinv(const double* __restrict__ sT, double* __restrict__ sM,
+                                           double* __restrict__ sW, const double* __restrict__ sInv,
+                                           int tid) {
+  for (int t = tid; t < 64 * 64; t += BA_NTHREADS) sM[(t >> 6) * BA_LDP + (t & 63)] = 0.0;
+  __syncthreads();
+  if (tid < 64) {
+    const int b0 = (tid >> 4) * 16, c = tid & 15;
+    double x[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      double s = (r == c) ? 1.0 : 0.0;
+#pragma unroll
+      for (int p = 0; p < r; ++p) s = __fma_rn(-sT[(b0 + p) * BA_LDP + b0 + r], x[p], s);
+      x[r] = s * sInv[b0 + r];
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) sM[(b0 + c) * BA_LDP + b0 + r] = (r >= c) ? x[r] : 0.0;
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int h = 16; h <= 32; h <<= 1) {
+    // diagonal blocks of size 2h at offsets o: 11 = [o, o+h), 22 = [o+h, o+2h)
+    const int nblk = 64 / (2 * h);
+    // W = L21 * M11   (h x h per block)
+    for (int t = tid; t < nblk * h * h; t += BA_NTHREADS) {
+      const int blk = t / (h * h), e = t - blk * h * h, c = e / h, r = e - c * h;
+      const int o = blk * 2 * h;
+      double s = 0;
+      for (int p = c; p < h; ++p) s = __fma_rn(sT[(o + p) * BA_LDP + o + h + r], sM[(o + c) * BA_LDP + o + p], s);
+      sW[(o + c) * BA_LDP + o + h + r] = s;
+    }
+    __syncthreads();
+    // M21 = -M22 * W
+    for (int t = tid; t < nblk * h * h; t += BA_NTHREADS) {
+      const int blk = t / (h * h), e = t - blk * h * h, c = e / h, r = e - c * h;
+      const int o = blk * 2 * h;
+      double s = 0;
+      for (int p = 0; p <= r; ++p) s = __fma_rn(sM[(o + h + p) * BA_LDP + o + h + r], sW[(o + c) * BA_LDP + o + h + p], s);
+      sM[(o + c) * BA_LDP + o + h + r] = -s;
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// out[c] (-)= sum_r G[r, c] * v[r] for one global column-major tile G: 4 threads per column.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double tile_colT_dot(const double* __restrict__ G, const double* __restrict__ sv,
+                                                int tid) {
+  const int c = tid >> 2, q = tid & 3;
+  const double2* col = reinterpret_cast<const double2*>(G + c * BA_TB + 16 * q);
+  double2 v[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) v[u] = __ldcg(col + u);
+  double s0 = 0, s1 = 0;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    s0 = __fma_rn(v[u].x, sv[16 * q + 2 * u], s0);
+    s1 = __fma_rn(v[u].y, sv[16 * q + 2 * u + 1], s1);
+  }
+  double s = s0 + s1;
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The persistent dataflow kernel.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
+  extern __shared__ double smem[];
+  double* sA = smem;                       // [64][68]
+  double* sB = sA + BA_TB * BA_LDS;        // [64][68]
+  double* sC = sB + BA_TB * BA_LDS;        // [64][68]
+  double* sX = sC + BA_TB * BA_LDS;        // [8][64] x vectors of a BWD chunk
+  double* sV = sX + 8 * BA_TB;             // [64]
+  double* sY = sV + BA_TB;                 // [64]
+  __shared__ int s_task, s_fail;
+  const int tid = threadIdx.x;
+  int* const ticket = d.cnt + d.nCounters;
+  for (;;) {
+    __syncthreads();
+    if (tid == 0) {
+      s_task = atomicAdd(ticket, 1);
+      s_fail = 0;
+    }
+    __syncthreads();
+    const int ti = s_task;
+    if (ti >= d.nTasks) break;
+    const BaTask t = d.tasks[ti];
+    if (tid == 0) {
+      if (d.trace) {
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        d.trace[4 * (size_t)ti] = smid;
+        d.trace[4 * (size_t)ti + 1] = ba_globaltimer();
+      }
+      if (t.w0i >= 0)
+        while (ld_acquire(d.cnt + t.w0i) < t.w0v) {}
+      if (t.w1i >= 0)
+        while (ld_acquire(d.cnt + t.w1i) < t.w1v) {}
+      if (t.w2i >= 0)
+        while (ld_acquire(d.cnt + t.w2i) < t.w2v) {}
+      if (t.type == BA_T_BWD)
+        for (int e = t.l0; e < t.l1; ++e)
+          while (ld_acquire(d.cnt + d.nTiles + d.bwd[e].blk) < 1) {}
+      if (d.trace) d.trace[4 * (size_t)ti + 2] = ba_globaltimer();
+    }
+    __syncthreads();
+    const int bk = d.blkRows[t.k];
+    if (t.type == BA_T_POTRF) {
+      // stage the lower part, identity on the padding
+      {
+        const double* g = d.tiles + (size_t)t.tC * BA_TILE;
+        double2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(reinterpret_cast<const double2*>(g) + tid + BA_NTHREADS * u);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = 2 * (tid + BA_NTHREADS * u);
+          const int c = e >> 6, r = e & 63;
+          double a = v[u].x, b = v[u].y;
+          if (r >= bk || c >= bk) a = (r == c) ? 1.0 : 0.0;
+          if (r + 1 >= bk || c >= bk) b = (r + 1 == c) ? 1.0 : 0.0;
+          sA[c * BA_LDP + r] = a;
+          sA[c * BA_LDP + r + 1] = b;
+        }
+        if (tid < 64) {
+          sV[tid] = (tid < bk) ? __ldcg(d.rhs + (size_t)t.k * BA_TB + tid) : 0.0;
+          sY[tid] = 1.0;  // reciprocal diagonal; panels beyond bk are identity padding
+        }
+      }
+      __syncthreads();
+      tile_potrf(sA, bk, tid, &s_fail, sY);
+      tile_trinv(sA, sB, sC, sY, tid);
+      // Linv (column-major, padding rows/cols zero) and y = Linv b
+      {
+        double* g = d.Linv + (size_t)t.k * BA_TILE;
+        for (int e = tid; e < BA_TILE; e += BA_NTHREADS) {
+          const int c = e >> 6, r = e & 63;
+          g[e] = (r < bk && c < bk) ? sB[c * BA_LDP + r] : 0.0;
+        }
+        if (tid < 64) {
+          double s = 0;
+          for (int p = 0; p <= tid && p < bk; ++p) s = __fma_rn(sB[p * BA_LDP + tid], sV[p], s);
+          d.y[(size_t)t.k * BA_TB + tid] = (tid < bk) ? s : 0.0;
+        }
+        if (tid == 0 && s_fail) d.sc[d.scFail] = 1.0;
+      }
+    } else if (t.type == BA_T_TRSM || t.type == BA_T_UPD) {
+      const bool upd = (t.type == BA_T_UPD);
+      double* gC = d.tiles + (size_t)t.tC * BA_TILE;
+      const double* gA = upd ? d.tiles + (size_t)t.tA * BA_TILE : gC;
+      const double* gB = upd ? d.tiles + (size_t)t.tB * BA_TILE : d.Linv + (size_t)t.tA * BA_TILE;
+      // C prefetch (independent of the operand staging: one round trip for everything)
+      double cold[2][4][2];
+      if (upd) {
+#pragma unroll
+        for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+          for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              int r, c;
+              tile_acc_rc(tid, mi, ni, e, r, c);
+              cold[mi][ni][e] = __ldcg(gC + c * BA_TB + r);
+            }
+      }
+      tile_load2<BA_LDS>(gA, sA, gB, sB, tid);
+      if (upd && (t.flags & 1) && tid < 64) sY[tid] = __ldcg(d.y + (size_t)t.k * BA_TB + tid);
+      __syncthreads();
+      TileAcc acc;
+      tile_gemm_dmma(sA, sB, (bk + 3) & ~3, tid, acc);
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            int r, c;
+            tile_acc_rc(tid, mi, ni, e, r, c);
+            gC[c * BA_TB + r] = upd ? (cold[mi][ni][e] - acc.c[mi][ni][e]) : acc.c[mi][ni][e];
+          }
+      if (upd && (t.flags & 1) && tid < 64) {
+        // b_i -= L_ik y_k (sequenced with the updates of the diagonal tile)
+        double s = 0;
+        for (int p = 0; p < bk; ++p) s = __fma_rn(sA[p * BA_LDS + tid], sY[p], s);
+        double* b = d.rhs + (size_t)t.i * BA_TB + tid;
+        *b = __ldcg(b) - s;
+      }
+    } else {  // BA_T_BWD: x_k = Linv_k^T (y_k - sum_i L_ik^T x_i)
+      if (tid < 64) sV[tid] = __ldcg(d.y + (size_t)t.k * BA_TB + tid);
+      for (int e0 = t.l0; e0 < t.l1; e0 += 8) {
+        const int ne = min(8, t.l1 - e0);
+        __syncthreads();
+        for (int q = tid; q < ne * BA_TB; q += BA_NTHREADS)
+          sX[q] = __ldcg(d.x + (size_t)d.bwd[e0 + (q >> 6)].blk * BA_TB + (q & 63));
+        __syncthreads();
+        double part = 0;
+#pragma unroll 2
+        for (int e = 0; e < ne; ++e)
+          part += tile_colT_dot(d.tiles + (size_t)d.bwd[e0 + e].tile * BA_TILE, sX + e * BA_TB, tid);
+        if ((tid & 3) == 0) sV[tid >> 2] -= part;
+      }
+      __syncthreads();
+      const double xv = tile_colT_dot(d.Linv + (size_t)t.k * BA_TILE, sV, tid);
+      if ((tid & 3) == 0) d.x[(size_t)t.k * BA_TB + (tid >> 2)] = xv;
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      red_release_add(d.cnt + t.done, 1);
+      if (d.trace) d.trace[4 * (size_t)ti + 3] = ba_globaltimer();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small systems (local BA: a handful of blocks): everything inside ONE CTA's shared memory,
+// dense column-major lower with leading dimension ns (rows of block k start at 60*k: every block
+// but the last is full when the plan has a single region).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ba_tile_small(BaTileDev d, const int* __restrict__ tileIdx, const int* __restrict__ blkRow0, int ns) {
+  extern __shared__ double sL[];
+  __shared__ int s_fail;
+  __shared__ double sx[1024];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int bj = 0; bj < d.nb; ++bj)
+    for (int bi = bj; bi < d.nb; ++bi) {
+      const int t = tileIdx[bi * d.nb + bj];
+      const int ri = d.blkRows[bi], rj = d.blkRows[bj], r0 = blkRow0[bi], c0 = blkRow0[bj];
+      for (int e = tid; e < ri * rj; e += nt) {
+        const int c = e / ri, r = e - c * ri;
+        const double v = (t >= 0) ? d.tiles[(size_t)t * BA_TILE + c * BA_TB + r] : 0.0;
+        sL[(c0 + c) * ns + r0 + r] = (r0 + r >= c0 + c) ? v : 0.0;
+      }
+    }
+  for (int bi = 0; bi < d.nb; ++bi)
+    for (int r = tid; r < d.blkRows[bi]; r += nt) sx[blkRow0[bi] + r] = d.rhs[(size_t)bi * BA_TB + r];
+  if (tid == 0) s_fail = 0;
+  __syncthreads();
+  for (int k = 0; k < ns; ++k) {
+    const double dkk = sL[k * ns + k];
+    if (!(dkk > 0) || !isfinite(dkk)) {
+      if (tid == 0) s_fail = 1;
+      break;  // uniform: every thread reads the same dkk
+    }
+    const double rs = 1.0 / sqrt(dkk);
+    __syncthreads();
+    for (int i = k + tid; i < ns; i += nt) sL[k * ns + i] = (i == k) ? sqrt(dkk) : sL[k * ns + i] * rs;
+    __syncthreads();
+    const int tj = tid >> 4, ti = tid & 15;
+    for (int j = k + 1 + tj; j < ns; j += 16) {
+      const double ljk = sL[k * ns + j];
+      for (int i = j + ti; i < ns; i += 16) sL[j * ns + i] -= sL[k * ns + i] * ljk;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (s_fail) {
+    if (tid == 0) d.sc[d.scFail] = 1.0;
+    return;
+  }
+  if (tid < 32) {
+    for (int k = 0; k < ns; ++k) {
+      const double xk = sx[k] / sL[k * ns + k];
+      __syncwarp();
+      if (tid == 0) sx[k] = xk;
+      for (int i = k + 1 + tid; i < ns; i += 32) sx[i] -= sL[k * ns + i] * xk;
+      __syncwarp();
+    }
+    for (int k = ns - 1; k >= 0; --k) {
+      double part = 0;
+      for (int i = k + 1 + tid; i < ns; i += 32) part += sL[k * ns + i] * sx[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+      __syncwarp();
+      if (tid == 0) sx[k] = (sx[k] - part) / sL[k * ns + k];
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int bi = 0; bi < d.nb; ++bi)
+    for (int r = tid; r < BA_TB; r += nt)
+      d.x[(size_t)bi * BA_TB + r] = (r < d.blkRows[bi]) ? sx[blkRow0[bi] + r] : 0.0;
+}
+
+}  // namespace coslam

@@ -275,10 +275,20 @@ const char* cosl_ba_solver_timer(cosl_ba_solver* s, int idx, double* ms, int* ca
 /* enable(1) resets and starts accumulating the per-kernel-class timers above. */
 int cosl_ba_solver_profile_enable(cosl_ba_solver* s, int on);
 /* Structure of the reduced camera system, for the roofline arithmetic of bench.py:
- * out[0] = order ns, out[1] = doubles inside the block envelope (what is cleared, all-reduced and
- * factored), out[2] = flops of the skyline Cholesky (sum over columns of height^2; ns^3/3 when
- * dense), out[3] = Schur pair entries, out[4] = pair work items, out[5..7] reserved (0). */
+ * out[0] = order ns, out[1] = doubles in the all-reduce payload [rhs | Schur-structure tiles],
+ * out[2] = multiply-adds of the tile Cholesky + substitutions on the used rows (ns^3/3 for the
+ * single-CTA small solve), out[3] = Schur pair entries, out[4] = pair work items, out[5] = blocks,
+ * out[6] = tiles incl. fill, out[7] = tasks of the solve DAG. */
 int cosl_ba_solver_stats(cosl_ba_solver* s, double out[8]);
+/* Plan of the reduced-system solve: out = {blocks, Schur-structure tiles, tiles incl. fill, tasks,
+ * nested-dissection depth, longest dependency chain (tasks), persistent grid size, small-solve}. */
+int cosl_ba_solver_plan_info(cosl_ba_solver* s, int out[8]);
+/* Diagnostic timeline of the persistent solve kernel.  enable != 0: arm tracing for the following
+ * solves (returns the task count).  enable == 0: copy the timeline of the LAST solve into
+ * out[cap][4] = {SM id, globaltimer ns at ticket, when operands were ready, when done} and
+ * meta[cap][3] = {task type 0 POTRF / 1 TRSM / 2 UPDATE / 3 BACKWARD, pivot block, row block},
+ * then disarm. */
+int cosl_ba_solver_trace(cosl_ba_solver* s, int enable, uint64_t* out, int32_t* meta, int cap);
 
 #ifdef __cplusplus
 }
