@@ -1,8 +1,11 @@
 /*
  * pose_oracle.cpp -- CPU restatement of the reference's per-frame 6-DoF pose refinement
- * (TEST INFRASTRUCTURE, see oracle.h).  PARITY UNPINNED (the reference has no tests for it; the
- * algorithm is fully in-tree, the primitives project/matInv/mat33AB come from LibVisualSLAM and
- * are restated from their use).
+ * (TEST INFRASTRUCTURE, see oracle.h).  PARITY PINNED: the unmodified reference file
+ * slam/SL_IntraCamPose.cpp is compiled here into oracle/_ref/libintracam_ref.so (oracle/Makefile
+ * target `ref`; only the 7 LibVisualSLAM primitives project/matATB/matAB/matInv/mat33AB/
+ * reprojError2/doubleArrCopy are supplied by oracle/ref_stubs/primitives.cpp, restated from their
+ * use) and this restatement reproduces its intraCamEstimate BIT FOR BIT: 40 seeded live cases +
+ * the committed reference-generated vectors tests/golden/pose_ref.npz (tests/test_pose_ref.py).
  *
  * Follows /root/reference/src/slam/SL_IntraCamPose.cpp:
  *   so3_exp            getSO3ExpMap                 :10-39
