@@ -22,3 +22,9 @@ class Point3d {
   Point3d() : x(0), y(0), z(0) {}
   Point3d(double x_, double y_, double z_) : x(x_), y(y_), z(z_) {}
 };
+class Point3dId : public Point3d {
+ public:
+  int id;
+  Point3dId() : Point3d(), id(-1) {}
+  Point3dId(double x_, double y_, double z_, int id_) : Point3d(x_, y_, z_), id(id_) {}
+};

@@ -4,6 +4,7 @@
 #pragma once
 #include <cstring>
 #include <vector>
+using std::vector;  // LibVisualSLAM headers leak std names; the reference relies on it (slam/SL_MapPoint.h:131)
 template <class T>
 class MyMat {
  public:
