@@ -404,9 +404,9 @@ class BaSolver:
         return int(LIB.cosl_ba_solver_trace(self.h, 1, None, None, 0))
 
     def trace_get(self):
-        """Timeline of the last persistent solve: (times [n,4] uint64, meta [n,3] int32)."""
+        """Timeline of the last persistent solve: (times [n,8] uint64, meta [n,3] int32)."""
         n = self.plan_info()["tasks"]
-        tm = np.zeros((n, 4), np.uint64)
+        tm = np.zeros((n, 8), np.uint64)
         meta = np.zeros((n, 3), np.int32)
         LIB.cosl_ba_solver_trace(self.h, 0, _ptr(tm), _ptr(meta), n)
         return tm, meta

@@ -99,6 +99,8 @@ struct cosl_ba_solver {
   int* d_cnt = nullptr;
   BaTask* d_tasks = nullptr;
   BaBwdEntry* d_bwd = nullptr;
+  BaSumEntry* d_sum = nullptr;
+  double* d_rhsS = nullptr;
   int *d_blkRows = nullptr, *d_blkRow0 = nullptr, *d_tileIdx = nullptr, *d_diagBlk = nullptr,
       *d_blkCam0 = nullptr, *d_order = nullptr, *d_solIdx = nullptr;
   BaTileDev td;
@@ -268,7 +270,7 @@ void free_solver(cosl_ba_solver* s) {
                   s->d_V, s->d_eb, s->d_Uea, s->d_S, s->d_y, s->d_x, s->d_sc, s->d_outlier,
                   s->d_items, s->d_entries, s->d_Linv, s->d_cnt, s->d_tasks, s->d_bwd, s->d_blkRows,
                   s->d_blkRow0, s->d_tileIdx, s->d_diagBlk, s->d_blkCam0, s->d_order, s->d_solIdx,
-                  s->d_trace};
+                  s->d_trace, s->d_sum, s->d_rhsS};
   for (void* b : bufs)
     if (b) cudaFreeAsync(b, s->stream);
   if (s->stream) cudaStreamSynchronize(s->stream);
@@ -446,7 +448,9 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   const size_t rhsLen = (size_t)nb * BA_TB;
   s->reduceCount = (long long)rhsLen + (long long)P.nTilesOrig * BA_TILE;
   s->factorFlops = P.flops;
-  COSL_TRY(dev_alloc(s->stream, &s->d_S, rhsLen + (size_t)nTiles * BA_TILE));
+  COSL_TRY(dev_alloc(s->stream, &s->d_S, rhsLen + ((size_t)nTiles + P.nScratch) * BA_TILE));
+  COSL_TRY(dev_alloc(s->stream, &s->d_rhsS, (size_t)std::max(1, P.nScratch) * BA_TB));
+  COSL_TRY(dev_alloc(s->stream, &s->d_sum, P.sumList.size()));
   COSL_TRY(dev_alloc(s->stream, &s->d_Linv, (size_t)nb * BA_TILE));
   COSL_TRY(dev_alloc(s->stream, &s->d_y, rhsLen));
   COSL_TRY(dev_alloc(s->stream, &s->d_x, rhsLen));
@@ -486,6 +490,7 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   if (nEntries) UP(s->d_entries, entries.data(), sizeof(int2) * (size_t)nEntries);
   if (!P.tasks.empty()) UP(s->d_tasks, P.tasks.data(), sizeof(BaTask) * P.tasks.size());
   if (!P.bwdList.empty()) UP(s->d_bwd, P.bwdList.data(), sizeof(BaBwdEntry) * P.bwdList.size());
+  if (!P.sumList.empty()) UP(s->d_sum, P.sumList.data(), sizeof(BaSumEntry) * P.sumList.size());
   if (P.nb) {
     UP(s->d_blkRows, P.blkRows.data(), sizeof(int) * P.nb);
     UP(s->d_tileIdx, P.tileIdx.data(), sizeof(int) * (size_t)P.nb * P.nb);
@@ -533,6 +538,9 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   td.cnt = s->d_cnt;
   td.tasks = s->d_tasks;
   td.bwd = s->d_bwd;
+  td.sum = s->d_sum;
+  td.rhsS = s->d_rhsS;
+  td.xdoneBase = P.nTiles + P.nScratch;
   td.blkRows = s->d_blkRows;
   td.nTasks = (int)P.tasks.size();
   td.nb = P.nb;
@@ -1037,20 +1045,20 @@ int cosl_ba_solver_plan_info(cosl_ba_solver* s, int out[8]) {
 }
 
 // diagnostic: per-task timeline of the LAST persistent solve launch.  enable -> run -> get.
-// out: [nTasks][4] = sm id, globaltimer ns at ticket / operands ready / done; meta: [nTasks][3] =
+// out: [nTasks][8] = sm id, globaltimer ns at ticket / operands ready / done, 4 phase stamps; meta: [nTasks][3] =
 // task type, pivot block k, row block i.
 int cosl_ba_solver_trace(cosl_ba_solver* s, int enable, uint64_t* out, int32_t* meta, int cap) {
   BA_ENTER(s)
   const int nt = (int)s->plan.tasks.size();
   if (enable) {
-    if (!s->d_trace) COSL_TRY(dev_alloc(s->stream, &s->d_trace, (size_t)std::max(1, nt) * 4));
-    COSL_CUDA(cudaMemsetAsync(s->d_trace, 0, sizeof(unsigned long long) * 4 * std::max(1, nt), s->stream));
+    if (!s->d_trace) COSL_TRY(dev_alloc(s->stream, &s->d_trace, (size_t)std::max(1, nt) * 8));
+    COSL_CUDA(cudaMemsetAsync(s->d_trace, 0, sizeof(unsigned long long) * 8 * std::max(1, nt), s->stream));
     s->td.trace = s->d_trace;
     return nt;
   }
   if (out && s->d_trace) {
     const int n = std::min(cap, nt);
-    COSL_CUDA(cudaMemcpyAsync(out, s->d_trace, sizeof(uint64_t) * 4 * n, cudaMemcpyDeviceToHost, s->stream));
+    COSL_CUDA(cudaMemcpyAsync(out, s->d_trace, sizeof(uint64_t) * 8 * n, cudaMemcpyDeviceToHost, s->stream));
     COSL_CUDA(cudaStreamSynchronize(s->stream));
     if (meta)
       for (int t = 0; t < n; ++t) {

@@ -18,10 +18,16 @@
 //        TRSM(i,k)  : L_ik = A_ik Linv_k^T
 //        UPD(i,j,k) : A_ij -= L_ik L_jk^T   (i == j: also b_i -= L_ik y_k)
 //        BWD(k)     : x_k = Linv_k^T (y_k - sum_i L_ik^T x_i)
-//      with per-tile completion counters (updates of one tile are sequenced in k order, so the
-//      result is deterministic) and a critical-path-first (bottom-level) list order that is also
-//      a topological order: CTAs take tasks by an atomic ticket and spin on the counters, which
-//      cannot deadlock because every dependency of a task precedes it in the list.
+//        SUM(i,j)   : A_ij += sum_g scratch_g(i,j)   (multifrontal-style extend-add, see below)
+//      with per-tile completion counters (the updates of one tile are applied in ONE fixed order,
+//      so the result is deterministic) and a critical-path-first (bottom-level) list order that
+//      is also a topological order: CTAs take tasks by an atomic ticket and spin on the counters,
+//      which cannot deadlock because every dependency of a task precedes it in the list.
+//      A separator tile receives an update from every block of every region below it; applied to
+//      the tile itself they would form one chain of ~nb read-modify-writes.  Updates whose pivot
+//      block lies in ANOTHER region than the target column are therefore accumulated in a scratch
+//      tile private to (target tile, pivot region) -- the regions proceed concurrently -- and one
+//      SUM task adds the scratch tiles to the target in a fixed order.
 #pragma once
 #include <algorithm>
 #include <cstdint>
@@ -34,19 +40,28 @@ constexpr int BA_TB = 64;                  // tile edge (storage)
 constexpr int BA_TILE = BA_TB * BA_TB;     // doubles per tile
 constexpr int BA_BLK_CAMS = 10;            // cameras per block (60 of the 64 tile rows are used)
 
-enum BaTaskType { BA_T_POTRF = 0, BA_T_TRSM = 1, BA_T_UPD = 2, BA_T_BWD = 3 };
+enum BaTaskType { BA_T_POTRF = 0, BA_T_TRSM = 1, BA_T_UPD = 2, BA_T_BWD = 3, BA_T_SUM = 4 };
 
 struct BaTask {  // 64 bytes, read by every thread of the CTA that executes it
-  int type, k, i, flags;  // flags bit 0: diagonal update (UPD with i == j) -> also updates b_i
+  // flags bit 0: diagonal tile (UPD with i == j / SUM of a diagonal tile) -> also handles b_i;
+  //       bit 1: UPD is the first one into a scratch tile -> overwrite instead of accumulate
+  int type, k, i, flags;
   int tC, tA, tB;         // tile indices: output tile; UPD: (i,k), (j,k); TRSM: tA = Linv index k
   int done;               // counter incremented on completion
   int w0i, w0v, w1i, w1v, w2i, w2v;  // wait until cnt[w?i] >= w?v (w?i < 0: unused)
-  int l0, l1;             // BWD: range in BaPlan::bwdList
+  // BWD: range in BaPlan::bwdList; SUM: range in BaPlan::sumList;
+  // UPD: l0 = scratch slot whose rhs vector receives the b_i part (-1: the real rhs of block i)
+  int l0, l1;
 };
 
 struct BaBwdEntry {
   int blk;   // block row i of struct(k)
   int tile;  // tile index of (i, k)
+};
+
+struct BaSumEntry {
+  int tile;   // scratch tile (index into the tile array, >= nTiles)
+  int count;  // updates it receives (its counter must reach this value)
 };
 
 struct BaPlan {
@@ -60,9 +75,12 @@ struct BaPlan {
   std::vector<int> tileIdx;  // nb*nb: tileIdx[i*nb + j], i >= j; -1 = structurally zero
   int nTilesOrig = 0;        // tiles the Schur contraction can touch (incl. all diagonal tiles)
   int nTiles = 0;            // + fill
+  int nScratch = 0;          // scratch tiles (tile indices nTiles .. nTiles + nScratch - 1)
+  std::vector<int> blkRegion;
+  std::vector<BaSumEntry> sumList;
   std::vector<BaTask> tasks; // in execution (ticket) order
   std::vector<BaBwdEntry> bwdList;
-  int nCounters = 0;         // nTiles tile counters + nb "x_k done" counters
+  int nCounters = 0;         // (nTiles + nScratch) tile counters + nb "x_k done" counters
   double flops = 0;          // 2 * (multiply-adds of the tile tasks, counted on the used rows)
   int criticalPathTasks = 0; // length (in tasks) of the longest dependency chain
   double criticalPathCost = 0;
@@ -161,9 +179,12 @@ inline BaPlan ba_make_plan(int mf, const std::vector<uint8_t>& adj, int ndDepthO
   nd_recurse(0, mf, depth, hiN, sepw, regions);
   // blocks: interiors are eliminated from both ends towards the middle, separators front to back
   std::vector<std::pair<int, int>> blocks;  // (first natural index, count) in elimination order
-  for (const Region& r : regions) {
+  std::vector<int> blockRegion;
+  for (size_t ri = 0; ri < regions.size(); ++ri) {
+    const Region& r = regions[ri];
     std::vector<std::pair<int, int>> nat;
     split_blocks(r.lo, r.hi - r.lo, nat);
+    for (size_t q = 0; q < nat.size(); ++q) blockRegion.push_back((int)ri);
     if (r.separator || !bandLike) {
       for (auto& b : nat) blocks.push_back(b);
     } else {
@@ -184,6 +205,7 @@ inline BaPlan ba_make_plan(int mf, const std::vector<uint8_t>& adj, int ndDepthO
   P.camOff.assign(mf, 0);
   P.blkRows.assign(nb, 0);
   P.blkCam0.assign(nb + 1, 0);
+  P.blkRegion = blockRegion;
   {
     int pos = 0;
     for (int k = 0; k < nb; ++k) {
@@ -225,18 +247,28 @@ inline BaPlan ba_make_plan(int mf, const std::vector<uint8_t>& adj, int ndDepthO
     for (int i = j; i < nb; ++i)
       if (st[(size_t)i * nb + j] && P.tileIdx[(size_t)i * nb + j] < 0) P.tileIdx[(size_t)i * nb + j] = nt++;
   P.nTiles = nt;
-  P.nCounters = nt + nb;
   // ---- 3. tasks ------------------------------------------------------------------------------
   // Generated pivot by pivot.  The updates of one tile commute mathematically but must be applied
   // in ONE fixed order (determinism, and no two CTAs may read-modify-write a tile at once).  Pivot
   // order would serialise a separator tile behind the slowest interior; instead the order follows
   // the estimated time at which each update's operands become available (pass 1 below).
   auto T = [&](int i, int j) { return P.tileIdx[(size_t)i * nb + j]; };
+  const bool useScratch = (regions.size() > 1) && (std::getenv("COSL_BA_NO_SCRATCH") == nullptr);
+  // scratch slot per (target tile, pivot region): created on first use
+  std::vector<std::vector<std::pair<int, int>>> scratchOf(nt);  // target tile -> (region, scratch tile)
+  int nScratch = 0;
+  auto scratchTile = [&](int tile, int region) {
+    for (auto& e : scratchOf[tile])
+      if (e.first == region) return e.second;
+    scratchOf[tile].push_back({region, nt + nScratch});
+    return nt + nScratch++;
+  };
   std::vector<BaTask> gen;
   std::vector<std::vector<int>> preds;  // predecessor task ids
   std::vector<double> cost;
-  std::vector<std::vector<int>> tileUpd(nt);  // UPD task ids per output tile
-  std::vector<int> finalTask(nt, -1);         // POTRF / TRSM task of a tile
+  std::vector<std::vector<int>> tileUpd;  // UPD task ids per output tile (real and scratch)
+  tileUpd.resize(nt);
+  std::vector<int> finalTask(nt, -1);     // POTRF / TRSM task of a real tile
   std::vector<int> potrfTask(nb, -1), bwdTask(nb, -1);
   auto blank = [] {
     BaTask t;
@@ -247,7 +279,7 @@ inline BaPlan ba_make_plan(int mf, const std::vector<uint8_t>& adj, int ndDepthO
     t.l0 = t.l1 = 0;
     return t;
   };
-  const double cPotrf = 9.0, cTrsm = 4.0, cUpd = 4.0, cBwd = 3.0;
+  const double cPotrf = 9.0, cTrsm = 4.0, cUpd = 4.0, cBwd = 3.0, cSum = 2.0;
   auto push = [&](const BaTask& t, double c) {
     gen.push_back(t);
     cost.push_back(c);
@@ -283,42 +315,106 @@ inline BaPlan ba_make_plan(int mf, const std::vector<uint8_t>& adj, int ndDepthO
     for (size_t b = 0; b < s.size(); ++b)
       for (size_t a = b; a < s.size(); ++a) {
         const int i = s[a], j = s[b], tij = T(i, j);
+        int target = tij;
+        if (useScratch && P.blkRegion[k] != P.blkRegion[j]) {
+          target = scratchTile(tij, P.blkRegion[k]);
+          if ((int)tileUpd.size() <= target) tileUpd.resize(target + 1);
+        }
         BaTask t = blank();
         t.type = BA_T_UPD;
         t.k = k;
         t.i = i;
         t.flags = (i == j) ? 1 : 0;
-        t.tC = t.done = t.w0i = tij;
+        t.tC = t.done = t.w0i = target;
         t.tA = t.w1i = T(i, k);
         t.tB = t.w2i = T(j, k);
+        t.l0 = (target == tij) ? -1 : target - nt;
         const int id = push(t, cUpd);
         preds[id].push_back(trsmTask[a]);
         if (a != b) preds[id].push_back(trsmTask[b]);
-        tileUpd[tij].push_back(id);
+        tileUpd[target].push_back(id);
         P.flops += 2.0 * P.blkRows[i] * (double)P.blkRows[j] * P.blkRows[k];
       }
   }
+  P.nScratch = nScratch;
+  const int ntAll = nt + nScratch;
+  tileUpd.resize(ntAll);
+  P.nCounters = ntAll + nb;
+  // SUM tasks: one per real tile that owns scratch tiles (generated after its contributors; the
+  // topological sort below puts it in place)
+  std::vector<int> sumTask(nt, -1);
+  for (int tl = 0; tl < nt; ++tl) {
+    if (scratchOf[tl].empty()) continue;
+    BaTask t = blank();
+    t.type = BA_T_SUM;
+    t.tC = t.done = t.w0i = tl;
+    t.w0v = 0;
+    // block coordinates of the tile (for the rhs of diagonal tiles)
+    sumTask[tl] = push(t, cSum);
+  }
+  for (int j = 0; j < nb; ++j)
+    for (int i = j; i < nb; ++i) {
+      const int tl = T(i, j);
+      if (tl >= 0 && sumTask[tl] >= 0) {
+        gen[sumTask[tl]].i = i;
+        gen[sumTask[tl]].k = j;
+        gen[sumTask[tl]].flags = (i == j) ? 1 : 0;
+      }
+    }
   const int nFactorTasks = (int)gen.size();
-  // pass 1: earliest finish with unlimited workers, updates of a tile treated as independent
-  std::vector<double> est(nFactorTasks, 0.0);
-  for (int t = 0; t < nFactorTasks; ++t) {  // generation order is topological for these edges
+  // pass 1: earliest finish with unlimited workers, updates of a tile treated as independent.
+  // Generation order is topological for POTRF/TRSM/UPD; SUM tasks sit at the end of `gen` but only
+  // depend on UPDs and only feed tasks of later pivots, so they are evaluated on demand.
+  std::vector<double> est(nFactorTasks, -1.0);
+  auto updDone = [&](int tile) {  // time when every update (and the SUM) of a real tile is in
+    double st = 0;
+    for (int u : tileUpd[tile]) st = std::max(st, est[u]);
+    if (sumTask[tile] >= 0) {
+      double ss = 0;
+      for (auto& e : scratchOf[tile])
+        for (int u : tileUpd[e.second]) ss = std::max(ss, est[u]);
+      est[sumTask[tile]] = ss + cSum;
+      st = std::max(st, est[sumTask[tile]]);
+    }
+    return st;
+  };
+  for (int t = 0; t < nFactorTasks; ++t) {
+    if (gen[t].type == BA_T_SUM) continue;
     double st = 0;
     for (int p : preds[t]) st = std::max(st, est[p]);
-    if (gen[t].type != BA_T_UPD)
-      for (int u : tileUpd[gen[t].tC]) st = std::max(st, est[u]);
+    if (gen[t].type != BA_T_UPD) st = std::max(st, updDone(gen[t].tC));
     est[t] = st + cost[t];
   }
-  // sequence the updates of every tile by operand-ready time; final wait values
-  std::vector<int> nupd(nt, 0);
-  for (int tl = 0; tl < nt; ++tl) {
+  // sequence the updates of every tile by operand-ready time; final wait values.  A real tile
+  // with scratch tiles takes its SUM as update number 0.
+  std::vector<int> nupd(ntAll, 0);
+  for (int tl = 0; tl < ntAll; ++tl) {
     auto& L = tileUpd[tl];
     std::stable_sort(L.begin(), L.end(), [&](int a, int b) { return est[a] < est[b]; });
+    const bool hasSum = tl < nt && sumTask[tl] >= 0;
+    const int base = hasSum ? 1 : 0;
     for (size_t q = 0; q < L.size(); ++q) {
-      gen[L[q]].w0v = (int)q;
+      gen[L[q]].w0v = base + (int)q;
       if (q > 0) preds[L[q]].push_back(L[q - 1]);
+      else if (hasSum) preds[L[q]].push_back(sumTask[tl]);
+      if (tl >= nt && q == 0) gen[L[q]].flags |= 2;  // first update of a scratch tile overwrites
     }
-    nupd[tl] = (int)L.size();
-    if (!L.empty() && finalTask[tl] >= 0) preds[finalTask[tl]].push_back(L.back());
+    nupd[tl] = base + (int)L.size();
+    if (tl < nt && finalTask[tl] >= 0) {
+      if (!L.empty()) preds[finalTask[tl]].push_back(L.back());
+      else if (hasSum) preds[finalTask[tl]].push_back(sumTask[tl]);
+    }
+  }
+  for (int tl = 0; tl < nt; ++tl) {
+    if (sumTask[tl] < 0) continue;
+    BaTask& g = gen[sumTask[tl]];
+    g.l0 = (int)P.sumList.size();
+    std::sort(scratchOf[tl].begin(), scratchOf[tl].end());
+    for (auto& e : scratchOf[tl]) {
+      P.sumList.push_back({e.second, nupd[e.second]});
+      preds[sumTask[tl]].push_back(tileUpd[e.second].back());
+    }
+    g.l1 = (int)P.sumList.size();
   }
   for (int t = 0; t < nFactorTasks; ++t) {
     BaTask& g = gen[t];
@@ -327,7 +423,7 @@ inline BaPlan ba_make_plan(int mf, const std::vector<uint8_t>& adj, int ndDepthO
     } else if (g.type == BA_T_TRSM) {
       g.w0v = nupd[g.tC];
       g.w1v = nupd[g.w1i] + 1;
-    } else {
+    } else if (g.type == BA_T_UPD) {
       g.w1v = nupd[g.tA] + 1;
       g.w2v = nupd[g.tB] + 1;
     }
@@ -338,7 +434,7 @@ inline BaPlan ba_make_plan(int mf, const std::vector<uint8_t>& adj, int ndDepthO
     t.k = t.i = k;
     t.tC = T(k, k);
     t.tA = k;
-    t.done = nt + k;
+    t.done = ntAll + k;
     t.w0i = T(k, k);
     t.w0v = nupd[T(k, k)] + 1;
     t.l0 = (int)P.bwdList.size();

@@ -25,18 +25,21 @@ namespace coslam {
 
 struct BaTileDev {
   double* rhs;    // [nb*64]
-  double* tiles;  // [nTiles][4096]
+  double* tiles;  // [nTiles + nScratch][4096]  (scratch tiles: see ba_plan.h)
+  double* rhsS;   // [nScratch*64] rhs parts that travel with the scratch tiles of diagonal tiles
   double* Linv;   // [nb][4096]
   double* y;      // [nb*64]
   double* x;      // [nb*64]
   int* cnt;       // [nCounters + 1]; the last one is the task ticket
   const BaTask* tasks;
   const BaBwdEntry* bwd;
+  const BaSumEntry* sum;
   const int* blkRows;
   int nTasks, nb, nTiles, nCounters;
+  int xdoneBase;  // counter index of "x_0 done" (= nTiles + nScratch)
   double* sc;
   int scFail;
-  unsigned long long* trace;  // optional [nTasks][4]: sm id, ns at ticket, ns when ready, ns when done
+  unsigned long long* trace;  // optional [nTasks][8]: sm id, ns at ticket / ready / done, 4 phase stamps
 };
 
 constexpr int BA_LDS = 68;                                   // smem leading dimension of a staged tile
@@ -352,8 +355,8 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
       if (d.trace) {
         unsigned int smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        d.trace[4 * (size_t)ti] = smid;
-        d.trace[4 * (size_t)ti + 1] = ba_globaltimer();
+        d.trace[8 * (size_t)ti] = smid;
+        d.trace[8 * (size_t)ti + 1] = ba_globaltimer();
       }
       if (t.w0i >= 0)
         while (ld_acquire(d.cnt + t.w0i) < t.w0v) {}
@@ -363,8 +366,11 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
         while (ld_acquire(d.cnt + t.w2i) < t.w2v) {}
       if (t.type == BA_T_BWD)
         for (int e = t.l0; e < t.l1; ++e)
-          while (ld_acquire(d.cnt + d.nTiles + d.bwd[e].blk) < 1) {}
-      if (d.trace) d.trace[4 * (size_t)ti + 2] = ba_globaltimer();
+          while (ld_acquire(d.cnt + d.xdoneBase + d.bwd[e].blk) < 1) {}
+      if (t.type == BA_T_SUM)
+        for (int e = t.l0; e < t.l1; ++e)
+          while (ld_acquire(d.cnt + d.sum[e].tile) < d.sum[e].count) {}
+      if (d.trace) d.trace[8 * (size_t)ti + 2] = ba_globaltimer();
     }
     __syncthreads();
     const int bk = d.blkRows[t.k];
@@ -391,8 +397,11 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
         }
       }
       __syncthreads();
+      if (d.trace && tid == 0) d.trace[8 * (size_t)ti + 4] = ba_globaltimer();
       tile_potrf(sA, bk, tid, &s_fail, sY);
+      if (d.trace && tid == 0) d.trace[8 * (size_t)ti + 5] = ba_globaltimer();
       tile_trinv(sA, sB, sC, sY, tid);
+      if (d.trace && tid == 0) d.trace[8 * (size_t)ti + 6] = ba_globaltimer();
       // Linv (column-major, padding rows/cols zero) and y = Linv b
       {
         double* g = d.Linv + (size_t)t.k * BA_TILE;
@@ -413,8 +422,9 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
       const double* gA = upd ? d.tiles + (size_t)t.tA * BA_TILE : gC;
       const double* gB = upd ? d.tiles + (size_t)t.tB * BA_TILE : d.Linv + (size_t)t.tA * BA_TILE;
       // C prefetch (independent of the operand staging: one round trip for everything)
+      const bool over = upd && (t.flags & 2);
       double cold[2][4][2];
-      if (upd) {
+      if (upd && !over) {
 #pragma unroll
         for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
@@ -429,8 +439,10 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
       tile_load2<BA_LDS>(gA, sA, gB, sB, tid);
       if (upd && (t.flags & 1) && tid < 64) sY[tid] = __ldcg(d.y + (size_t)t.k * BA_TB + tid);
       __syncthreads();
+      if (d.trace && tid == 0) d.trace[8 * (size_t)ti + 4] = ba_globaltimer();
       TileAcc acc;
       tile_gemm_dmma(sA, sB, (bk + 3) & ~3, tid, acc);
+      if (d.trace && tid == 0) d.trace[8 * (size_t)ti + 5] = ba_globaltimer();
 #pragma unroll
       for (int mi = 0; mi < 2; ++mi)
 #pragma unroll
@@ -439,38 +451,89 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
           for (int e = 0; e < 2; ++e) {
             int r, c;
             tile_acc_rc(tid, mi, ni, e, r, c);
-            gC[c * BA_TB + r] = upd ? (cold[mi][ni][e] - acc.c[mi][ni][e]) : acc.c[mi][ni][e];
+            gC[c * BA_TB + r] = upd ? ((over ? 0.0 : cold[mi][ni][e]) - acc.c[mi][ni][e]) : acc.c[mi][ni][e];
           }
       if (upd && (t.flags & 1) && tid < 64) {
         // b_i -= L_ik y_k (sequenced with the updates of the diagonal tile)
         double s = 0;
         for (int p = 0; p < bk; ++p) s = __fma_rn(sA[p * BA_LDS + tid], sY[p], s);
-        double* b = d.rhs + (size_t)t.i * BA_TB + tid;
-        *b = __ldcg(b) - s;
+        double* b = (t.l0 >= 0) ? d.rhsS + (size_t)t.l0 * BA_TB + tid : d.rhs + (size_t)t.i * BA_TB + tid;
+        *b = (over ? 0.0 : __ldcg(b)) - s;
       }
+    } else if (t.type == BA_T_SUM) {
+      // C += sum of the scratch tiles (fixed order); diagonal tiles also collect their rhs parts
+      double2* gC = reinterpret_cast<double2*>(d.tiles + (size_t)t.tC * BA_TILE);
+      double2 acc[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc[u] = __ldcg(gC + tid + BA_NTHREADS * u);
+      double rb = 0;
+      const bool dg = (t.flags & 1) && tid < 64;
+      if (dg) rb = __ldcg(d.rhs + (size_t)t.i * BA_TB + tid);
+      for (int e = t.l0; e < t.l1; ++e) {
+        const int st = d.sum[e].tile;
+        const double2* gS = reinterpret_cast<const double2*>(d.tiles + (size_t)st * BA_TILE);
+        double2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldcg(gS + tid + BA_NTHREADS * u);
+        if (dg) rb += __ldcg(d.rhsS + (size_t)(st - d.nTiles) * BA_TB + tid);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          acc[u].x += v[u].x;
+          acc[u].y += v[u].y;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) gC[tid + BA_NTHREADS * u] = acc[u];
+      if (dg) d.rhs[(size_t)t.i * BA_TB + tid] = rb;
     } else {  // BA_T_BWD: x_k = Linv_k^T (y_k - sum_i L_ik^T x_i)
       if (tid < 64) sV[tid] = __ldcg(d.y + (size_t)t.k * BA_TB + tid);
+      // thread (c = tid >> 2, q = tid & 3) accumulates rows 16q .. 16q+15 of column c over ALL
+      // entries and reduces once; the loads of four tiles are in flight together
+      const int c = tid >> 2, q = tid & 3;
+      double p0 = 0, p1 = 0;
       for (int e0 = t.l0; e0 < t.l1; e0 += 8) {
         const int ne = min(8, t.l1 - e0);
         __syncthreads();
-        for (int q = tid; q < ne * BA_TB; q += BA_NTHREADS)
-          sX[q] = __ldcg(d.x + (size_t)d.bwd[e0 + (q >> 6)].blk * BA_TB + (q & 63));
+        for (int u = tid; u < ne * BA_TB; u += BA_NTHREADS)
+          sX[u] = __ldcg(d.x + (size_t)d.bwd[e0 + (u >> 6)].blk * BA_TB + (u & 63));
         __syncthreads();
-        double part = 0;
-#pragma unroll 2
-        for (int e = 0; e < ne; ++e)
-          part += tile_colT_dot(d.tiles + (size_t)d.bwd[e0 + e].tile * BA_TILE, sX + e * BA_TB, tid);
-        if ((tid & 3) == 0) sV[tid >> 2] -= part;
+        for (int eb = 0; eb < ne; eb += 4) {
+          double2 v[4][8];
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int e = min(eb + w, ne - 1);
+            const double2* col = reinterpret_cast<const double2*>(
+                d.tiles + (size_t)d.bwd[e0 + e].tile * BA_TILE + c * BA_TB + 16 * q);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[w][u] = __ldcg(col + u);
+          }
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            if (eb + w < ne) {
+              const double* xv = sX + (eb + w) * BA_TB + 16 * q;
+#pragma unroll
+              for (int u = 0; u < 8; ++u) {
+                p0 = __fma_rn(v[w][u].x, xv[2 * u], p0);
+                p1 = __fma_rn(v[w][u].y, xv[2 * u + 1], p1);
+              }
+            }
+          }
+        }
       }
+      double part = p0 + p1;
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      __syncthreads();
+      if (q == 0) sV[c] -= part;
       __syncthreads();
       const double xv = tile_colT_dot(d.Linv + (size_t)t.k * BA_TILE, sV, tid);
-      if ((tid & 3) == 0) d.x[(size_t)t.k * BA_TB + (tid >> 2)] = xv;
+      if (q == 0) d.x[(size_t)t.k * BA_TB + c] = xv;
     }
     __threadfence();
     __syncthreads();
     if (tid == 0) {
       red_release_add(d.cnt + t.done, 1);
-      if (d.trace) d.trace[4 * (size_t)ti + 3] = ba_globaltimer();
+      if (d.trace) d.trace[8 * (size_t)ti + 3] = ba_globaltimer();
     }
   }
 }

@@ -285,8 +285,9 @@ int cosl_ba_solver_stats(cosl_ba_solver* s, double out[8]);
 int cosl_ba_solver_plan_info(cosl_ba_solver* s, int out[8]);
 /* Diagnostic timeline of the persistent solve kernel.  enable != 0: arm tracing for the following
  * solves (returns the task count).  enable == 0: copy the timeline of the LAST solve into
- * out[cap][4] = {SM id, globaltimer ns at ticket, when operands were ready, when done} and
- * meta[cap][3] = {task type 0 POTRF / 1 TRSM / 2 UPDATE / 3 BACKWARD, pivot block, row block},
+ * out[cap][8] = {SM id, globaltimer ns at ticket, when operands were ready, when done, up to 4
+ * phase stamps inside the task} and
+ * meta[cap][3] = {task type 0 POTRF / 1 TRSM / 2 UPDATE / 3 BACKWARD / 4 SUM, pivot block, row block},
  * then disarm. */
 int cosl_ba_solver_trace(cosl_ba_solver* s, int enable, uint64_t* out, int32_t* meta, int cap);
 

@@ -58,7 +58,10 @@ int main(int argc, char** argv) {
   BaPlan P = ba_make_plan(mf, adj, depth);
   const int nb = P.nb;
   // scatter into tiles (lower triangle in the PERMUTED order)
-  std::vector<double> S((size_t)P.nTiles * BA_TILE, 0.0), b((size_t)nb * BA_TB, 0.0);
+  const int ntAll = P.nTiles + P.nScratch;
+  // scratch tiles start with garbage: the first update must overwrite them
+  std::vector<double> S((size_t)ntAll * BA_TILE, 0.0), b((size_t)nb * BA_TB, 0.0), bS((size_t)std::max(1, P.nScratch) * BA_TB, 777.0);
+  for (size_t e = (size_t)P.nTiles * BA_TILE; e < S.size(); ++e) S[e] = 1e300;
   for (int a = 0; a < mf; ++a)
     for (int c = 0; c < mf; ++c) {
       if (!adj[(size_t)a * mf + c]) continue;
@@ -136,24 +139,48 @@ int main(int argc, char** argv) {
       double* C = tile(S, t.tC);
       const double* Ai = tile(S, t.tA);
       const double* Aj = tile(S, t.tB);
+      const bool over = (t.flags & 2) != 0;
+      if (over != (t.tC >= P.nTiles && cnt[t.tC] == 0)) {
+        std::printf("FAIL: overwrite flag inconsistent\n");
+        return 1;
+      }
       for (int r = 0; r < BA_TB; ++r)
         for (int c = 0; c < BA_TB; ++c) {
           double s = 0;
           for (int p = 0; p < bk; ++p) s += Ai[p * BA_TB + r] * Aj[p * BA_TB + c];
-          C[c * BA_TB + r] -= s;
+          C[c * BA_TB + r] = (over ? 0.0 : C[c * BA_TB + r]) - s;
         }
-      if (t.flags & 1)
+      if (t.flags & 1) {
+        double* bb = (t.l0 >= 0) ? &bS[(size_t)t.l0 * BA_TB] : &b[(size_t)t.i * BA_TB];
+        if ((t.l0 >= 0) != (t.tC >= P.nTiles)) {
+          std::printf("FAIL: rhs slot inconsistent\n");
+          return 1;
+        }
         for (int r = 0; r < BA_TB; ++r) {
           double s = 0;
           for (int p = 0; p < bk; ++p) s += Ai[p * BA_TB + r] * y[(size_t)t.k * BA_TB + p];
-          b[(size_t)t.i * BA_TB + r] -= s;
+          bb[r] = (over ? 0.0 : bb[r]) - s;
         }
+      }
+    } else if (t.type == BA_T_SUM) {
+      double* C = tile(S, t.tC);
+      for (int e = t.l0; e < t.l1; ++e) {
+        const BaSumEntry se = P.sumList[e];
+        if (cnt[se.tile] < se.count) {
+          std::printf("FAIL: SUM before its scratch tile %d is complete\n", se.tile);
+          return 1;
+        }
+        const double* Sc = tile(S, se.tile);
+        for (int q = 0; q < BA_TILE; ++q) C[q] += Sc[q];
+        if (t.flags & 1)
+          for (int r = 0; r < BA_TB; ++r) b[(size_t)t.i * BA_TB + r] += bS[(size_t)(se.tile - P.nTiles) * BA_TB + r];
+      }
     } else {  // BWD
       std::vector<double> v(BA_TB);
       for (int p = 0; p < BA_TB; ++p) v[p] = y[(size_t)t.k * BA_TB + p];
       for (int e = t.l0; e < t.l1; ++e) {
         const BaBwdEntry be = P.bwdList[e];
-        if (cnt[P.nTiles + be.blk] < 1) {
+        if (cnt[ntAll + be.blk] < 1) {
           std::printf("FAIL: BWD(%d) before x_%d\n", t.k, be.blk);
           return 1;
         }
@@ -202,10 +229,10 @@ int main(int argc, char** argv) {
       err = std::fmax(err, std::fabs(xv - xr[6 * a + r]));
       nrm = std::fmax(nrm, std::fabs(xr[6 * a + r]));
     }
-  std::printf("{\"mf\": %d, \"nb\": %d, \"nd_depth\": %d, \"tiles_orig\": %d, \"tiles\": %d, \"tasks\": %zu, "
-              "\"critical_tasks\": %d, \"critical_cost\": %.1f, \"gflop\": %.4f, \"rel_err\": %.3e}\n",
-              mf, nb, P.ndDepth, P.nTilesOrig, P.nTiles, P.tasks.size(), P.criticalPathTasks, P.criticalPathCost,
-              P.flops * 1e-9, err / nrm);
+  std::printf("{\"mf\": %d, \"nb\": %d, \"nd_depth\": %d, \"tiles_orig\": %d, \"tiles\": %d, \"scratch\": %d, "
+              "\"tasks\": %d, \"critical_tasks\": %d, \"critical_cost\": %.1f, \"gflop\": %.4f, \"rel_err\": %.3e}\n",
+              mf, nb, P.ndDepth, P.nTilesOrig, P.nTiles, P.nScratch, (int)P.tasks.size(), P.criticalPathTasks,
+              P.criticalPathCost, P.flops * 1e-9, err / nrm);
   if (!(err / nrm < 1e-9)) {
     std::printf("FAIL: solution differs\n");
     return 1;

@@ -22,15 +22,31 @@ s.run_fixed(1)
 tm, meta = s.trace_get()
 t0 = tm[:, 1].min()
 tick, ready, done = [(tm[:, k].astype(np.int64) - int(t0)) / 1e3 for k in (1, 2, 3)]
-names = ["POTRF", "TRSM", "UPD", "BWD"]
+names = ["POTRF", "TRSM", "UPD", "BWD", "SUM"]
 print(f"makespan {done.max():.1f} us, {len(tm)} tasks on {len(np.unique(tm[:, 0]))} SMs")
-for ty in range(4):
+for ty in range(5):
     m = meta[:, 0] == ty
     if m.any():
         ex = done[m] - ready[m]
         wt = ready[m] - tick[m]
         print(f"{names[ty]:6s} n {m.sum():5d}  exec us: mean {ex.mean():6.2f} p50 {np.median(ex):6.2f} max {ex.max():6.2f}"
               f"   wait us: mean {wt.mean():7.2f} max {wt.max():7.2f}")
+        ph = tm[m][:, 4:8].astype(np.int64)
+        if (ph[:, 0] > 0).any():
+            rd = tm[m][:, 2].astype(np.int64)
+            dn = tm[m][:, 3].astype(np.int64)
+            segs = [ph[:, 0] - rd]
+            for k in range(1, 4):
+                if (ph[:, k] > 0).any():
+                    segs.append(ph[:, k] - ph[:, k - 1])
+                    last = ph[:, k]
+                else:
+                    break
+            else:
+                last = ph[:, 3]
+            last = ph[:, max(k for k in range(4) if (ph[:, k] > 0).any())]
+            segs.append(dn - last)
+            print("       phases us (mean):", [round(float(np.mean(sg)) / 1e3, 2) for sg in segs])
 # chain: walk back from the last task through the latest-finishing task that ended before ready
 order = np.argsort(done)
 cur = int(np.argmax(done))
