@@ -82,6 +82,7 @@ def _load():
     L.cosl_ba_solver_stats.argtypes = [vp, C.POINTER(cd)]
     L.cosl_ba_solver_plan_info.argtypes = [vp, pint]
     L.cosl_ba_solver_trace.argtypes = [vp, ci, vp, vp, ci]
+    L.cosl_ba_solver_tasks.argtypes = [vp, vp, ci, vp, ci]
     return L
 
 
@@ -399,6 +400,14 @@ class BaSolver:
         keys = ("blocks", "tiles_schur", "tiles", "tasks", "nd_depth", "critical_tasks", "grid",
                 "small_solve")
         return dict(zip(keys, [int(v) for v in out]))
+
+    def tasks(self):
+        """Task list of the solve plan: (tasks [n,16] int32, wait lists [m,2] int32)."""
+        n = self.plan_info()["tasks"]
+        t = np.zeros((n, 16), np.int32)
+        lst = np.zeros((64 * n + 16, 2), np.int32)
+        LIB.cosl_ba_solver_tasks(self.h, _ptr(t), n, _ptr(lst), len(lst))
+        return t, lst
 
     def trace_arm(self):
         return int(LIB.cosl_ba_solver_trace(self.h, 1, None, None, 0))

@@ -1071,6 +1071,33 @@ int cosl_ba_solver_trace(cosl_ba_solver* s, int enable, uint64_t* out, int32_t* 
   return nt;
 }
 
+// diagnostic: the task list of the solve plan, 16 ints per task (BaTask of ba_plan.h), and the
+// BACKWARD / SUM wait lists flattened as (counter index, required value) pairs in `lists`, with
+// tasks[.].l0/l1 of those two task types rewritten to index into it.  Returns the task count.
+int cosl_ba_solver_tasks(cosl_ba_solver* s, int32_t* tasks, int cap, int32_t* lists, int listCap) {
+  if (!s) return set_error(COSL_E_INVALID, "null solver handle");
+  const BaPlan& P = s->plan;
+  const int nt = (int)P.tasks.size();
+  int nl = 0;
+  for (int t = 0; t < nt && t < cap; ++t) {
+    BaTask k = P.tasks[t];
+    if (k.type == BA_T_BWD || k.type == BA_T_SUM) {
+      const int l0 = nl;
+      for (int e = k.l0; e < k.l1; ++e) {
+        if (lists && nl < listCap) {
+          lists[2 * nl] = (k.type == BA_T_BWD) ? P.nTiles + P.nScratch + P.bwdList[e].blk : P.sumList[e].tile;
+          lists[2 * nl + 1] = (k.type == BA_T_BWD) ? 1 : P.sumList[e].count;
+        }
+        ++nl;
+      }
+      k.l0 = l0;
+      k.l1 = nl;
+    }
+    if (tasks) std::memcpy(tasks + 16 * (size_t)t, &k, sizeof(BaTask));
+  }
+  return nt;
+}
+
 int cosl_ba_solver_profile_enable(cosl_ba_solver* s, int on) {
   BA_ENTER(s)
   COSL_CUDA(cudaStreamSynchronize(s->stream));

@@ -43,7 +43,7 @@ struct BaTileDev {
 };
 
 constexpr int BA_LDS = 68;                                   // smem leading dimension of a staged tile
-constexpr int BA_TILE_SMEM_DOUBLES = 3 * BA_TB * BA_LDS + 8 * BA_TB + 2 * BA_TB;
+constexpr int BA_TILE_SMEM_DOUBLES = 3 * BA_TB * BA_LDS + 8 * BA_TB + 8 * BA_TB + 2 * BA_TB + 80;
 constexpr int BA_TILE_SMEM = BA_TILE_SMEM_DOUBLES * (int)sizeof(double);
 constexpr int BA_NTHREADS = 256;
 
@@ -327,6 +327,220 @@ __device__ __forceinline__ double tile_colT_dot(const double* __restrict__ G, co
   return s;
 }
 
+// =============================================================================================
+// Version 2 of the diagonal-block path: no explicit 64x64 inverse.
+//   POTRF2 : factor with 8-column panels and LOOK-AHEAD: warps 0-1 ("panel warps", thread = row)
+//            own the pivot chain -- they factor the 8x8 diagonal block redundantly in registers,
+//            solve their row of the panel, and apply the rank-8 update to the NEXT panel's columns
+//            themselves (kept in registers) -- while warps 2-7 apply it to the rest of the trailing
+//            triangle and to the right-hand side, off the chain.  One CTA barrier + one 64-thread
+//            named barrier per panel.  Outputs: L (lower, in place), the inverses M_b of the eight
+//            8x8 diagonal blocks of L, and y = L^-1 b.
+//   TRSM2  : X L^T = A by blocked substitution over the 8 column blocks; every warp owns 8 rows and
+//            needs no CTA barrier: T_b = A_b - X_{<b} L_{b,<b}^T and X_b = T_b M_b^T are DMMA m8n8k4
+//            products (2b + 2 per block).
+//   BWD2   : x = L^-T v by the same blocking, one warp.
+// =============================================================================================
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// sT: tile staged column-major with ld BA_LDS (element (r, c) at c*BA_LDS + r), lower part valid,
+// identity on the padding.  sBv: right-hand side (64); sYv: y out (64); sM: [8][8][8] M_b[q][q']
+// out; sD: 72 doubles scratch.
+__device__ __forceinline__ void tile_potrf2(double* __restrict__ sT, double* __restrict__ sBv,
+                                            double* __restrict__ sYv, double* __restrict__ sM,
+                                            double* __restrict__ sD, int tid, int* s_fail) {
+  const bool isP = tid < 64;
+  const int r = tid;
+  double a[8], x[8];
+  double br = isP ? sBv[r] : 0.0;  // this row's right-hand side, updated along with the look-ahead
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    a[q] = isP ? sT[q * BA_LDS + r] : 0.0;
+    x[q] = 0.0;
+  }
+#pragma unroll 1
+  for (int pb = 0; pb < 8; ++pb) {
+    const int c0 = 8 * pb;
+    if (isP) {
+      if (r >= c0 && r < c0 + 8) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sD[(r - c0) * 8 + q] = a[q];
+        sD[64 + r - c0] = br;
+      }
+      named_bar_sync(1, 64);
+      double D[8][8], inv[8], bb[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) D[i][j] = sD[i * 8 + j];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) bb[q] = sD[64 + q];
+      bool bad = false;
+#pragma unroll
+      for (int p = 0; p < 8; ++p) {
+        double dd = D[p][p];
+        if (!(dd > 0) || !isfinite(dd)) {
+          bad = true;
+          dd = 1.0;
+        }
+        const double rs = ba_rsqrt_fast(dd);
+        inv[p] = rs;
+        D[p][p] = dd * rs;
+#pragma unroll
+        for (int i = p + 1; i < 8; ++i) D[i][p] *= rs;
+#pragma unroll
+        for (int j = p + 1; j < 8; ++j)
+#pragma unroll
+          for (int i = j; i < 8; ++i) D[i][j] = __fma_rn(-D[i][p], D[j][p], D[i][j]);
+      }
+      // y of this panel (every panel thread computes it; thread 0 publishes)
+      {
+        double yv[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          double s = bb[q];
+#pragma unroll
+          for (int p = 0; p < q; ++p) s = __fma_rn(-D[q][p], yv[p], s);
+          yv[q] = s * inv[q];
+        }
+        if (r == 0) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) sYv[c0 + q] = yv[q];
+          if (bad) *s_fail = 1;
+        }
+      }
+      if (r >= c0 + 8) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          double s = a[q];
+#pragma unroll
+          for (int p = 0; p < q; ++p) s = __fma_rn(-x[p], D[q][p], s);
+          x[q] = s * inv[q];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sT[(c0 + q) * BA_LDS + r] = x[q];
+      } else if (r >= c0) {
+        const int cc = r - c0;
+        double m[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          double v = 0.0;
+#pragma unroll
+          for (int aa = 0; aa < 8; ++aa)
+            if (aa == cc && q <= aa) v = D[aa][q];
+          sT[(c0 + q) * BA_LDS + r] = v;  // row cc of the factored diagonal block, zeros above
+          double s = (q == cc) ? 1.0 : 0.0;  // column cc of M = inverse of the 8x8 factor
+#pragma unroll
+          for (int p = 0; p < q; ++p) s = __fma_rn(-D[q][p], m[p], s);
+          m[q] = s * inv[q];
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) sM[pb * 64 + q * 8 + cc] = m[q];
+      }
+    }
+    __syncthreads();  // X and y of this panel are visible; the update warps finished the previous panel
+    if (pb == 7) break;
+    if (isP) {
+      if (r >= c0 + 8) {  // look-ahead: next panel's columns of this row, kept in registers
+#pragma unroll
+        for (int qn = 0; qn < 8; ++qn) a[qn] = sT[(c0 + 8 + qn) * BA_LDS + r];
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+#pragma unroll
+          for (int qn = 0; qn < 8; ++qn) a[qn] = __fma_rn(-x[q], sT[(c0 + q) * BA_LDS + c0 + 8 + qn], a[qn]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) br = __fma_rn(-x[q], sYv[c0 + q], br);  // b_r -= X(r, :) y_panel
+      }
+    } else {
+      const int u = tid - 64;  // 0 .. 191
+      // trailing lower triangle right of the NEXT panel: rows ti + 16a, columns tj + 12b
+      const int ti = u & 15, tj = u >> 4;
+      if (c0 + 16 < 64) {
+        double xi[4][8];
+#pragma unroll
+        for (int aa = 0; aa < 4; ++aa)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) xi[aa][q] = sT[(c0 + q) * BA_LDS + ti + 16 * aa];
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+          const int j = tj + 12 * b;
+          if (j >= c0 + 16 && j < 64) {
+            double xj[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) xj[q] = sT[(c0 + q) * BA_LDS + j];
+#pragma unroll
+            for (int aa = 0; aa < 4; ++aa) {
+              const int i = ti + 16 * aa;
+              if (i >= j) {
+                double s = sT[j * BA_LDS + i];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) s = __fma_rn(-xi[aa][q], xj[q], s);
+                sT[j * BA_LDS + i] = s;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// X L^T = A in place in sA (rows = this warp's 8 rows; ld BA_LDS); sL: L staged like sA; sM: M_b.
+// nbk = number of 8-column blocks to process.
+__device__ __forceinline__ void tile_trsm2(double* __restrict__ sA, const double* __restrict__ sL,
+                                           const double* __restrict__ sM, int nbk, int tid) {
+  const int lane = tid & 31, w = tid >> 5;
+  const int rb = 8 * w, lr = lane >> 2, lk = lane & 3;
+  for (int b = 0; b < nbk; ++b) {
+    double c0 = 0.0, c1 = 0.0;
+    for (int p0 = 0; p0 < 8 * b; p0 += 4) {
+      const double av = sA[(p0 + lk) * BA_LDS + rb + lr];         // X(row, p)
+      const double bv = sL[(p0 + lk) * BA_LDS + 8 * b + lr];      // L(8b + n, p)
+      dmma884(c0, c1, av, bv);
+    }
+    // T = A_b - acc, written over A_b (C layout: row lr, columns 2 lk, 2 lk + 1)
+    double* t0 = sA + (8 * b + 2 * lk) * BA_LDS + rb + lr;
+    t0[0] -= c0;
+    t0[BA_LDS] -= c1;
+    __syncwarp();
+    const double a0 = sA[(8 * b + lk) * BA_LDS + rb + lr], a1 = sA[(8 * b + 4 + lk) * BA_LDS + rb + lr];
+    const double m0 = sM[b * 64 + lr * 8 + lk], m1 = sM[b * 64 + lr * 8 + 4 + lk];  // B(k, n) = M(n, k)
+    double x0 = 0.0, x1 = 0.0;
+    dmma884(x0, x1, a0, m0);
+    dmma884(x0, x1, a1, m1);
+    __syncwarp();
+    t0[0] = x0;
+    t0[BA_LDS] = x1;
+    __syncwarp();
+  }
+}
+
+// x = L^-T v, one warp (call with the whole warp 0): sL staged tile (lower), sM the M_b, sv in/out.
+__device__ __forceinline__ void tile_bwd2(const double* __restrict__ sL, const double* __restrict__ sM,
+                                          double* __restrict__ sv, int nbk, int lane) {
+  const int q = lane >> 2, part = lane & 3;  // output q of the block, 4-way split of the dot
+  for (int b = nbk - 1; b >= 0; --b) {
+    // t_q = v(8b + q) - sum_{p >= 8b + 8} L(p, 8b + q) x(p)
+    double s = 0;
+    for (int p = 8 * b + 8 + part; p < 8 * nbk; p += 4) s = __fma_rn(sL[(8 * b + q) * BA_LDS + p], sv[p], s);
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    const double tq = sv[8 * b + q] - s;
+    // x_q = sum_{q' >= q} M(q', q) t_q'
+    double xq = 0;
+#pragma unroll
+    for (int qq = 0; qq < 8; ++qq) {
+      const double tv = __shfl_sync(0xffffffffu, tq, 4 * qq);
+      xq = __fma_rn(sM[b * 64 + qq * 8 + q], tv, xq);  // M is lower: entries with qq < q are zero
+    }
+    __syncwarp();
+    if (part == 0) sv[8 * b + q] = xq;
+    __syncwarp();
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // The persistent dataflow kernel.
 // ---------------------------------------------------------------------------------------------
@@ -336,8 +550,10 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
   double* sB = sA + BA_TB * BA_LDS;        // [64][68]
   double* sC = sB + BA_TB * BA_LDS;        // [64][68]
   double* sX = sC + BA_TB * BA_LDS;        // [8][64] x vectors of a BWD chunk
-  double* sV = sX + 8 * BA_TB;             // [64]
+  double* sM = sX + 8 * BA_TB;             // [8][8][8] inverses of the diagonal 8x8 blocks
+  double* sV = sM + 8 * BA_TB;             // [64]
   double* sY = sV + BA_TB;                 // [64]
+  double* sD = sY + BA_TB;                 // [72] panel scratch of tile_potrf2
   __shared__ int s_task, s_fail;
   const int tid = threadIdx.x;
   int* const ticket = d.cnt + d.nCounters;
@@ -351,31 +567,33 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
     const int ti = s_task;
     if (ti >= d.nTasks) break;
     const BaTask t = d.tasks[ti];
-    if (tid == 0) {
-      if (d.trace) {
+    if (tid < 32) {
+      if (tid == 0 && d.trace) {
         unsigned int smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         d.trace[8 * (size_t)ti] = smid;
         d.trace[8 * (size_t)ti + 1] = ba_globaltimer();
       }
-      if (t.w0i >= 0)
+      // the lanes of warp 0 poll different counters concurrently
+      if (tid == 0 && t.w0i >= 0)
         while (ld_acquire(d.cnt + t.w0i) < t.w0v) {}
-      if (t.w1i >= 0)
+      if (tid == 1 && t.w1i >= 0)
         while (ld_acquire(d.cnt + t.w1i) < t.w1v) {}
-      if (t.w2i >= 0)
+      if (tid == 2 && t.w2i >= 0)
         while (ld_acquire(d.cnt + t.w2i) < t.w2v) {}
       if (t.type == BA_T_BWD)
-        for (int e = t.l0; e < t.l1; ++e)
+        for (int e = t.l0 + tid; e < t.l1; e += 32)
           while (ld_acquire(d.cnt + d.xdoneBase + d.bwd[e].blk) < 1) {}
       if (t.type == BA_T_SUM)
-        for (int e = t.l0; e < t.l1; ++e)
+        for (int e = t.l0 + tid; e < t.l1; e += 32)
           while (ld_acquire(d.cnt + d.sum[e].tile) < d.sum[e].count) {}
-      if (d.trace) d.trace[8 * (size_t)ti + 2] = ba_globaltimer();
+      __syncwarp();
+      if (tid == 0 && d.trace) d.trace[8 * (size_t)ti + 2] = ba_globaltimer();
     }
     __syncthreads();
     const int bk = d.blkRows[t.k];
     if (t.type == BA_T_POTRF) {
-      // stage the lower part, identity on the padding
+      // stage the lower part (ld BA_LDS), identity on the padding; b into sV
       {
         const double* g = d.tiles + (size_t)t.tC * BA_TILE;
         double2 v[8];
@@ -385,42 +603,52 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
         for (int u = 0; u < 8; ++u) {
           const int e = 2 * (tid + BA_NTHREADS * u);
           const int c = e >> 6, r = e & 63;
-          double a = v[u].x, b = v[u].y;
-          if (r >= bk || c >= bk) a = (r == c) ? 1.0 : 0.0;
-          if (r + 1 >= bk || c >= bk) b = (r + 1 == c) ? 1.0 : 0.0;
-          sA[c * BA_LDP + r] = a;
-          sA[c * BA_LDP + r + 1] = b;
+          double2 w = v[u];
+          if (r >= bk || c >= bk) w.x = (r == c) ? 1.0 : 0.0;
+          if (r + 1 >= bk || c >= bk) w.y = (r + 1 == c) ? 1.0 : 0.0;
+          *reinterpret_cast<double2*>(sA + c * BA_LDS + r) = w;
         }
-        if (tid < 64) {
-          sV[tid] = (tid < bk) ? __ldcg(d.rhs + (size_t)t.k * BA_TB + tid) : 0.0;
-          sY[tid] = 1.0;  // reciprocal diagonal; panels beyond bk are identity padding
-        }
+        if (tid < 64) sV[tid] = (tid < bk) ? __ldcg(d.rhs + (size_t)t.k * BA_TB + tid) : 0.0;
       }
       __syncthreads();
       if (d.trace && tid == 0) d.trace[8 * (size_t)ti + 4] = ba_globaltimer();
-      tile_potrf(sA, bk, tid, &s_fail, sY);
+      tile_potrf2(sA, sV, sY, sM, sD, tid, &s_fail);
       if (d.trace && tid == 0) d.trace[8 * (size_t)ti + 5] = ba_globaltimer();
-      tile_trinv(sA, sB, sC, sY, tid);
-      if (d.trace && tid == 0) d.trace[8 * (size_t)ti + 6] = ba_globaltimer();
-      // Linv (column-major, padding rows/cols zero) and y = Linv b
       {
-        double* g = d.Linv + (size_t)t.k * BA_TILE;
+        double* g = d.tiles + (size_t)t.tC * BA_TILE;  // L in place (lower), zeros above
         for (int e = tid; e < BA_TILE; e += BA_NTHREADS) {
           const int c = e >> 6, r = e & 63;
-          g[e] = (r < bk && c < bk) ? sB[c * BA_LDP + r] : 0.0;
+          g[e] = (r >= c) ? sA[c * BA_LDS + r] : 0.0;
         }
-        if (tid < 64) {
-          double s = 0;
-          for (int p = 0; p <= tid && p < bk; ++p) s = __fma_rn(sB[p * BA_LDP + tid], sV[p], s);
-          d.y[(size_t)t.k * BA_TB + tid] = (tid < bk) ? s : 0.0;
-        }
+        double* gm = d.Linv + (size_t)t.k * BA_TILE;  // the eight 8x8 inverses
+        gm[tid] = sM[tid];
+        gm[tid + BA_NTHREADS] = sM[tid + BA_NTHREADS];
+        if (tid < 64) d.y[(size_t)t.k * BA_TB + tid] = sY[tid];
         if (tid == 0 && s_fail) d.sc[d.scFail] = 1.0;
       }
-    } else if (t.type == BA_T_TRSM || t.type == BA_T_UPD) {
-      const bool upd = (t.type == BA_T_UPD);
+    } else if (t.type == BA_T_TRSM) {
+      // L_ik = A_ik L_kk^-T by blocked substitution (tile_trsm2); every warp owns 8 rows
       double* gC = d.tiles + (size_t)t.tC * BA_TILE;
-      const double* gA = upd ? d.tiles + (size_t)t.tA * BA_TILE : gC;
-      const double* gB = upd ? d.tiles + (size_t)t.tB * BA_TILE : d.Linv + (size_t)t.tA * BA_TILE;
+      const double* gm = d.Linv + (size_t)t.tA * BA_TILE;
+      tile_load2<BA_LDS>(gC, sA, d.tiles + (size_t)t.w1i * BA_TILE, sB, tid);
+      sM[tid] = __ldcg(gm + tid);
+      sM[tid + BA_NTHREADS] = __ldcg(gm + tid + BA_NTHREADS);
+      __syncthreads();
+      if (d.trace && tid == 0) d.trace[8 * (size_t)ti + 4] = ba_globaltimer();
+      tile_trsm2(sA, sB, sM, (bk + 7) >> 3, tid);
+      __syncthreads();
+      if (d.trace && tid == 0) d.trace[8 * (size_t)ti + 5] = ba_globaltimer();
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int e = 2 * (tid + BA_NTHREADS * u);
+        reinterpret_cast<double2*>(gC)[tid + BA_NTHREADS * u] =
+            *reinterpret_cast<const double2*>(sA + (e >> 6) * BA_LDS + (e & 63));
+      }
+    } else if (t.type == BA_T_UPD) {
+      const bool upd = true;
+      double* gC = d.tiles + (size_t)t.tC * BA_TILE;
+      const double* gA = d.tiles + (size_t)t.tA * BA_TILE;
+      const double* gB = d.tiles + (size_t)t.tB * BA_TILE;
       // C prefetch (independent of the operand staging: one round trip for everything)
       const bool over = upd && (t.flags & 2);
       double cold[2][4][2];
@@ -485,8 +713,14 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
 #pragma unroll
       for (int u = 0; u < 8; ++u) gC[tid + BA_NTHREADS * u] = acc[u];
       if (dg) d.rhs[(size_t)t.i * BA_TB + tid] = rb;
-    } else {  // BA_T_BWD: x_k = Linv_k^T (y_k - sum_i L_ik^T x_i)
+    } else {  // BA_T_BWD: x_k = L_kk^-T (y_k - sum_i L_ik^T x_i)
       if (tid < 64) sV[tid] = __ldcg(d.y + (size_t)t.k * BA_TB + tid);
+      {  // L_kk and its diagonal inverses, needed last: in flight under the entry loop
+        const double* gm = d.Linv + (size_t)t.k * BA_TILE;
+        tile_load<BA_LDS>(d.tiles + (size_t)t.tC * BA_TILE, sA, tid);
+        sM[tid] = __ldcg(gm + tid);
+        sM[tid + BA_NTHREADS] = __ldcg(gm + tid + BA_NTHREADS);
+      }
       // thread (c = tid >> 2, q = tid & 3) accumulates rows 16q .. 16q+15 of column c over ALL
       // entries and reduces once; the loads of four tiles are in flight together
       const int c = tid >> 2, q = tid & 3;
@@ -526,8 +760,10 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
       __syncthreads();
       if (q == 0) sV[c] -= part;
       __syncthreads();
-      const double xv = tile_colT_dot(d.Linv + (size_t)t.k * BA_TILE, sV, tid);
-      if (q == 0) d.x[(size_t)t.k * BA_TB + c] = xv;
+      if (d.trace && tid == 0) d.trace[8 * (size_t)ti + 4] = ba_globaltimer();
+      if (tid < 32) tile_bwd2(sA, sM, sV, (bk + 7) >> 3, tid);
+      __syncthreads();
+      if (tid < 64) d.x[(size_t)t.k * BA_TB + tid] = (tid < bk) ? sV[tid] : 0.0;
     }
     __threadfence();
     __syncthreads();

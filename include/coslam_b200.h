@@ -290,6 +290,10 @@ int cosl_ba_solver_plan_info(cosl_ba_solver* s, int out[8]);
  * meta[cap][3] = {task type 0 POTRF / 1 TRSM / 2 UPDATE / 3 BACKWARD / 4 SUM, pivot block, row block},
  * then disarm. */
 int cosl_ba_solver_trace(cosl_ba_solver* s, int enable, uint64_t* out, int32_t* meta, int cap);
+/* Diagnostic: the task list of the solve plan (16 int32 per task, layout of BaTask in
+ * coslam_b200/csrc/ba_plan.h) and the wait lists of the BACKWARD / SUM tasks as (counter, value)
+ * pairs; returns the number of tasks. */
+int cosl_ba_solver_tasks(cosl_ba_solver* s, int32_t* tasks, int cap, int32_t* lists, int listCap);
 
 #ifdef __cplusplus
 }
