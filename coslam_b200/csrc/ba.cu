@@ -104,12 +104,20 @@ struct cosl_ba_solver {
   int *d_blkRows = nullptr, *d_blkRow0 = nullptr, *d_tileIdx = nullptr, *d_diagBlk = nullptr,
       *d_blkCam0 = nullptr, *d_order = nullptr, *d_solIdx = nullptr;
   BaTileDev td;
+  std::vector<BaTask> taskOrder;  // as uploaded: [POTRF / BACKWARD | TRSM / UPDATE / SUM]
   unsigned long long* d_trace = nullptr;
   int solveGrid = 1;
   double factorFlops = 0.0;
   double* d_sc = nullptr;
   unsigned char* d_outlier = nullptr;
   BaPairItem* d_items = nullptr;
+  BaRowDst* d_rowDst = nullptr;
+  int* d_cptrFree = nullptr;
+  double* d_Vinv = nullptr;
+  int nSlots = 1;
+  size_t rowsSmem = 0;
+  bool useRows = false;
+  int rowSplits = 1;
   int2* d_entries = nullptr;
   int nItems = 0;
   long long nEntries = 0;
@@ -270,7 +278,7 @@ void free_solver(cosl_ba_solver* s) {
                   s->d_V, s->d_eb, s->d_Uea, s->d_S, s->d_y, s->d_x, s->d_sc, s->d_outlier,
                   s->d_items, s->d_entries, s->d_Linv, s->d_cnt, s->d_tasks, s->d_bwd, s->d_blkRows,
                   s->d_blkRow0, s->d_tileIdx, s->d_diagBlk, s->d_blkCam0, s->d_order, s->d_solIdx,
-                  s->d_trace, s->d_sum, s->d_rhsS};
+                  s->d_trace, s->d_sum, s->d_rhsS, s->d_rowDst, s->d_cptrFree, s->d_Vinv};
   for (void* b : bufs)
     if (b) cudaFreeAsync(b, s->stream);
   if (s->stream) cudaStreamSynchronize(s->stream);
@@ -316,60 +324,36 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
         ccam[q] = cam[o];
       }
   }
-  // pair lists of the Schur contraction: for every free point, every pair (a <= b) of its
-  // free-camera observations, bucketed by camera pair (counting sort)
+  // camera co-visibility (which pairs of free cameras share a free point) -> plan of the
+  // reduced-system solve (ordering, tiles, task DAG) and the work lists of the Schur contraction.
+  // In the multi-GPU case every rank must derive the SAME structure although it only sees the
+  // pairs of its own point shard: the presence bitmap is all-reduced (max) first.
   const int mf = s->mf;
   const double tPair0 = now_s();
-  std::vector<long long> pcount((size_t)mf * mf + 1, 0);
-  std::vector<int2> entries;
-  long long nEntries = 0;
+  std::vector<uint8_t> adj((size_t)mf * mf, 0);
+  auto run_threads = [&](int T, auto&& body) {
+    std::vector<std::thread> th;
+    for (int t = 1; t < T; ++t) th.emplace_back(body, t);
+    body(0);
+    for (auto& x : th) x.join();
+  };
   {
-    // Worker t owns the camera pairs whose smaller camera lies in its range, so counting and
-    // filling need no synchronisation and the entry order inside a bucket (by point index) does
-    // not depend on the number of workers.
-    const int T = (mf >= 64) ? host_threads() : 1;
-    auto for_pairs = [&](int t, auto&& emit) {
-      const int ja0 = (int)((long long)mf * t / T), ja1 = (int)((long long)mf * (t + 1) / T);
-      for (int i = ncon; i < n; ++i) {
+    const int T = (n >= 4096) ? host_threads() : 1;
+    run_threads(T, [&](int t) {  // benign races: every writer stores 1
+      const int i0 = ncon + (int)((long long)(n - ncon) * t / T), i1 = ncon + (int)((long long)(n - ncon) * (t + 1) / T);
+      for (int i = i0; i < i1; ++i) {
         const long long o0 = p->ptr[i], o1 = p->ptr[i + 1];
         for (long long a = o0; a < o1; ++a) {
           const int ja = cam[a] - mcon;
-          if (ja < ja0 || ja >= ja1) continue;
-          for (long long b = o0; b < o1; ++b) {
+          if (ja < 0) continue;
+          for (long long b = a; b < o1; ++b) {
             const int jb = cam[b] - mcon;
-            if (jb > ja || (jb == ja && b >= a)) emit((size_t)ja * mf + jb, a, b);
+            if (jb >= 0) adj[(size_t)ja * mf + jb] = adj[(size_t)jb * mf + ja] = 1;
           }
         }
       }
-    };
-    auto run = [&](auto&& body) {
-      std::vector<std::thread> th;
-      for (int t = 1; t < T; ++t) th.emplace_back(body, t);
-      body(0);
-      for (auto& x : th) x.join();
-    };
-    run([&](int t) { for_pairs(t, [&](size_t bucket, long long, long long) { pcount[bucket + 1]++; }); });
-    for (size_t k = 0; k < (size_t)mf * mf; ++k) pcount[k + 1] += pcount[k];
-    nEntries = pcount[(size_t)mf * mf];
-    entries.resize((size_t)nEntries);
-    std::vector<long long> fill(pcount.begin(), pcount.end() - 1);
-    run([&](int t) {
-      for_pairs(t, [&](size_t bucket, long long a, long long b) {
-        entries[fill[bucket]++] = make_int2((int)a, (int)b);
-      });
     });
   }
-  s->nEntries = nEntries;
-  if (ba_timing()) std::fprintf(stderr, "[ba timing] pair lists %.1f ms (%lld entries, %d threads)\n",
-                                1e3 * (now_s() - tPair0), nEntries, host_threads());
-  // camera co-visibility -> plan of the reduced-system solve (ordering, tiles, task DAG).  In the
-  // multi-GPU case every rank must derive the SAME structure although it only sees the pairs of
-  // its own point shard: the presence bitmap is all-reduced (max) first.
-  std::vector<uint8_t> adj((size_t)mf * mf, 0);
-  for (int ja = 0; ja < mf; ++ja)
-    for (int jb = ja; jb < mf; ++jb)
-      if (pcount[(size_t)ja * mf + jb + 1] > pcount[(size_t)ja * mf + jb])
-        adj[(size_t)ja * mf + jb] = adj[(size_t)jb * mf + ja] = 1;
   if (s->comm && s->comm->nranks > 1 && mf > 0) {
     uint8_t* d_adj = nullptr;
     COSL_TRY(dev_alloc(s->stream, &d_adj, adj.size()));
@@ -387,33 +371,103 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
     if (s->plan.nb < 0) return set_error(COSL_E_INVALID, "solve plan: dependency cycle (internal error)");
   }
   const BaPlan& P = s->plan;
-  std::vector<BaPairItem> items;
-  const int chunk = 512;
+  // destination of the 6x6 block of camera pair (ja <= jb) in the tile storage: the lower
+  // triangle of the permuted system, i.e. the later camera (block, offset) gives the row
+  auto pair_dst = [&](int ja, int jb, int& dst, int& rOff, int& cOff, int& trans) {
+    const int bA = P.camBlk[ja], oA = P.camOff[ja], bB = P.camBlk[jb], oB = P.camOff[jb];
+    const bool bLater = (bB > bA) || (bB == bA && oB >= oA);
+    const int tile = bLater ? P.tileIdx[(size_t)bB * P.nb + bA] : P.tileIdx[(size_t)bA * P.nb + bB];
+    if (tile < 0 || tile >= P.nTilesOrig) return false;
+    dst = tile * BA_TILE;
+    trans = bLater ? 0 : 1;
+    cOff = bLater ? oA : oB;
+    rOff = bLater ? oB : oA;
+    return true;
+  };
+  // band of the reduced camera system in the natural camera order -> camera-row Schur kernel
+  int bandw = 0;
   for (int ja = 0; ja < mf; ++ja)
-    for (int jb = ja; jb < mf; ++jb) {
-      const long long b0 = pcount[(size_t)ja * mf + jb], b1 = pcount[(size_t)ja * mf + jb + 1];
-      if (b1 == b0) continue;
-      BaPairItem it;
-      std::memset(&it, 0, sizeof(it));
-      it.rowCam = ja;
-      it.colCam = jb;
-      // lower triangle of the permuted system: the later camera (block, offset) gives the row
-      const int bA = P.camBlk[ja], oA = P.camOff[ja], bB = P.camBlk[jb], oB = P.camOff[jb];
-      const bool bLater = (bB > bA) || (bB == bA && oB >= oA);
-      const int tile = bLater ? P.tileIdx[(size_t)bB * P.nb + bA] : P.tileIdx[(size_t)bA * P.nb + bB];
-      if (tile < 0 || tile >= P.nTilesOrig) return set_error(COSL_E_INVALID, "solve plan: missing tile");
-      it.dst = tile * BA_TILE;
-      it.trans = bLater ? 0 : 1;
-      it.cOff = bLater ? oA : oB;
-      it.rOff = bLater ? oB : oA;
-      it.rhsIdx = bA * BA_TB + oA;
-      for (long long b = b0; b < b1; b += chunk) {
-        it.begin = (int)b;
-        it.end = (int)std::min(b1, b + chunk);
-        items.push_back(it);
+    for (int jb = mf - 1; jb > ja + bandw; --jb)
+      if (adj[(size_t)ja * mf + jb]) {
+        bandw = jb - ja;
+        break;
       }
-    }
+  s->nSlots = bandw + 1;
+  s->rowsSmem = sizeof(double) * (size_t)BA_ROWS_WARPS * ((size_t)s->nSlots * 36 + 8);
+  s->useRows = mf > 0 && s->rowsSmem <= 160 * 1024 && std::getenv("COSL_BA_SCHUR_PAIRS") == nullptr;
+  // few cameras with long observation lists (local BA): split each list over several CTAs
+  s->rowSplits = (mf > 0 && mf < 296) ? std::max(1, std::min(64, 296 / mf)) : 1;
+  if (Nc / std::max(1, mf * s->rowSplits) < 64) s->rowSplits = std::max(1, (int)(Nc / 64 / std::max(1, mf)));
+  std::vector<BaRowDst> rowDst;
+  std::vector<int> cptrFree(mf + 1, 0);
+  std::vector<BaPairItem> items;
+  std::vector<int2> entries;
+  long long nEntries = 0;
+  if (s->useRows) {
+    rowDst.assign((size_t)mf * s->nSlots, BaRowDst{-1, 0, 0, 0});
+    for (int ja = 0; ja < mf; ++ja)
+      for (int sl = 0; sl < s->nSlots && ja + sl < mf; ++sl)
+        if (adj[(size_t)ja * mf + ja + sl]) {
+          BaRowDst& r = rowDst[(size_t)ja * s->nSlots + sl];
+          if (!pair_dst(ja, ja + sl, r.dst, r.rOff, r.cOff, r.trans))
+            return set_error(COSL_E_INVALID, "solve plan: missing tile");
+        }
+    for (int jf = 0; jf <= mf; ++jf) cptrFree[jf] = (int)cptr[std::min(m, jf + mcon)];
+  } else {
+    // pair lists: for every free point, every pair (a <= b) of its free-camera observations,
+    // bucketed by camera pair (counting sort).  Worker t owns the camera pairs whose smaller
+    // camera lies in its range, so counting and filling need no synchronisation and the entry
+    // order inside a bucket (by point index) does not depend on the number of workers.
+    std::vector<long long> pcount((size_t)mf * mf + 1, 0);
+    const int T = (mf >= 64) ? host_threads() : 1;
+    auto for_pairs = [&](int t, auto&& emit) {
+      const int ja0 = (int)((long long)mf * t / T), ja1 = (int)((long long)mf * (t + 1) / T);
+      for (int i = ncon; i < n; ++i) {
+        const long long o0 = p->ptr[i], o1 = p->ptr[i + 1];
+        for (long long a = o0; a < o1; ++a) {
+          const int ja = cam[a] - mcon;
+          if (ja < ja0 || ja >= ja1) continue;
+          for (long long b = o0; b < o1; ++b) {
+            const int jb = cam[b] - mcon;
+            if (jb > ja || (jb == ja && b >= a)) emit((size_t)ja * mf + jb, a, b);
+          }
+        }
+      }
+    };
+    run_threads(T, [&](int t) { for_pairs(t, [&](size_t bucket, long long, long long) { pcount[bucket + 1]++; }); });
+    for (size_t k = 0; k < (size_t)mf * mf; ++k) pcount[k + 1] += pcount[k];
+    nEntries = pcount[(size_t)mf * mf];
+    entries.resize((size_t)nEntries);
+    std::vector<long long> fill(pcount.begin(), pcount.end() - 1);
+    run_threads(T, [&](int t) {
+      for_pairs(t, [&](size_t bucket, long long a, long long b) {
+        entries[fill[bucket]++] = make_int2((int)a, (int)b);
+      });
+    });
+    const int chunk = 512;
+    for (int ja = 0; ja < mf; ++ja)
+      for (int jb = ja; jb < mf; ++jb) {
+        const long long b0 = pcount[(size_t)ja * mf + jb], b1 = pcount[(size_t)ja * mf + jb + 1];
+        if (b1 == b0) continue;
+        BaPairItem it;
+        std::memset(&it, 0, sizeof(it));
+        it.rowCam = ja;
+        it.colCam = jb;
+        if (!pair_dst(ja, jb, it.dst, it.rOff, it.cOff, it.trans))
+          return set_error(COSL_E_INVALID, "solve plan: missing tile");
+        it.rhsIdx = P.camBlk[ja] * BA_TB + P.camOff[ja];
+        for (long long b = b0; b < b1; b += chunk) {
+          it.begin = (int)b;
+          it.end = (int)std::min(b1, b + chunk);
+          items.push_back(it);
+        }
+      }
+  }
+  s->nEntries = nEntries;
   s->nItems = (int)items.size();
+  if (ba_timing())
+    std::fprintf(stderr, "[ba timing] co-visibility + Schur work lists %.1f ms (%s, band %d, %lld pair entries, %d threads)\n",
+                 1e3 * (now_s() - tPair0), s->useRows ? "camera rows" : "pair lists", bandw, nEntries, host_threads());
   // intrinsics: only K0,K1,K2,K4,K5 are used (as BundleRTS packs them, app/SL_CoSLAMBA.cpp:337-343)
   std::vector<double> camK((size_t)m * 5);
   for (int j = 0; j < m; ++j) {
@@ -454,7 +508,7 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   COSL_TRY(dev_alloc(s->stream, &s->d_Linv, (size_t)nb * BA_TILE));
   COSL_TRY(dev_alloc(s->stream, &s->d_y, rhsLen));
   COSL_TRY(dev_alloc(s->stream, &s->d_x, rhsLen));
-  COSL_TRY(dev_alloc(s->stream, &s->d_cnt, (size_t)P.nCounters + 1));
+  COSL_TRY(dev_alloc(s->stream, &s->d_cnt, (size_t)P.nCounters + 2));
   COSL_TRY(dev_alloc(s->stream, &s->d_tasks, P.tasks.size()));
   COSL_TRY(dev_alloc(s->stream, &s->d_bwd, P.bwdList.size()));
   COSL_TRY(dev_alloc(s->stream, &s->d_blkRows, (size_t)nb));
@@ -473,6 +527,9 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   COSL_TRY(dev_alloc(s->stream, &s->d_sc, (size_t)SC_NTOT));
   COSL_TRY(dev_alloc(s->stream, &s->d_outlier, (size_t)N));
   COSL_TRY(dev_alloc(s->stream, &s->d_items, items.size()));
+  COSL_TRY(dev_alloc(s->stream, &s->d_rowDst, rowDst.size()));
+  COSL_TRY(dev_alloc(s->stream, &s->d_cptrFree, cptrFree.size()));
+  COSL_TRY(dev_alloc(s->stream, &s->d_Vinv, (size_t)n * 6));
   COSL_TRY(dev_alloc(s->stream, &s->d_entries, (size_t)nEntries));
   COSL_CUDA(cudaMallocHost(&s->h_sc, sizeof(double) * SC_NTOT));
 #define UP(dst, src, bytes) \
@@ -487,8 +544,17 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   UP(s->d_xy, p->xy, sizeof(double) * 2 * (size_t)N);
   UP(s->d_ptr, p->ptr, sizeof(long long) * ((size_t)n + 1));
   if (!items.empty()) UP(s->d_items, items.data(), sizeof(BaPairItem) * items.size());
+  if (!rowDst.empty()) UP(s->d_rowDst, rowDst.data(), sizeof(BaRowDst) * rowDst.size());
+  UP(s->d_cptrFree, cptrFree.data(), sizeof(int) * cptrFree.size());
   if (nEntries) UP(s->d_entries, entries.data(), sizeof(int2) * (size_t)nEntries);
-  if (!P.tasks.empty()) UP(s->d_tasks, P.tasks.data(), sizeof(BaTask) * P.tasks.size());
+  // two ticket lists (each keeps the critical-path-first order, hence stays topological)
+  s->taskOrder.clear();
+  for (const BaTask& t : P.tasks)
+    if (t.type == BA_T_POTRF || t.type == BA_T_BWD) s->taskOrder.push_back(t);
+  const int nA = (int)s->taskOrder.size();
+  for (const BaTask& t : P.tasks)
+    if (!(t.type == BA_T_POTRF || t.type == BA_T_BWD)) s->taskOrder.push_back(t);
+  if (!s->taskOrder.empty()) UP(s->d_tasks, s->taskOrder.data(), sizeof(BaTask) * s->taskOrder.size());
   if (!P.bwdList.empty()) UP(s->d_bwd, P.bwdList.data(), sizeof(BaBwdEntry) * P.bwdList.size());
   if (!P.sumList.empty()) UP(s->d_sum, P.sumList.data(), sizeof(BaSumEntry) * P.sumList.size());
   if (P.nb) {
@@ -543,6 +609,7 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   td.xdoneBase = P.nTiles + P.nScratch;
   td.blkRows = s->d_blkRows;
   td.nTasks = (int)P.tasks.size();
+  td.nA = nA;
   td.nb = P.nb;
   td.nTiles = P.nTiles;
   td.nCounters = P.nCounters;
@@ -559,6 +626,9 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
                                    (int)smallBytes));
   COSL_CUDA(cudaFuncSetAttribute(ba_tile_solve, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  BA_TILE_SMEM));
+  if (s->useRows && s->rowsSmem > 40 * 1024)
+    COSL_CUDA(cudaFuncSetAttribute(ba_schur_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)s->rowsSmem));
   {
     // persistent grid: never more CTAs than can be co-resident (the ticket scheduler spins)
     int nsm = 0, perSm = 0;
@@ -566,8 +636,12 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
     COSL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, ba_tile_solve, BA_NTHREADS,
                                                             BA_TILE_SMEM));
     int grid = nsm * std::max(1, std::min(perSm, 1));
-    if (const char* e = std::getenv("COSL_BA_SOLVE_GRID")) grid = std::max(1, std::min(std::atoi(e), nsm * std::max(1, perSm)));
-    s->solveGrid = std::max(1, std::min(grid, td.nTasks));
+    if (const char* e = std::getenv("COSL_BA_SOLVE_GRID")) grid = std::max(2, std::min(std::atoi(e), nsm * std::max(1, perSm)));
+    s->solveGrid = std::max(2, std::min(grid, td.nTasks + 1));
+    // CTAs that only ever run the diagonal-block tasks (see BaTileDev::nSpecial)
+    int nsp = std::min(24, std::max(1, s->solveGrid / 6));
+    if (const char* e = std::getenv("COSL_BA_SPECIAL")) nsp = std::atoi(e);
+    td.nSpecial = std::max(1, std::min(nsp, s->solveGrid - 1));
   }
   s->secLin = s->timer.section("ba_linearize");
   s->secSchur = s->timer.section("ba_schur");
@@ -668,7 +742,7 @@ int dense_solve(cosl_ba_solver* s) {
     COSL_LAUNCH(ba_tile_small, 1, 256, sizeof(double) * (size_t)ns * ns, s->stream, s->td,
                 s->d_tileIdx, s->d_blkRow0, ns);
   } else {
-    COSL_CUDA(cudaMemsetAsync(s->d_cnt, 0, sizeof(int) * ((size_t)s->td.nCounters + 1), s->stream));
+    COSL_CUDA(cudaMemsetAsync(s->d_cnt, 0, sizeof(int) * ((size_t)s->td.nCounters + 2), s->stream));
     COSL_LAUNCH(ba_tile_solve, s->solveGrid, BA_NTHREADS, BA_TILE_SMEM, s->stream, s->td);
   }
   s->timer.end(s->stream);
@@ -688,9 +762,15 @@ int solve_trial(cosl_ba_solver* s, double mu, bool* solved) {
   if (ns) {
     COSL_LAUNCH(ba_tile_init, std::max(1, s->plan.nTiles), 256, 0, s->stream, s->d, mu, r0 ? 1 : 0,
                 s->d_diagBlk, s->d_blkCam0, s->d_order);
-    if (s->nItems)
+    if (s->useRows) {
+      if (s->n) COSL_LAUNCH(ba_vinv_kernel, (unsigned)div_up64(s->n, 256), 256, 0, s->stream, s->d, mu, s->d_Vinv);
+      if (s->Nc)
+        COSL_LAUNCH(ba_schur_rows, s->mf * s->rowSplits, 32 * BA_ROWS_WARPS, s->rowsSmem, s->stream, s->d,
+                    s->d_cptrFree, s->d_rowDst, s->nSlots, s->d_Vinv, s->d_solIdx, s->rowSplits);
+    } else if (s->nItems) {
       COSL_LAUNCH(ba_schur_pairs, div_up(s->nItems, 4), 128, 0, s->stream, s->d, s->d_items,
                   s->nItems, s->d_entries, mu);
+    }
   }
   s->timer.end(s->stream);
   // the one exchange of an LM trial: [rhs | Schur-structure tiles] is contiguous, no packing
@@ -1062,9 +1142,9 @@ int cosl_ba_solver_trace(cosl_ba_solver* s, int enable, uint64_t* out, int32_t* 
     COSL_CUDA(cudaStreamSynchronize(s->stream));
     if (meta)
       for (int t = 0; t < n; ++t) {
-        meta[3 * t] = s->plan.tasks[t].type;
-        meta[3 * t + 1] = s->plan.tasks[t].k;
-        meta[3 * t + 2] = s->plan.tasks[t].i;
+        meta[3 * t] = s->taskOrder[t].type;
+        meta[3 * t + 1] = s->taskOrder[t].k;
+        meta[3 * t + 2] = s->taskOrder[t].i;
       }
   }
   s->td.trace = nullptr;
@@ -1080,7 +1160,7 @@ int cosl_ba_solver_tasks(cosl_ba_solver* s, int32_t* tasks, int cap, int32_t* li
   const int nt = (int)P.tasks.size();
   int nl = 0;
   for (int t = 0; t < nt && t < cap; ++t) {
-    BaTask k = P.tasks[t];
+    BaTask k = s->taskOrder[t];
     if (k.type == BA_T_BWD || k.type == BA_T_SUM) {
       const int l0 = nl;
       for (int e = k.l0; e < k.l1; ++e) {

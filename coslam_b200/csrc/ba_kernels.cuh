@@ -485,6 +485,115 @@ ba_schur_pairs(BaDev d, const BaPairItem* __restrict__ items, int nItems,
 }
 
 // ------------------------------------------------------------------------------------------
+// Schur contraction, camera-row form (the default): CTA = one free camera a.  It walks a's
+// observations (camera-major list); for each point i it reads the point's W rows -- ONE contiguous
+// segment of the point-major W array -- and accumulates Y_a(i) W_b(i)^T for every free camera
+// b >= a that sees i into warp-private shared-memory accumulators indexed by b - a (the band of
+// the reduced camera system), plus Y_a(i) eb_i for the right-hand side.  At the end the four warp
+// copies are summed in a fixed order and subtracted from the tiles: every 6x6 block (a, b) has
+// exactly one owner, so there are no atomics and the result is deterministic.  Traffic: W is read
+// ~(k_i + 1)/2 times per row from L2 in contiguous 144-byte rows (the pair-list kernel gathered
+// 288 B per pair entry through index lists).  Used when the band (nSlots = max(b - a) + 1) fits
+// shared memory; ba_schur_pairs remains for arbitrary co-visibility.
+// ------------------------------------------------------------------------------------------
+struct BaRowDst {
+  int dst, rOff, cOff, trans;  // as in BaPairItem; dst < 0: cameras (a, a + slot) share no point
+};
+
+__global__ void __launch_bounds__(256) ba_vinv_kernel(BaDev d, double mu, double* __restrict__ Vinv) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= d.n) return;
+  double I[6] = {0, 0, 0, 0, 0, 0};
+  if (i >= d.ncon) inv3sym_mu(d.V + 6 * i, mu, I);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) Vinv[6 * i + k] = I[k];
+}
+
+constexpr int BA_ROWS_WARPS = 4;
+
+__global__ void __launch_bounds__(32 * BA_ROWS_WARPS)
+ba_schur_rows(BaDev d, const int* __restrict__ cptr, const BaRowDst* __restrict__ rowDst, int nSlots,
+              const double* __restrict__ Vinv, const int* __restrict__ rhsIdx, int splits) {
+  extern __shared__ double sacc[];  // [BA_ROWS_WARPS][stride]
+  __shared__ int s_list[BA_ROWS_WARPS][32], s_slot[BA_ROWS_WARPS][32];
+  __shared__ double s_Y[BA_ROWS_WARPS][18];
+  // splits > 1 (few cameras, many observations: local BA): several CTAs share a camera's
+  // observation list and add their partial blocks with atomics
+  const int af = blockIdx.x / splits, part = blockIdx.x - af * splits;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int stride = nSlots * 36 + 8;
+  double* acc = sacc + (size_t)w * stride;
+  for (int e = lane; e < stride; e += 32) acc[e] = 0.0;
+  __syncwarp();
+  for (int q = cptr[af] + part * BA_ROWS_WARPS + w; q < cptr[af + 1]; q += BA_ROWS_WARPS * splits) {
+    const int o = d.cobs[q], i = d.pt[o];
+    if (i < d.ncon) continue;  // fixed points do not enter the reduced system (warp-uniform)
+    const double* Vi = Vinv + 6 * (size_t)i;
+    const double i0 = Vi[0], i1 = Vi[1], i2 = Vi[2], i3 = Vi[3], i4 = Vi[4], i5 = Vi[5];
+    if (lane < 18) {  // Y = W_o Vinv_i, entry (r, c) = lane
+      const int r = lane / 3, c = lane - 3 * r;
+      const double* wr = d.W + 18 * (size_t)o + 3 * r;
+      const double v0 = (c == 0) ? i0 : (c == 1) ? i1 : i2;
+      const double v1 = (c == 0) ? i1 : (c == 1) ? i3 : i4;
+      const double v2 = (c == 0) ? i2 : (c == 1) ? i4 : i5;
+      s_Y[w][lane] = wr[0] * v0 + wr[1] * v1 + wr[2] * v2;
+    }
+    __syncwarp();
+    double Y[18];
+#pragma unroll
+    for (int k = 0; k < 18; ++k) Y[k] = s_Y[w][k];
+    if (lane < 6) {  // rhs_a -= Y eb_i
+      const double* eb = d.eb + 3 * (size_t)i;
+      const double* yr = &s_Y[w][3 * lane];
+      acc[nSlots * 36 + lane] += yr[0] * eb[0] + yr[1] * eb[1] + yr[2] * eb[2];
+    }
+    const long long p0 = d.ptr[i], p1 = d.ptr[i + 1];
+    for (long long base = p0; base < p1; base += 32) {
+      const long long ob = base + lane;
+      const int bf = (ob < p1) ? d.cam[ob] - d.mcon : -1;
+      const bool ok = bf >= af;
+      const unsigned mask = __ballot_sync(0xffffffffu, ok);
+      const int nq = __popc(mask);
+      if (ok) {
+        const int pos = __popc(mask & ((1u << lane) - 1u));
+        s_list[w][pos] = (int)ob;
+        s_slot[w][pos] = bf - af;
+      }
+      __syncwarp();
+      for (int t = lane; t < 6 * nq; t += 32) {
+        const int j = t / 6, sc = t - 6 * j;
+        const double* wb = d.W + 18 * (size_t)s_list[w][j] + 3 * sc;
+        const double w0 = wb[0], w1 = wb[1], w2 = wb[2];
+        double* ap = acc + s_slot[w][j] * 36 + sc;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) ap[6 * r] += Y[3 * r] * w0 + Y[3 * r + 1] * w1 + Y[3 * r + 2] * w2;
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < nSlots * 36; e += 32 * BA_ROWS_WARPS) {
+    const int slot = e / 36, rs = e - 36 * slot, r = rs / 6, sc = rs - 6 * r;
+    const BaRowDst rd = rowDst[(size_t)af * nSlots + slot];
+    if (rd.dst < 0) continue;
+    if (slot == 0 && sc < r) continue;  // diagonal block: lower part of the tile only
+    double v = 0;
+#pragma unroll
+    for (int ww = 0; ww < BA_ROWS_WARPS; ++ww) v += sacc[(size_t)ww * stride + e];
+    const int col = rd.cOff + (rd.trans ? sc : r), row = rd.rOff + (rd.trans ? r : sc);
+    if (splits > 1) atomicAdd(&d.tiles[rd.dst + col * 64 + row], -v);
+    else d.tiles[rd.dst + col * 64 + row] -= v;
+  }
+  if (threadIdx.x < 6) {
+    double v = 0;
+#pragma unroll
+    for (int ww = 0; ww < BA_ROWS_WARPS; ++ww) v += sacc[(size_t)ww * stride + nSlots * 36 + threadIdx.x];
+    if (splits > 1) atomicAdd(&d.rhs[rhsIdx[af] + threadIdx.x], -v);
+    else d.rhs[rhsIdx[af] + threadIdx.x] -= v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Back substitution, step 1, point-major, one observation per thread: t_i = sum_j W_ij^T da_j,
 // collapsed per point with segmented shuffles; run heads add into acc3[n][3] (zeroed before).
 // ------------------------------------------------------------------------------------------

@@ -30,12 +30,14 @@ struct BaTileDev {
   double* Linv;   // [nb][4096]
   double* y;      // [nb*64]
   double* x;      // [nb*64]
-  int* cnt;       // [nCounters + 1]; the last one is the task ticket
+  int* cnt;       // [nCounters + 2]; the last two are the task tickets of the two CTA roles
   const BaTask* tasks;
   const BaBwdEntry* bwd;
   const BaSumEntry* sum;
   const int* blkRows;
   int nTasks, nb, nTiles, nCounters;
+  int nA;        // tasks [0, nA) = POTRF / BACKWARD (specialist CTAs), [nA, nTasks) = TRSM / UPDATE / SUM
+  int nSpecial;  // CTAs [0, nSpecial) serve the first list: code working sets stay inside the I-cache
   int xdoneBase;  // counter index of "x_0 done" (= nTiles + nScratch)
   double* sc;
   int scFail;
@@ -327,6 +329,38 @@ __device__ __forceinline__ double tile_colT_dot(const double* __restrict__ G, co
   return s;
 }
 
+// x = L^-T v for 64 threads (warps 0-1; named barrier 2): blocks last to first, right-looking --
+// after x_b = M_b^T v_b every remaining v_p gets its update from block row b at once.
+__device__ __forceinline__ void tile_bwd3(const double* __restrict__ sL, const double* __restrict__ sM,
+                                          double* __restrict__ sv, double* __restrict__ sx, int nbk, int t) {
+  double v = sv[t];
+  for (int b = nbk - 1; b >= 0; --b) {
+    const bool mine = (t >> 3) == b;
+    if (mine) sv[t] = v;
+    asm volatile("bar.sync 2, 64;" ::: "memory");
+    if (mine) {
+      const int q = t & 7;
+      double x0 = 0, x1 = 0;
+#pragma unroll
+      for (int qq = 0; qq < 8; qq += 2) {
+        x0 = __fma_rn(sM[b * 64 + qq * 8 + q], sv[8 * b + qq], x0);  // M lower: zero for qq < q
+        x1 = __fma_rn(sM[b * 64 + (qq + 1) * 8 + q], sv[8 * b + qq + 1], x1);
+      }
+      sx[t] = x0 + x1;
+    }
+    asm volatile("bar.sync 2, 64;" ::: "memory");
+    if (t < 8 * b) {
+      double s0 = 0, s1 = 0;
+#pragma unroll
+      for (int q = 0; q < 8; q += 2) {
+        s0 = __fma_rn(sL[t * BA_LDS + 8 * b + q], sx[8 * b + q], s0);
+        s1 = __fma_rn(sL[t * BA_LDS + 8 * b + q + 1], sx[8 * b + q + 1], s1);
+      }
+      v -= s0 + s1;
+    }
+  }
+}
+
 // =============================================================================================
 // Version 2 of the diagonal-block path: no explicit 64x64 inverse.
 //   POTRF2 : factor with 8-column panels and LOOK-AHEAD: warps 0-1 ("panel warps", thread = row)
@@ -556,7 +590,9 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
   double* sD = sY + BA_TB;                 // [72] panel scratch of tile_potrf2
   __shared__ int s_task, s_fail;
   const int tid = threadIdx.x;
-  int* const ticket = d.cnt + d.nCounters;
+  const bool special = (int)blockIdx.x < d.nSpecial;
+  int* const ticket = d.cnt + d.nCounters + (special ? 0 : 1);
+  const int tBase = special ? 0 : d.nA, tCount = special ? d.nA : d.nTasks - d.nA;
   for (;;) {
     __syncthreads();
     if (tid == 0) {
@@ -564,8 +600,8 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
       s_fail = 0;
     }
     __syncthreads();
-    const int ti = s_task;
-    if (ti >= d.nTasks) break;
+    if (s_task >= tCount) break;
+    const int ti = tBase + s_task;
     const BaTask t = d.tasks[ti];
     if (tid < 32) {
       if (tid == 0 && d.trace) {
@@ -761,9 +797,12 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
       if (q == 0) sV[c] -= part;
       __syncthreads();
       if (d.trace && tid == 0) d.trace[8 * (size_t)ti + 4] = ba_globaltimer();
-      if (tid < 32) tile_bwd2(sA, sM, sV, (bk + 7) >> 3, tid);
+      if (tid < 64) {
+        sY[tid] = 0.0;
+        tile_bwd3(sA, sM, sV, sY, (bk + 7) >> 3, tid);
+      }
       __syncthreads();
-      if (tid < 64) d.x[(size_t)t.k * BA_TB + tid] = (tid < bk) ? sV[tid] : 0.0;
+      if (tid < 64) d.x[(size_t)t.k * BA_TB + tid] = (tid < bk) ? sY[tid] : 0.0;
     }
     __threadfence();
     __syncthreads();

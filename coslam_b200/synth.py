@@ -131,9 +131,12 @@ def _rodrigues(w):
 
 def make_ba_scene(n_cams=4, n_kf=5, n_pts=20000, width=1280, height=720, seed=BASE_SEED,
                   m_con=None, n_con=2, window=4, p_vis=0.55, noise_px=0.5, outlier_frac=0.02,
-                  pose_rot_deg=0.1, pose_trans_frac=0.002, point_frac=0.002, min_obs=2):
+                  pose_rot_deg=0.1, pose_trans_frac=0.002, point_frac=0.002, min_obs=2,
+                  sort_by_home=False):
     """Synthetic multi-camera BA problem.  Returns (BAProblem with perturbed
-    initial values, dict of ground truth)."""
+    initial values, dict of ground truth).  sort_by_home: number the points in the order of their
+    home key frame (map-creation order of a real SLAM run), so that contiguous point shards see
+    DIFFERENT camera pairs -- the realistic case for the multi-GPU structure exchange."""
     rng = np.random.default_rng(seed)
     f = 0.9 * width
     K1 = np.array([f, 0, width / 2.0, 0, f, height / 2.0, 0, 0, 1.0])
@@ -158,6 +161,8 @@ def make_ba_scene(n_cams=4, n_kf=5, n_pts=20000, width=1280, height=720, seed=BA
     m = n_kf * n_cams
     # points: slab 4..20 m in front of the trajectory, home key frame uniform
     home = rng.integers(0, n_kf, n_pts)
+    if sort_by_home:
+        home = np.sort(home)
     depth = rng.uniform(4.0, 20.0, n_pts)
     lat = rng.uniform(-1.0, 1.0, n_pts) * depth * (width / 2.0 / f) * 1.3
     vert = rng.uniform(-1.0, 1.0, n_pts) * depth * (height / 2.0 / f) * 1.1

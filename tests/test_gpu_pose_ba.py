@@ -165,3 +165,29 @@ def test_ba_c4_slice_parity(api, orc):
     assert abs(ig[1] - io[1]) <= 1e-9 * io[1], (ig[1], io[1])
     assert abs(pg.rms() - po.rms()) <= REL_RMS_TOL * po.rms()
     assert np.abs(pg.X - po.X).max() < 1e-6
+
+
+def test_ba_schur_pair_list_fallback(api, orc, monkeypatch):
+    """The pair-list Schur kernel (used when the camera band does not fit shared memory) must give
+    the same solve as the default camera-row kernel; forced here through COSL_BA_SCHUR_PAIRS."""
+    prob, truth = synth.make_ba_scene(4, 12, 2500, 1280, 720, seed=33, m_con=4, n_con=1)
+    opt = BaOptions.defaults()
+    opt.outer_iters, opt.inner_iters = 2, 6
+    p_rows, p_pairs = prob.copy(), prob.copy()
+    i_rows = api.ba_solve(p_rows, opt)
+    monkeypatch.setenv("COSL_BA_SCHUR_PAIRS", "1")
+    i_pairs = api.ba_solve(p_pairs, opt)
+    monkeypatch.delenv("COSL_BA_SCHUR_PAIRS")
+    assert i_rows[10] == i_pairs[10]
+    assert abs(i_rows[1] - i_pairs[1]) <= 1e-10 * i_rows[1]
+    assert np.abs(p_rows.X - p_pairs.X).max() < 1e-8
+    _ba_compare(api, orc, prob, opt)
+
+
+def test_ba_time_ordered_points_two_solvers_agree(api, orc):
+    """Points sorted by home key frame (map-creation order): same solution as the oracle
+    -- the single-GPU counterpart of the sharded test in tools/mgpu_ba_check.py."""
+    prob, truth = synth.make_ba_scene(4, 20, 3000, 1280, 720, seed=34, m_con=4, n_con=0, sort_by_home=True)
+    opt = BaOptions.defaults()
+    opt.outer_iters, opt.inner_iters = 2, 6
+    _ba_compare(api, orc, prob, opt)

@@ -16,7 +16,8 @@ from coslam_b200.ctypes_defs import BaOptions
 def log(*a):
     print(f"[rank {rank}]", *a, file=sys.stderr, flush=True)
 
-prob, truth = synth.make_ba_scene(4, 30, 5000, 1280, 720, seed=21, m_con=4, n_con=3)
+# points in map-creation order: every rank sees different camera pairs
+prob, truth = synth.make_ba_scene(4, 30, 5000, 1280, 720, seed=21, m_con=4, n_con=3, sort_by_home=True)
 opt = BaOptions.defaults()
 opt.device = local
 opt.outer_iters, opt.inner_iters = 2, 6

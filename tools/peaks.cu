@@ -53,6 +53,59 @@ __global__ void __launch_bounds__(256) k_dmma(double* out, double a, double b) {
   if (s == 12345.678) out[0] = s;
 }
 
+// dependent-chain latencies, one warp, cycles per operation
+__global__ void k_lat(long long* out, double a, double b, float fa) {
+  __shared__ double sm[64];
+  sm[threadIdx.x] = a;
+  sm[threadIdx.x + 32] = b;
+  __syncwarp();
+  const int N = 2048;
+  double x = a + threadIdx.x * 1e-9;
+  long long t0 = clock64();
+  for (int i = 0; i < N; ++i) x = __fma_rn(x, a, b);
+  long long t1 = clock64();
+  out[0] = t1 - t0;
+  double y = x;
+  t0 = clock64();
+  for (int i = 0; i < N; ++i) y = __dmul_rn(y, a);
+  t1 = clock64();
+  out[1] = t1 - t0;
+  float f = fa + threadIdx.x;
+  t0 = clock64();
+  for (int i = 0; i < N; ++i) f = __fmaf_rn(f, fa, 1e-9f);
+  t1 = clock64();
+  out[2] = t1 - t0;
+  double z = y + 2.0;
+  t0 = clock64();
+  for (int i = 0; i < N; ++i) z = (double)rsqrtf((float)z) + 1.5;  // cvt + MUFU.RSQ + cvt + DADD
+  t1 = clock64();
+  out[3] = t1 - t0;
+  double w = z;
+  t0 = clock64();
+  for (int i = 0; i < N; ++i) w = __shfl_xor_sync(0xffffffffu, w, 1);
+  t1 = clock64();
+  out[4] = t1 - t0;
+  int idx = threadIdx.x & 31;
+  double v = w;
+  t0 = clock64();
+  for (int i = 0; i < N; ++i) {
+    v = sm[idx];
+    idx = (idx + (int)v) & 31;
+  }
+  t1 = clock64();
+  out[5] = t1 - t0;
+  double c0 = x, c1 = y;
+  t0 = clock64();
+  for (int i = 0; i < N; ++i)
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+  t1 = clock64();
+  out[6] = t1 - t0;
+  out[7] = N;
+  if (x + y + f + z + w + v + c0 + c1 == 12345.0) out[8] = 1;
+}
+
 template <typename F>
 static double best_ms(F launch) {
   cudaEvent_t e0, e1;
@@ -88,7 +141,17 @@ int main() {
   const double ffma = 2.0 * 8 * ITERS * nthr / (msF * 1e-3) / 1e12;
   // one DMMA m8n8k4 per warp = 8*8*4 multiply-adds
   const double dmma = 2.0 * 256.0 * 8 * (ITERS / 4) * (nthr / 32) / (msM * 1e-3) / 1e12;
-  std::printf("{\"gpu\": \"%s\", \"sms\": %d, \"fp64_fma_tflops\": %.2f, \"fp64_dmma_tflops\": %.2f, "
+  long long* lat;
+  cudaMallocManaged(&lat, 16 * sizeof(long long));
+  k_lat<<<1, 32>>>(lat, 1.0000001, 1e-9, 1.0000001f);
+  cudaDeviceSynchronize();
+  k_lat<<<1, 32>>>(lat, 1.0000001, 1e-9, 1.0000001f);
+  cudaDeviceSynchronize();
+  const double N = (double)lat[7];
+  std::printf("{\"latency_cycles\": {\"dfma\": %.1f, \"dmul\": %.1f, \"ffma\": %.1f, \"cvt_rsqrtf_cvt_dadd\": %.1f, "
+              "\"shfl_f64\": %.1f, \"lds_f64_dependent\": %.1f, \"dmma884\": %.1f}, ",
+              lat[0] / N, lat[1] / N, lat[2] / N, lat[3] / N, lat[4] / N, lat[5] / N, lat[6] / N);
+  std::printf("\"gpu\": \"%s\", \"sms\": %d, \"fp64_fma_tflops\": %.2f, \"fp64_dmma_tflops\": %.2f, "
               "\"fp32_fma_tflops\": %.2f, \"how\": \"register-only FMA / DMMA.8x8x4 chains, 8 independent "
               "accumulators per thread, %d CTAs x 256 threads, best of 5, CUDA events\"}\n",
               prop.name, prop.multiProcessorCount, dfma, dmma, ffma, grid);
