@@ -112,6 +112,7 @@ struct cosl_ba_solver {
   unsigned char* d_outlier = nullptr;
   BaPairItem* d_items = nullptr;
   BaRowDst* d_rowDst = nullptr;
+  int4* d_visit = nullptr;
   int* d_cptrFree = nullptr;
   double* d_Vinv = nullptr;
   int nSlots = 1;
@@ -278,7 +279,7 @@ void free_solver(cosl_ba_solver* s) {
                   s->d_V, s->d_eb, s->d_Uea, s->d_S, s->d_y, s->d_x, s->d_sc, s->d_outlier,
                   s->d_items, s->d_entries, s->d_Linv, s->d_cnt, s->d_tasks, s->d_bwd, s->d_blkRows,
                   s->d_blkRow0, s->d_tileIdx, s->d_diagBlk, s->d_blkCam0, s->d_order, s->d_solIdx,
-                  s->d_trace, s->d_sum, s->d_rhsS, s->d_rowDst, s->d_cptrFree, s->d_Vinv};
+                  s->d_trace, s->d_sum, s->d_rhsS, s->d_rowDst, s->d_cptrFree, s->d_Vinv, s->d_visit};
   for (void* b : bufs)
     if (b) cudaFreeAsync(b, s->stream);
   if (s->stream) cudaStreamSynchronize(s->stream);
@@ -400,6 +401,7 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   if (Nc / std::max(1, mf * s->rowSplits) < 64) s->rowSplits = std::max(1, (int)(Nc / 64 / std::max(1, mf)));
   std::vector<BaRowDst> rowDst;
   std::vector<int> cptrFree(mf + 1, 0);
+  std::vector<int4> visit;
   std::vector<BaPairItem> items;
   std::vector<int2> entries;
   long long nEntries = 0;
@@ -413,6 +415,11 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
             return set_error(COSL_E_INVALID, "solve plan: missing tile");
         }
     for (int jf = 0; jf <= mf; ++jf) cptrFree[jf] = (int)cptr[std::min(m, jf + mcon)];
+    visit.resize((size_t)Nc);
+    for (long long q = 0; q < Nc; ++q) {
+      const int o = cobs[q], i = pt[o];
+      visit[q] = make_int4(o, i, (int)p->ptr[i], (int)(p->ptr[i + 1] - p->ptr[i]));
+    }
   } else {
     // pair lists: for every free point, every pair (a <= b) of its free-camera observations,
     // bucketed by camera pair (counting sort).  Worker t owns the camera pairs whose smaller
@@ -528,6 +535,7 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   COSL_TRY(dev_alloc(s->stream, &s->d_outlier, (size_t)N));
   COSL_TRY(dev_alloc(s->stream, &s->d_items, items.size()));
   COSL_TRY(dev_alloc(s->stream, &s->d_rowDst, rowDst.size()));
+  COSL_TRY(dev_alloc(s->stream, &s->d_visit, visit.size()));
   COSL_TRY(dev_alloc(s->stream, &s->d_cptrFree, cptrFree.size()));
   COSL_TRY(dev_alloc(s->stream, &s->d_Vinv, (size_t)n * 6));
   COSL_TRY(dev_alloc(s->stream, &s->d_entries, (size_t)nEntries));
@@ -545,6 +553,7 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   UP(s->d_ptr, p->ptr, sizeof(long long) * ((size_t)n + 1));
   if (!items.empty()) UP(s->d_items, items.data(), sizeof(BaPairItem) * items.size());
   if (!rowDst.empty()) UP(s->d_rowDst, rowDst.data(), sizeof(BaRowDst) * rowDst.size());
+  if (!visit.empty()) UP(s->d_visit, visit.data(), sizeof(int4) * visit.size());
   UP(s->d_cptrFree, cptrFree.data(), sizeof(int) * cptrFree.size());
   if (nEntries) UP(s->d_entries, entries.data(), sizeof(int2) * (size_t)nEntries);
   // two ticket lists (each keeps the critical-path-first order, hence stays topological)
@@ -766,7 +775,7 @@ int solve_trial(cosl_ba_solver* s, double mu, bool* solved) {
       if (s->n) COSL_LAUNCH(ba_vinv_kernel, (unsigned)div_up64(s->n, 256), 256, 0, s->stream, s->d, mu, s->d_Vinv);
       if (s->Nc)
         COSL_LAUNCH(ba_schur_rows, s->mf * s->rowSplits, 32 * BA_ROWS_WARPS, s->rowsSmem, s->stream, s->d,
-                    s->d_cptrFree, s->d_rowDst, s->nSlots, s->d_Vinv, s->d_solIdx, s->rowSplits);
+                    s->d_cptrFree, s->d_visit, s->d_rowDst, s->nSlots, s->d_Vinv, s->d_solIdx, s->rowSplits);
     } else if (s->nItems) {
       COSL_LAUNCH(ba_schur_pairs, div_up(s->nItems, 4), 128, 0, s->stream, s->d, s->d_items,
                   s->nItems, s->d_entries, mu);

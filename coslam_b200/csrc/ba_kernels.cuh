@@ -511,9 +511,14 @@ __global__ void __launch_bounds__(256) ba_vinv_kernel(BaDev d, double mu, double
 
 constexpr int BA_ROWS_WARPS = 4;
 
+// visit = one (camera a, point i) pair of the camera-major list: {observation o, point i, first
+// observation of i, number of observations of i}.  The records and the camera lists of the NEXT
+// visits are prefetched while the current one is processed, so the dependent chain per visit is
+// one level of loads (W rows) instead of four (cobs -> pt -> ptr -> cam -> W).
 __global__ void __launch_bounds__(32 * BA_ROWS_WARPS)
-ba_schur_rows(BaDev d, const int* __restrict__ cptr, const BaRowDst* __restrict__ rowDst, int nSlots,
-              const double* __restrict__ Vinv, const int* __restrict__ rhsIdx, int splits) {
+ba_schur_rows(BaDev d, const int* __restrict__ cptr, const int4* __restrict__ visit,
+              const BaRowDst* __restrict__ rowDst, int nSlots, const double* __restrict__ Vinv,
+              const int* __restrict__ rhsIdx, int splits) {
   extern __shared__ double sacc[];  // [BA_ROWS_WARPS][stride]
   __shared__ int s_list[BA_ROWS_WARPS][32], s_slot[BA_ROWS_WARPS][32];
   __shared__ double s_Y[BA_ROWS_WARPS][18];
@@ -525,51 +530,64 @@ ba_schur_rows(BaDev d, const int* __restrict__ cptr, const BaRowDst* __restrict_
   double* acc = sacc + (size_t)w * stride;
   for (int e = lane; e < stride; e += 32) acc[e] = 0.0;
   __syncwarp();
-  for (int q = cptr[af] + part * BA_ROWS_WARPS + w; q < cptr[af + 1]; q += BA_ROWS_WARPS * splits) {
-    const int o = d.cobs[q], i = d.pt[o];
-    if (i < d.ncon) continue;  // fixed points do not enter the reduced system (warp-uniform)
-    const double* Vi = Vinv + 6 * (size_t)i;
-    const double i0 = Vi[0], i1 = Vi[1], i2 = Vi[2], i3 = Vi[3], i4 = Vi[4], i5 = Vi[5];
-    if (lane < 18) {  // Y = W_o Vinv_i, entry (r, c) = lane
-      const int r = lane / 3, c = lane - 3 * r;
-      const double* wr = d.W + 18 * (size_t)o + 3 * r;
-      const double v0 = (c == 0) ? i0 : (c == 1) ? i1 : i2;
-      const double v1 = (c == 0) ? i1 : (c == 1) ? i3 : i4;
-      const double v2 = (c == 0) ? i2 : (c == 1) ? i4 : i5;
-      s_Y[w][lane] = wr[0] * v0 + wr[1] * v1 + wr[2] * v2;
-    }
-    __syncwarp();
-    double Y[18];
-#pragma unroll
-    for (int k = 0; k < 18; ++k) Y[k] = s_Y[w][k];
-    if (lane < 6) {  // rhs_a -= Y eb_i
-      const double* eb = d.eb + 3 * (size_t)i;
-      const double* yr = &s_Y[w][3 * lane];
-      acc[nSlots * 36 + lane] += yr[0] * eb[0] + yr[1] * eb[1] + yr[2] * eb[2];
-    }
-    const long long p0 = d.ptr[i], p1 = d.ptr[i + 1];
-    for (long long base = p0; base < p1; base += 32) {
-      const long long ob = base + lane;
-      const int bf = (ob < p1) ? d.cam[ob] - d.mcon : -1;
-      const bool ok = bf >= af;
-      const unsigned mask = __ballot_sync(0xffffffffu, ok);
-      const int nq = __popc(mask);
-      if (ok) {
-        const int pos = __popc(mask & ((1u << lane) - 1u));
-        s_list[w][pos] = (int)ob;
-        s_slot[w][pos] = bf - af;
+  const int qend = cptr[af + 1], step = BA_ROWS_WARPS * splits;
+  int q = cptr[af] + part * BA_ROWS_WARPS + w;
+  const int4 none = make_int4(0, -1, 0, 0);
+  int4 r0 = (q < qend) ? visit[q] : none;
+  int4 r1 = (q + step < qend) ? visit[q + step] : none;
+  int camCur = (r0.y >= 0 && lane < r0.w) ? d.cam[r0.z + lane] : -1;
+  for (; q < qend; q += step) {
+    const int4 r2 = (q + 2 * step < qend) ? visit[q + 2 * step] : none;
+    const int camNext = (r1.y >= 0 && lane < r1.w) ? d.cam[r1.z + lane] : -1;
+    const int o = r0.x, i = r0.y;
+    if (i >= d.ncon) {  // fixed points do not enter the reduced system (warp-uniform)
+      const double* Vi = Vinv + 6 * (size_t)i;
+      const double i0 = Vi[0], i1 = Vi[1], i2 = Vi[2], i3 = Vi[3], i4 = Vi[4], i5 = Vi[5];
+      if (lane < 18) {  // Y = W_o Vinv_i, entry (r, c) = lane
+        const int r = lane / 3, c = lane - 3 * r;
+        const double* wr = d.W + 18 * (size_t)o + 3 * r;
+        const double v0 = (c == 0) ? i0 : (c == 1) ? i1 : i2;
+        const double v1 = (c == 0) ? i1 : (c == 1) ? i3 : i4;
+        const double v2 = (c == 0) ? i2 : (c == 1) ? i4 : i5;
+        s_Y[w][lane] = wr[0] * v0 + wr[1] * v1 + wr[2] * v2;
       }
       __syncwarp();
-      for (int t = lane; t < 6 * nq; t += 32) {
-        const int j = t / 6, sc = t - 6 * j;
-        const double* wb = d.W + 18 * (size_t)s_list[w][j] + 3 * sc;
-        const double w0 = wb[0], w1 = wb[1], w2 = wb[2];
-        double* ap = acc + s_slot[w][j] * 36 + sc;
+      double Y[18];
 #pragma unroll
-        for (int r = 0; r < 6; ++r) ap[6 * r] += Y[3 * r] * w0 + Y[3 * r + 1] * w1 + Y[3 * r + 2] * w2;
+      for (int k = 0; k < 18; ++k) Y[k] = s_Y[w][k];
+      if (lane < 6) {  // rhs_a -= Y eb_i
+        const double* eb = d.eb + 3 * (size_t)i;
+        const double* yr = &s_Y[w][3 * lane];
+        acc[nSlots * 36 + lane] += yr[0] * eb[0] + yr[1] * eb[1] + yr[2] * eb[2];
       }
-      __syncwarp();
+      const int p0 = r0.z, p1 = r0.z + r0.w;
+      for (int base = p0; base < p1; base += 32) {
+        const int ob = base + lane;
+        const int cm = (base == p0) ? camCur : ((ob < p1) ? d.cam[ob] : -1);
+        const int bf = (ob < p1) ? cm - d.mcon : -1;
+        const bool ok = bf >= af;
+        const unsigned mask = __ballot_sync(0xffffffffu, ok);
+        const int nq = __popc(mask);
+        if (ok) {
+          const int pos = __popc(mask & ((1u << lane) - 1u));
+          s_list[w][pos] = ob;
+          s_slot[w][pos] = bf - af;
+        }
+        __syncwarp();
+        for (int t = lane; t < 6 * nq; t += 32) {
+          const int j = t / 6, sc = t - 6 * j;
+          const double* wb = d.W + 18 * (size_t)s_list[w][j] + 3 * sc;
+          const double w0 = wb[0], w1 = wb[1], w2 = wb[2];
+          double* ap = acc + s_slot[w][j] * 36 + sc;
+#pragma unroll
+          for (int r = 0; r < 6; ++r) ap[6 * r] += Y[3 * r] * w0 + Y[3 * r + 1] * w1 + Y[3 * r + 2] * w2;
+        }
+        __syncwarp();
+      }
     }
+    r0 = r1;
+    r1 = r2;
+    camCur = camNext;
   }
   __syncthreads();
   for (int e = threadIdx.x; e < nSlots * 36; e += 32 * BA_ROWS_WARPS) {

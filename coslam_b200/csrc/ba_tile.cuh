@@ -757,10 +757,13 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
         sM[tid] = __ldcg(gm + tid);
         sM[tid + BA_NTHREADS] = __ldcg(gm + tid + BA_NTHREADS);
       }
-      // thread (c = tid >> 2, q = tid & 3) accumulates rows 16q .. 16q+15 of column c over ALL
-      // entries and reduces once; the loads of four tiles are in flight together
-      const int c = tid >> 2, q = tid & 3;
-      double p0 = 0, p1 = 0;
+      // warp w owns columns 8w .. 8w+7, lane l rows 2l, 2l+1: every load instruction of a warp reads
+      // one whole 512-byte column (coalesced); partial sums stay in registers over ALL entries and
+      // are reduced across the lanes once.  The loads of four tiles are in flight together.
+      const int lane = tid & 31, wq = tid >> 5;
+      double p[8];
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) p[jj] = 0.0;
       for (int e0 = t.l0; e0 < t.l1; e0 += 8) {
         const int ne = min(8, t.l1 - e0);
         __syncthreads();
@@ -770,31 +773,47 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
         for (int eb = 0; eb < ne; eb += 4) {
           double2 v[4][8];
 #pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            const int e = min(eb + w, ne - 1);
+          for (int w4 = 0; w4 < 4; ++w4) {
+            const int e = min(eb + w4, ne - 1);
             const double2* col = reinterpret_cast<const double2*>(
-                d.tiles + (size_t)d.bwd[e0 + e].tile * BA_TILE + c * BA_TB + 16 * q);
+                d.tiles + (size_t)d.bwd[e0 + e].tile * BA_TILE + (8 * wq) * BA_TB) + lane;
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[w][u] = __ldcg(col + u);
+            for (int jj = 0; jj < 8; ++jj) v[w4][jj] = __ldcg(col + jj * (BA_TB / 2));
           }
 #pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            if (eb + w < ne) {
-              const double* xv = sX + (eb + w) * BA_TB + 16 * q;
+          for (int w4 = 0; w4 < 4; ++w4) {
+            if (eb + w4 < ne) {
+              const double2 xv = *reinterpret_cast<const double2*>(sX + (eb + w4) * BA_TB + 2 * lane);
 #pragma unroll
-              for (int u = 0; u < 8; ++u) {
-                p0 = __fma_rn(v[w][u].x, xv[2 * u], p0);
-                p1 = __fma_rn(v[w][u].y, xv[2 * u + 1], p1);
-              }
+              for (int jj = 0; jj < 8; ++jj) p[jj] = __fma_rn(v[w4][jj].x, xv.x, __fma_rn(v[w4][jj].y, xv.y, p[jj]));
             }
           }
         }
       }
-      double part = p0 + p1;
-      part += __shfl_xor_sync(0xffffffffu, part, 1);
-      part += __shfl_xor_sync(0xffffffffu, part, 2);
-      __syncthreads();
-      if (q == 0) sV[c] -= part;
+      // transpose-reduce: 8 values x 32 lanes -> lane group (l >> 2) holds column 8w + (l >> 2)
+      {
+        const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+        double a4[4], a2[2];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          const double send = b4 ? p[jj] : p[jj + 4];
+          const double keep = b4 ? p[jj + 4] : p[jj];
+          a4[jj] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const double send = b3 ? a4[jj] : a4[jj + 2];
+          const double keep = b3 ? a4[jj + 2] : a4[jj];
+          a2[jj] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+        const double send = b2 ? a2[0] : a2[1];
+        double part = (b2 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, send, 4);
+        part += __shfl_xor_sync(0xffffffffu, part, 2);
+        part += __shfl_xor_sync(0xffffffffu, part, 1);
+        __syncthreads();
+        // the lane group with bits (b4, b3, b2) holds column 4 b4 + 2 b3 + b2 of this warp
+        if ((lane & 3) == 0) sV[8 * wq + (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0)] -= part;
+      }
       __syncthreads();
       if (d.trace && tid == 0) d.trace[8 * (size_t)ti + 4] = ba_globaltimer();
       if (tid < 64) {
