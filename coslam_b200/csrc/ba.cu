@@ -395,7 +395,10 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
       }
   s->nSlots = bandw + 1;
   s->rowsSmem = sizeof(double) * (size_t)BA_ROWS_WARPS * ((size_t)s->nSlots * 36 + 8);
-  s->useRows = mf > 0 && s->rowsSmem <= 160 * 1024 && std::getenv("COSL_BA_SCHUR_PAIRS") == nullptr;
+  // Measured at c4 (profiles/r2d_ba_schur_rows.summary.txt): the camera-row kernel halves the DRAM
+  // traffic and needs no atomics but is L1TEX-bound on its 24-byte row reads (0.73 ms vs 0.51 ms
+  // for the pair lists), so the pair-list kernel stays the default; COSL_BA_SCHUR_ROWS=1 selects it.
+  s->useRows = mf > 0 && s->rowsSmem <= 160 * 1024 && std::getenv("COSL_BA_SCHUR_ROWS") != nullptr;
   // few cameras with long observation lists (local BA): split each list over several CTAs
   s->rowSplits = (mf > 0 && mf < 296) ? std::max(1, std::min(64, 296 / mf)) : 1;
   if (Nc / std::max(1, mf * s->rowSplits) < 64) s->rowSplits = std::max(1, (int)(Nc / 64 / std::max(1, mf)));

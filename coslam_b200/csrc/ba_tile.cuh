@@ -45,7 +45,7 @@ struct BaTileDev {
 };
 
 constexpr int BA_LDS = 68;                                   // smem leading dimension of a staged tile
-constexpr int BA_TILE_SMEM_DOUBLES = 3 * BA_TB * BA_LDS + 8 * BA_TB + 8 * BA_TB + 2 * BA_TB + 80;
+constexpr int BA_TILE_SMEM_DOUBLES = 3 * BA_TB * BA_LDS + 8 * BA_TB + 8 * BA_TB + 2 * BA_TB + 96;
 constexpr int BA_TILE_SMEM = BA_TILE_SMEM_DOUBLES * (int)sizeof(double);
 constexpr int BA_NTHREADS = 256;
 
@@ -381,7 +381,19 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 
 // sT: tile staged column-major with ld BA_LDS (element (r, c) at c*BA_LDS + r), lower part valid,
 // identity on the padding.  sBv: right-hand side (64); sYv: y out (64); sM: [8][8][8] M_b[q][q']
-// out; sD: 72 doubles scratch.
+// out; sD: 80 doubles scratch.
+// The panel warps are alone on their schedulers, so their time is their instruction count: every
+// row -- the panel's own rows included -- runs the same row solve (for a panel row it yields the row
+// of the Cholesky factor), and the 8x8 inverses are left to the update warps.
+__device__ __forceinline__ double ba_rsqrt_pivot(double d) {
+  // pivots of a damped Gauss-Newton system lie far inside the float range (checked by the caller)
+  double y = (double)rsqrtf((float)d);
+  const double h = 0.5 * d;
+  y = __fma_rn(y, __fma_rn(-h * y, y, 0.5), y);
+  y = __fma_rn(y, __fma_rn(-h * y, y, 0.5), y);
+  return y;
+}
+
 __device__ __forceinline__ void tile_potrf2(double* __restrict__ sT, double* __restrict__ sBv,
                                             double* __restrict__ sYv, double* __restrict__ sM,
                                             double* __restrict__ sD, int tid, int* s_fail) {
@@ -404,24 +416,21 @@ __device__ __forceinline__ void tile_potrf2(double* __restrict__ sT, double* __r
         sD[64 + r - c0] = br;
       }
       named_bar_sync(1, 64);
-      double D[8][8], inv[8], bb[8];
+      double D[8][8], inv[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i)
 #pragma unroll
         for (int j = 0; j <= i; ++j) D[i][j] = sD[i * 8 + j];
-#pragma unroll
-      for (int q = 0; q < 8; ++q) bb[q] = sD[64 + q];
       bool bad = false;
 #pragma unroll
       for (int p = 0; p < 8; ++p) {
         double dd = D[p][p];
-        if (!(dd > 0) || !isfinite(dd)) {
+        if (!(dd > 1e-30 && dd < 1e30)) {  // also catches NaN
           bad = true;
           dd = 1.0;
         }
-        const double rs = ba_rsqrt_fast(dd);
+        const double rs = ba_rsqrt_pivot(dd);
         inv[p] = rs;
-        D[p][p] = dd * rs;
 #pragma unroll
         for (int i = p + 1; i < 8; ++i) D[i][p] *= rs;
 #pragma unroll
@@ -429,66 +438,66 @@ __device__ __forceinline__ void tile_potrf2(double* __restrict__ sT, double* __r
 #pragma unroll
           for (int i = j; i < 8; ++i) D[i][j] = __fma_rn(-D[i][p], D[j][p], D[i][j]);
       }
-      // y of this panel (every panel thread computes it; thread 0 publishes)
-      {
+      if (r == 0) {  // y of this panel and the reciprocal diagonal, for the other warps
         double yv[8];
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          double s = bb[q];
+          double s = sD[64 + q];
 #pragma unroll
           for (int p = 0; p < q; ++p) s = __fma_rn(-D[q][p], yv[p], s);
           yv[q] = s * inv[q];
+          sYv[c0 + q] = yv[q];
+          sD[72 + 8 * (pb & 1) + q] = inv[q];  // double buffered: read by the update warps of this panel
         }
-        if (r == 0) {
-#pragma unroll
-          for (int q = 0; q < 8; ++q) sYv[c0 + q] = yv[q];
-          if (bad) *s_fail = 1;
-        }
+        if (bad) *s_fail = 1;
       }
-      if (r >= c0 + 8) {
+      if (r >= c0) {
+        // row solve x L_D^T = a.  For a row of the panel itself (r = c0 + cc) the entries q <= cc are
+        // exactly row cc of the Cholesky factor; the ones right of the diagonal are zeroed.
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           double s = a[q];
 #pragma unroll
           for (int p = 0; p < q; ++p) s = __fma_rn(-x[p], D[q][p], s);
-          x[q] = s * inv[q];
+          x[q] = (c0 + q <= r) ? s * inv[q] : 0.0;
         }
 #pragma unroll
         for (int q = 0; q < 8; ++q) sT[(c0 + q) * BA_LDS + r] = x[q];
-      } else if (r >= c0) {
-        const int cc = r - c0;
-        double m[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          double v = 0.0;
-#pragma unroll
-          for (int aa = 0; aa < 8; ++aa)
-            if (aa == cc && q <= aa) v = D[aa][q];
-          sT[(c0 + q) * BA_LDS + r] = v;  // row cc of the factored diagonal block, zeros above
-          double s = (q == cc) ? 1.0 : 0.0;  // column cc of M = inverse of the 8x8 factor
-#pragma unroll
-          for (int p = 0; p < q; ++p) s = __fma_rn(-D[q][p], m[p], s);
-          m[q] = s * inv[q];
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) sM[pb * 64 + q * 8 + cc] = m[q];
       }
     }
     __syncthreads();  // X and y of this panel are visible; the update warps finished the previous panel
-    if (pb == 7) break;
     if (isP) {
-      if (r >= c0 + 8) {  // look-ahead: next panel's columns of this row, kept in registers
+      if (pb < 7 && r >= c0 + 8) {  // look-ahead: next panel's columns of this row, kept in registers
 #pragma unroll
         for (int qn = 0; qn < 8; ++qn) a[qn] = sT[(c0 + 8 + qn) * BA_LDS + r];
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
+        for (int q = 0; q < 8; ++q) {
+          const double2* xr = reinterpret_cast<const double2*>(sT + (c0 + q) * BA_LDS + c0 + 8);
 #pragma unroll
-          for (int qn = 0; qn < 8; ++qn) a[qn] = __fma_rn(-x[q], sT[(c0 + q) * BA_LDS + c0 + 8 + qn], a[qn]);
+          for (int h2 = 0; h2 < 4; ++h2) {
+            const double2 xx = xr[h2];  // X(c0+8+2h2, q), X(c0+9+2h2, q)
+            a[2 * h2] = __fma_rn(-x[q], xx.x, a[2 * h2]);
+            a[2 * h2 + 1] = __fma_rn(-x[q], xx.y, a[2 * h2 + 1]);
+          }
+        }
 #pragma unroll
         for (int q = 0; q < 8; ++q) br = __fma_rn(-x[q], sYv[c0 + q], br);  // b_r -= X(r, :) y_panel
       }
     } else {
       const int u = tid - 64;  // 0 .. 191
+      if (u >= 184) {
+        // inverse of the panel's 8x8 factor block, column cc per thread: M e_cc by forward substitution
+        const int cc = u - 184;
+        double m[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          double s = (q == cc) ? 1.0 : 0.0;
+#pragma unroll
+          for (int p = 0; p < q; ++p) s = __fma_rn(-sT[(c0 + p) * BA_LDS + c0 + q], m[p], s);
+          m[q] = s * sD[72 + 8 * (pb & 1) + q];
+          sM[pb * 64 + q * 8 + cc] = m[q];
+        }
+      }
       // trailing lower triangle right of the NEXT panel: rows ti + 16a, columns tj + 12b
       const int ti = u & 15, tj = u >> 4;
       if (c0 + 16 < 64) {
@@ -519,6 +528,7 @@ __device__ __forceinline__ void tile_potrf2(double* __restrict__ sT, double* __r
       }
     }
   }
+  __syncthreads();  // the last panel's inverse block (written by the update warps)
 }
 
 // X L^T = A in place in sA (rows = this warp's 8 rows; ld BA_LDS); sL: L staged like sA; sM: M_b.
@@ -587,7 +597,7 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
   double* sM = sX + 8 * BA_TB;             // [8][8][8] inverses of the diagonal 8x8 blocks
   double* sV = sM + 8 * BA_TB;             // [64]
   double* sY = sV + BA_TB;                 // [64]
-  double* sD = sY + BA_TB;                 // [72] panel scratch of tile_potrf2
+  double* sD = sY + BA_TB;                 // [80] panel scratch of tile_potrf2
   __shared__ int s_task, s_fail;
   const int tid = threadIdx.x;
   const bool special = (int)blockIdx.x < d.nSpecial;

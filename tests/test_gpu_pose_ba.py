@@ -167,17 +167,17 @@ def test_ba_c4_slice_parity(api, orc):
     assert np.abs(pg.X - po.X).max() < 1e-6
 
 
-def test_ba_schur_pair_list_fallback(api, orc, monkeypatch):
-    """The pair-list Schur kernel (used when the camera band does not fit shared memory) must give
-    the same solve as the default camera-row kernel; forced here through COSL_BA_SCHUR_PAIRS."""
+def test_ba_schur_camera_row_kernel(api, orc, monkeypatch):
+    """The camera-row Schur kernel (no atomics, deterministic; COSL_BA_SCHUR_ROWS=1) must give the
+    same solve as the default pair-list kernel."""
     prob, truth = synth.make_ba_scene(4, 12, 2500, 1280, 720, seed=33, m_con=4, n_con=1)
     opt = BaOptions.defaults()
     opt.outer_iters, opt.inner_iters = 2, 6
     p_rows, p_pairs = prob.copy(), prob.copy()
-    i_rows = api.ba_solve(p_rows, opt)
-    monkeypatch.setenv("COSL_BA_SCHUR_PAIRS", "1")
     i_pairs = api.ba_solve(p_pairs, opt)
-    monkeypatch.delenv("COSL_BA_SCHUR_PAIRS")
+    monkeypatch.setenv("COSL_BA_SCHUR_ROWS", "1")
+    i_rows = api.ba_solve(p_rows, opt)
+    monkeypatch.delenv("COSL_BA_SCHUR_ROWS")
     assert i_rows[10] == i_pairs[10]
     assert abs(i_rows[1] - i_pairs[1]) <= 1e-10 * i_rows[1]
     assert np.abs(p_rows.X - p_pairs.X).max() < 1e-8
