@@ -29,7 +29,18 @@ sys.path.insert(0, ROOT)
 KLT_W, KLT_H, KLT_C, KLT_FW, KLT_FH, KLT_L = 1280, 720, 4, 50, 40, 6
 KLT_FRAMES = 8
 BA_CAMS, BA_KF, BA_PTS = 4, 200, 50000
-FP64_NOMINAL_TFLOPS = 40.0  # B200 FP64 (nominal; MEASURED_PEAKS.json has no fp64 entry)
+FP64_NOMINAL_TFLOPS = 40.0  # fallback only: the measured figure is in profiles/r2_peaks.json
+
+
+def pipe_peaks():
+    """fp64 / fp32 peaks of this pool's B200s measured with tools/peaks.cu (register-only FMA and
+    DMMA chains on all SMs); MEASURED_PEAKS.json only holds HBM and bf16 tensor figures."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2_peaks.json")))
+        return {"fp64": float(d["fp64_fma_tflops"]), "fp64_dmma": float(d["fp64_dmma_tflops"]),
+                "fp32": float(d["fp32_fma_tflops"]), "source": "measured (tools/peaks.cu, profiles/r2_peaks.json)"}
+    except Exception:
+        return {"fp64": FP64_NOMINAL_TFLOPS, "fp64_dmma": FP64_NOMINAL_TFLOPS, "fp32": 74.4, "source": "nominal"}
 
 
 def peaks():
@@ -121,7 +132,7 @@ class ClockSampler:
 
 # dominant kernel of every timed class, and its DRAM bytes per launch from the committed ncu capture
 KERNEL_OF_CLASS = {"klt_track": "klt_gain_fused", "klt_pyramid": "klt_front",
-                   "ba_solve": "ba_chol_potf2_inv", "ba_schur": "ba_schur_pairs"}
+                   "ba_solve": "ba_tile_solve", "ba_schur": "ba_schur_pairs"}
 
 
 def ncu_traffic(kernel):
@@ -166,8 +177,8 @@ def run_reference(args):
     trk = [orc.OracleKlt(cfg, KLT_W, KLT_H, KLT_L, KLT_FW, KLT_FH) for _ in range(KLT_C)]
     for c in range(KLT_C):
         trk[c].first(seqs[c].frame(0))
-    steps = max(1, min(args.steps, 12))
-    warm = max(1, min(args.warmup, 2))
+    steps = max(1, args.steps)  # one step = one 4-camera frame (~50 ms of CPU): no cap
+    warm = max(1, args.warmup)
     i = 1
     for _ in range(warm):
         for c in range(KLT_C):
@@ -304,15 +315,14 @@ def run_cuda(args):
                             "achieved": grp.algorithmic_bytes() / (ms_val / K * 1e-3) / 1e9,
                             "frac": grp.algorithmic_bytes() / (ms_val / K * 1e-3) / 1e9 / hbm_peak}}
     # SURVEY 8(d) lists the LK solve as FP32-SIMT co-bound: 123 kflop per feature (70 w^2 flops per
-    # window evaluation, 36 evaluations).  No measured fp32 peak exists in MEASURED_PEAKS.json, so the
-    # denominator is the nominal 148 SMs x 128 FMA lanes x 2 flop at 1.965 GHz, labelled as such.
+    # window evaluation, 36 evaluations); denominator = the fp32 FMA peak measured by tools/peaks.cu.
     if top == "klt_track":
         lk_flops = 123.0e3 * KLT_C * F
-        fp32_nominal = 148 * 128 * 2 * 1.965e9 / 1e12
+        pp = pipe_peaks()
         roof["fp32_co_bound"] = {"algorithmic_flops_per_step": lk_flops,
                                  "achieved_tflops": lk_flops / (top_ms * 1e-3) / 1e12,
-                                 "peak_tflops": fp32_nominal, "peak_source": "nominal",
-                                 "frac": lk_flops / (top_ms * 1e-3) / 1e12 / fp32_nominal}
+                                 "peak_tflops": pp["fp32"], "peak_source": pp["source"],
+                                 "frac": lk_flops / (top_ms * 1e-3) / 1e12 / pp["fp32"]}
     # ---- e2e: host buffers through the public C-ABI call, H2D + D2H inside the timed region
     host_np = [[h.numpy() for h in row] for row in host]
     host_args = [grp.host_ptrs(row) for row in host_np]  # pointer arrays built once per frame
@@ -330,6 +340,22 @@ def run_cuda(args):
     grp.sync()
     wall = time.perf_counter() - t_wall
     ms_e2e = max_over_ranks(max(e2.elapsed_time(e3), wall * 1e3))
+    # the real caller's frames (SingleSLAM::m_img) are pageable: same call from ordinary numpy arrays
+    e2e_pageable = None
+    if rank == 0:
+        pag = [[np.array(h.numpy(), copy=True) for h in row] for row in host]
+        pag_args = [grp.host_ptrs(row) for row in pag]
+        for _ in range(3):
+            grp.next_raw(pag_args[fidx(i)])
+            i += 1
+        tpg = time.perf_counter()
+        for _ in range(K):
+            grp.next_raw(pag_args[fidx(i)])
+            i += 1
+        grp.sync()
+        mspg = 1e3 * (time.perf_counter() - tpg)
+        e2e_pageable = {"value": KLT_C * F * K / (mspg * 1e-3), "unit": "features/s", "ms_per_step": mspg / K,
+                        "note": "pageable host frames (plain numpy), rank 0 only"}
     clk = clocks.stop()  # sampled across the device-resident, profiled and end-to-end regions
     barrier()
     klt_value = world * KLT_C * F * K / (ms_val * 1e-3)
@@ -398,8 +424,53 @@ def run_cuda(args):
                                     "cores": 1, "kind": "port", "sample": "10 repetitions"}
 
 
+    # ------------------------------------------------------------------ the other BASELINE configs
+    extra = {}
+    if rank == 0 and world == 1 and not args.quick:
+        # c3: local BA per key frame (20 poses / 20 k points) and the 30 fps pipeline target
+        lb3, prob3 = run_local_ba(api, synth, BaOptions, torch, local, "c3", 4, 20000, KLT_W, KLT_H, args.no_cpu)
+        extra["c3_local_ba"] = lb3
+        extra["pipeline"] = run_pipeline(api, synth, BaOptions, torch, local, grp, seqs, host_args, prob3)
+        # c2: 2 cameras 640x480, 1 k features/camera, 5 k-point local BA
+        k2, g2c, _, _ = run_klt_leg(api, synth, torch, local, "c2", 2, 640, 480, 40, 25, min(K, 50), synth.BASE_SEED + 200)
+        g2c.close()
+        lb2, _ = run_local_ba(api, synth, BaOptions, torch, local, "c2", 2, 5000, 640, 480, args.no_cpu)
+        extra["c2"] = {"klt": k2, "local_ba": lb2}
+    if not args.quick:
+        # c5: 8 cameras 1920x1080, 4 k features/camera; camera c -> GPU c mod N (replicas only)
+        ncam5 = max(1, 8 // world)
+        k5, g5, _, _ = run_klt_leg(api, synth, torch, local, "c5", ncam5, 1920, 1080, 80, 50, min(K, 30),
+                                   synth.BASE_SEED + 300 + 16 * rank, frames=3)
+        g5.close()
+        ms5 = max_over_ranks(k5["e2e"]["ms_per_step"])
+        if rank == 0:
+            k5["config"]["workload"] += f"; 8 cameras over {world} GPU(s), {ncam5} per GPU"
+            k5["fps_8cam_e2e"] = 1e3 / ms5
+            k5["meets_30fps"] = bool(1e3 / ms5 >= 30.0)
+            extra["c5"] = k5
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
     cpu = None
+    klt_parity = None
+    if rank == 0 and not args.no_cpu:
+        # oracle parity of the LK solve + slot logic on the benchmark's own sequence (camera 0,
+        # first + 2 x next): max |dpos| in pixels and status flips
+        from oracle import orc as _o
+        _o.set_threads(_o.max_threads())
+        gk = api.KltTracker(cfg, KLT_W, KLT_H, KLT_L, KLT_FW, KLT_FH, device=local)
+        ok = _o.OracleKlt(cfg, KLT_W, KLT_H, KLT_L, KLT_FW, KLT_FH)
+        fg, _ = gk.first(seqs[0].frames[0])
+        fo, _ = ok.first(seqs[0].frames[0])
+        worst, flips = 0.0, 0
+        for kk in (1, 2):
+            fg, _ = gk.next(seqs[0].frames[kk])
+            fo, _ = ok.next(seqs[0].frames[kk])
+            same = fg["status"] == fo["status"]
+            flips += int((~same).sum())
+            live = same & (fo["status"] >= 0)
+            if live.any():
+                worst = max(worst, float((np.abs(fg["pos"][live] - fo["pos"][live]) * [KLT_W, KLT_H]).max()))
+        klt_parity = {"parity_max_dpos_px": worst, "status_flips": flips, "slots": KLT_FW * KLT_FH,
+                      "sample": "camera 0 of the bench sequence, first() + 2 x next() vs the CPU oracle"}
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = cpu_baseline_klt(cfg, seqs)
     if rank == 0:
@@ -430,6 +501,12 @@ def run_cuda(args):
             line["ba"] = ba
         if pose is not None:
             line["pose"] = pose
+        if klt_parity is not None:
+            line["klt_parity"] = klt_parity
+        if e2e_pageable is not None:
+            line["e2e"]["pageable"] = e2e_pageable
+        line.update(extra)
+        line["peaks"] = {"hbm_gbs": hbm_peak, "hbm_source": peak_src, **pipe_peaks()}
         emit(line)
     if dist is not None:
         dist.barrier()
@@ -452,6 +529,40 @@ def cpu_baseline_klt(cfg, seqs):
     return {"value": KLT_C * KLT_FW * KLT_FH * nfr / dt, "unit": "features/s", "cores": cores,
             "kind": "port", "sample": f"{nfr} frames x {KLT_C} cameras of the same c3 sequence",
             "ms_per_step": 1e3 * dt / nfr}
+
+
+def ba_roofline(tm, trials, prob, st, world, solver):
+    """Roofline of the dominant kernel class of an LM trial (per-class CUDA events)."""
+    tot = sum(v[0] for v in tm.values())
+    top = max(tm, key=lambda k: tm[k][0])
+    top_ms = tm[top][0] / max(1, trials)
+    ns = 6 * (prob.m - prob.m_con)
+    pp = pipe_peaks()
+    if top == "ba_solve":
+        # multiply-adds the tile Cholesky + substitutions really perform (ba_plan.h counts them on
+        # the used rows: nested dissection adds fill but cuts the dependency chain); the kernel is
+        # bound by that chain, not by the fp64 pipe -- the fraction says how far
+        flops = 2.0 * st["factor_flops"]
+        roof = {"bound": "tensor", "kernel": "ba_tile_solve (persistent dataflow tile Cholesky, fp64 DMMA)",
+                "achieved": flops / (top_ms * 1e-3) / 1e12, "peak": pp["fp64_dmma"], "unit": "TFLOP/s",
+                "frac": flops / (top_ms * 1e-3) / 1e12 / pp["fp64_dmma"],
+                "traffic": ncu_traffic("ba_tile_solve"), "peak_source": pp["source"],
+                "algorithmic_flops_per_trial": flops, "dense_flops_per_trial": 2.0 * ns ** 3 / 3.0,
+                "plan": solver.plan_info()}
+    else:
+        hbm_peak, src = peaks()
+        byts = {"ba_schur": 8.0 * st["reduce_doubles"] + 144.0 * prob.nobs + 48.0 * prob.n,
+                "ba_linearize": 24.0 * prob.nobs + 24.0 * prob.n + 144.0 * prob.nobs,
+                "ba_backsub": 8.0 * prob.nobs + 48.0 * prob.n, "ba_cost": 24.0 * prob.nobs,
+                "ba_allreduce": 8.0 * st["reduce_doubles"] * world}.get(top, 0.0) / world
+        roof = {"bound": "hbm", "kernel": top, "achieved": byts / (top_ms * 1e-3) / 1e9,
+                "peak": hbm_peak, "unit": "GB/s", "frac": byts / (top_ms * 1e-3) / 1e9 / hbm_peak,
+                "traffic": ncu_traffic(KERNEL_OF_CLASS.get(top)), "peak_source": src,
+                "algorithmic_bytes_per_trial": byts}
+    roof["share_of_trial"] = {k: v[0] / max(tot, 1e-9) for k, v in tm.items()}
+    roof["ms_per_trial_by_class"] = {k: v[0] / max(1, trials) for k, v in tm.items()}
+    roof["avg_ms_per_trial"] = top_ms
+    return roof
 
 
 def run_ba(args, api, synth, BaOptions, torch, dist, rank, world, local, barrier, max_over_ranks):
@@ -495,34 +606,13 @@ def run_ba(args, api, synth, BaOptions, torch, dist, rank, world, local, barrier
     solver.run_fixed(K)
     tm = solver.timers()
     solver.profile_enable(False)
-    tot = sum(v[0] for v in tm.values())
-    top = max(tm, key=lambda k: tm[k][0])
-    ns = 6 * (prob.m - prob.m_con)
-    top_ms = tm[top][0] / max(1, trials)
     kk = np.diff(prob.ptr).astype(np.float64)
     st = solver.stats()
-    if top == "ba_solve":
-        # flops the skyline factorisation really performs (sum of column heights squared), not the
-        # dense ns^3/3: sequential key frames make the reduced system banded
-        flops = st["factor_flops"]
-        roof = {"bound": "tensor", "kernel": "ba_solve (skyline blocked fp64 Cholesky + trsv)",
-                "achieved": flops / (top_ms * 1e-3) / 1e12, "peak": FP64_NOMINAL_TFLOPS,
-                "unit": "TFLOP/s", "frac": flops / (top_ms * 1e-3) / 1e12 / FP64_NOMINAL_TFLOPS,
-                "traffic": ncu_traffic("ba_chol_potf2_inv"),
-                "peak_source": "nominal fp64 (not in MEASURED_PEAKS.json)",
-                "algorithmic_flops_per_trial": flops, "dense_flops_per_trial": ns ** 3 / 3.0,
-                "envelope_doubles": st["envelope_doubles"]}
-    else:
-        hbm_peak, src = peaks()
-        byts = {"ba_schur": 216.0 * 0.0 + 8.0 * (ns * (ns + 1) / 2) + 144.0 * prob.nobs,
-                "ba_linearize": 24.0 * prob.nobs + 24.0 * prob.n,
-                "ba_backsub": 8.0 * prob.nobs + 48.0 * prob.n, "ba_cost": 24.0 * prob.nobs,
-                "ba_allreduce": 8.0 * st["envelope_doubles"] * world}.get(top, 0.0) / world
-        roof = {"bound": "hbm", "kernel": top, "achieved": byts / (top_ms * 1e-3) / 1e9,
-                "peak": hbm_peak, "unit": "GB/s", "frac": byts / (top_ms * 1e-3) / 1e9 / hbm_peak,
-                "traffic": ncu_traffic(KERNEL_OF_CLASS.get(top)), "peak_source": src}
-    roof["share_of_trial"] = {k: v[0] / max(tot, 1e-9) for k, v in tm.items()}
-    roof["avg_ms_per_trial"] = top_ms
+    roof = ba_roofline(tm, trials, prob, st, world, solver)
+    ns = 6 * (prob.m - prob.m_con)
+    # parity at full size at EVERY N: the same 3 LM trials -> the same cost as the CPU oracle
+    solver.reset()
+    ig = solver.run_fixed(3)
     # e2e: the drop-in call with host buffers (upload + index build + solve + download)
     e2e = None
     if world == 1:
@@ -552,23 +642,185 @@ def run_ba(args, api, synth, BaOptions, torch, dist, rank, world, local, barrier
            "roofline": roof}
     if e2e is not None:
         out["e2e"] = e2e
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and not args.no_cpu:
         from oracle import orc
         cores = orc.max_threads()
         orc.set_threads(cores)
         p3 = prob.copy()
         i3 = orc.ba_run_fixed(p3, opt, 3)
-        out["cpu_baseline"] = {"value": i3[9] / i3[11], "unit": "LM-iter/s", "cores": cores,
-                               "kind": "port", "sample": f"{int(i3[9])} LM trials of the same c4 "
-                               "problem (OpenMP + OpenBLAS dpotrf)"}
-        # parity at full size: same trial count -> same cost
-        solver.reset()
-        ig = solver.run_fixed(3)
+        if world == 1:
+            out["cpu_baseline"] = {"value": i3[9] / i3[11], "unit": "LM-iter/s", "cores": cores,
+                                   "kind": "port", "sample": f"{int(i3[9])} LM trials of the same c4 "
+                                   "problem (OpenMP + OpenBLAS dpotrf)"}
         out["parity_rel_cost_diff_3_trials"] = abs(ig[1] - i3[1]) / i3[1]
     solver.close()
     if comm is not None:
         comm.close()
     return out
+
+
+def run_local_ba(api, synth, BaOptions, torch, local, name, n_cams, n_pts, W, H, no_cpu):
+    """Local BA of BASELINE c2 / c3: 5 key frames x n_cams poses, the oldest two key frames fixed
+    (nCamsCon = 2 C, app/SL_CoSLAM.cpp:1769), 2 fixed points: LM trials/s with the solver resident
+    + the drop-in call, against the HBM contract of SURVEY.md 8(d) (one pass over the observations
+    and points per LM iteration)."""
+    prob, truth = synth.make_ba_scene(n_cams, 5, n_pts, W, H, seed=synth.BASE_SEED + (3 if n_cams == 4 else 2),
+                                      m_con=2 * n_cams, n_con=2)
+    opt = BaOptions.defaults()
+    opt.device = local
+    solver = api.BaSolver(prob, opt)
+    stream = torch.cuda.ExternalStream(solver.stream(), device=local)
+    solver.run_fixed(5)
+    solver.reset()
+    K = 40
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = api.kernel_launch_count()
+    e0.record(stream)
+    info = solver.run_fixed(K)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    launches = api.kernel_launch_count() - l0
+    trials = int(info[9])
+    solver.reset()
+    solver.profile_enable(True)
+    solver.run_fixed(K)
+    tm = solver.timers()
+    solver.profile_enable(False)
+    hbm_peak, src = peaks()
+    byts = 32.0 * prob.nobs + 72.0 * prob.n  # SURVEY 8(d) "Local BA LM-iteration" contract
+    out = {"metric": "ba_lm_iters_per_s", "value": trials / (ms * 1e-3), "unit": "LM-iter/s",
+           "us_per_trial": 1e3 * ms / max(1, trials), "lm_trials": trials, "gpu_launches": int(launches),
+           "config": {"workload": f"{name} local BA: {prob.m} poses ({prob.m_con} fixed), {prob.n} points, "
+                                  f"{prob.nobs} obs, reduced system {6 * (prob.m - prob.m_con)}^2"},
+           "roofline": {"bound": "hbm", "kernel": "whole LM trial", "achieved": byts / (ms / max(1, trials) * 1e-3) / 1e9,
+                        "peak": hbm_peak, "unit": "GB/s", "peak_source": src,
+                        "frac": byts / (ms / max(1, trials) * 1e-3) / 1e9 / hbm_peak,
+                        "algorithmic_bytes_per_trial": byts,
+                        "us_per_trial_by_class": {k: 1e3 * v[0] / max(1, trials) for k, v in tm.items()}}}
+    # drop-in call (robust loop with the live parameters: 5 rounds x 10 iterations, host arrays)
+    o2 = BaOptions.defaults()
+    o2.device = local
+    api.ba_solve(prob.copy(), o2)
+    reps, dt = 3, 0.0
+    for _ in range(reps):
+        p2 = prob.copy()
+        t0 = time.perf_counter()
+        inf2 = api.ba_solve(p2, o2)
+        dt += time.perf_counter() - t0
+    dt /= reps
+    out["e2e"] = {"value": inf2[10] / dt, "unit": "LM-iter/s", "ms_per_call": 1e3 * dt, "lm_trials": int(inf2[10]),
+                  "h2d_bytes_per_step": int(prob.nobs * 24 + prob.n * 24 + prob.m * 168),
+                  "d2h_bytes_per_step": int(prob.n * 24 + prob.m * 96 + prob.nobs),
+                  "call": "bundleAdjustRobust drop-in (cosl_ba_solve, maxErr 6, 5 rounds x 10 LM iterations)",
+                  "rms_after": p2.rms(~truth["is_outlier"])}
+    if not no_cpu:
+        from oracle import orc
+        po = prob.copy()
+        t0 = time.perf_counter()
+        io = orc.ba_solve(po, o2)
+        dto = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": io[10] / dto, "unit": "LM-iter/s", "cores": orc.max_threads(), "kind": "port",
+                               "sample": "one bundleAdjustRobust call of the same problem", "ms_per_call": 1e3 * dto}
+        out["parity_rel_rms_diff"] = abs(p2.rms() - po.rms()) / po.rms()
+    solver.close()
+    return out, prob
+
+
+def run_klt_leg(api, synth, torch, local, name, C, W, H, fw, fh, K, seed0, frames=4):
+    """KLT next() for C cameras of W x H with fw x fh slots: device-resident value + host-buffer e2e."""
+    cfg = klt_cfg()
+    seqs = [synth.ImageSequence(H, W, seed0 + c, n_frames=frames) for c in range(C)]
+    grp = api.KltGroup(cfg, C, W, H, KLT_L, fw, fh, device=local)
+    stream = torch.cuda.ExternalStream(grp.stream(), device=local)
+    host = [[torch.from_numpy(seqs[c].frames[k]).pin_memory() for c in range(C)] for k in range(frames)]
+    dev = [[h.cuda() for h in row] for row in host]
+    torch.cuda.synchronize()
+    grp.first([host[0][c].numpy() for c in range(C)])
+    fidx = seqs[0].frame_index
+    i = 1
+    for _ in range(3):
+        grp.next_dev([t.data_ptr() for t in dev[fidx(i)]], W)
+        i += 1
+    grp.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        grp.next_dev([t.data_ptr() for t in dev[fidx(i)]], W)
+        i += 1
+    e1.record(stream)
+    grp.sync()
+    ms = e0.elapsed_time(e1)
+    feats, _ = grp.fetch()
+    tracked = float(np.mean([(feats[c]["status"] == 0).mean() for c in range(C)]))
+    host_args = [grp.host_ptrs([h.numpy() for h in row]) for row in host]
+    for _ in range(3):
+        grp.next_raw(host_args[fidx(i)])
+        i += 1
+    t0 = time.perf_counter()
+    for _ in range(K):
+        grp.next_raw(host_args[fidx(i)])
+        i += 1
+    grp.sync()
+    ms_e2e = 1e3 * (time.perf_counter() - t0)
+    hbm_peak, src = peaks()
+    out = {"metric": "klt_features_per_s", "value": C * fw * fh * K / (ms * 1e-3), "unit": "features/s",
+           "ms_per_step": ms / K, "fps": K / (ms_e2e * 1e-3), "tracked_fraction": tracked,
+           "config": {"workload": f"{name}: {C} cams {W}x{H}, {fw * fh} slots/cam, KLT next()"},
+           "e2e": {"value": C * fw * fh * K / (ms_e2e * 1e-3), "unit": "features/s", "ms_per_step": ms_e2e / K,
+                   "h2d_bytes_per_step": C * W * H, "d2h_bytes_per_step": C * fw * fh * 20 + C * 32},
+           "roofline": {"bound": "hbm", "kernel": "whole frame", "achieved": grp.algorithmic_bytes() / (ms / K * 1e-3) / 1e9,
+                        "peak": hbm_peak, "unit": "GB/s", "peak_source": src,
+                        "frac": grp.algorithmic_bytes() / (ms / K * 1e-3) / 1e9 / hbm_peak}}
+    return out, grp, seqs, host_args
+
+
+def run_pipeline(api, synth, BaOptions, torch, local, grp, seqs, host_args, ba_prob, n_frames=60, kf_every=10):
+    """north_star target: >= 30 fps end to end on 4 synthetic 1280x720 streams at 2k features/cam
+    WITH per-key-frame local BA on one B200.  Per frame: cosl_klt_group_next (host frames in,
+    features out) + cosl_pose_intracam_batch (4 cameras x 192 points, host arrays); every
+    `kf_every`-th frame a key frame: the bundleAdjustRobust drop-in on the c3 local-BA problem (20
+    poses / 20 k points, host arrays), run synchronously (the reference runs it on a second thread)."""
+    cases = [synth.make_pose_case(192, KLT_W, KLT_H, seed=200 + c) for c in range(len(seqs))]
+    pa = ([c[0] for c in cases], [c[1] for c in cases], [c[2] for c in cases],
+          [c[3] for c in cases], [c[4] for c in cases], 10.0)
+    o2 = BaOptions.defaults()
+    o2.device = local
+    fidx = seqs[0].frame_index
+    i = 1
+    for _ in range(3):
+        grp.next_raw(host_args[fidx(i)])
+        api.pose_intracam_batch(*pa, device=local)
+        i += 1
+    api.ba_solve(ba_prob.copy(), o2)
+    t_klt = t_pose = t_ba = 0.0
+    nkf = 0
+    t0 = time.perf_counter()
+    for f in range(n_frames):
+        a = time.perf_counter()
+        grp.next_raw(host_args[fidx(i)])
+        grp.sync()
+        b = time.perf_counter()
+        api.pose_intracam_batch(*pa, device=local)
+        c = time.perf_counter()
+        if f % kf_every == kf_every - 1:
+            api.ba_solve(ba_prob.copy(), o2)
+            nkf += 1
+        d = time.perf_counter()
+        t_klt += b - a
+        t_pose += c - b
+        t_ba += d - c
+        i += 1
+    dt = time.perf_counter() - t0
+    return {"metric": "fps_pipeline", "value": n_frames / dt, "unit": "frames/s (4 cameras each)",
+            "target": 30.0, "meets_target": bool(n_frames / dt >= 30.0),
+            "config": {"workload": f"c3 pipeline: KLT next (4 x 1280x720, 2000 slots) + batched pose (4 x 192 pts) every "
+                                   f"frame, local BA (20 poses / 20 k points, 5 x 10 LM iterations) every {kf_every}th frame, "
+                                   "all through the C-ABI with host buffers, single thread"},
+            "frames": n_frames, "key_frames": nkf,
+            "ms_per_frame": {"klt": 1e3 * t_klt / n_frames, "pose": 1e3 * t_pose / n_frames,
+                             "local_ba_amortised": 1e3 * t_ba / n_frames,
+                             "local_ba_per_key_frame": 1e3 * t_ba / max(1, nkf)}}
 
 
 def emit(line):
@@ -591,6 +843,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--quick", action="store_true", help="headline KLT c3 + BA c4 only (skip c2 / c3 local BA / "
+                    "pipeline / c5 legs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -63,6 +63,7 @@ def _load():
     L.cosl_pose_intracam_batch.argtypes = [ci, vp, vp, vp, vp, vp, vp, vp, cd, vp, vp, vp, vp, ci]
     L.cosl_ba_options_default.argtypes = [C.POINTER(BaOptions)]
     L.cosl_ba_solve.argtypes = [C.POINTER(BaProblem), C.POINTER(BaOptions), vp]
+    L.cosl_ba_solve_multi.argtypes = [C.POINTER(BaProblem), C.POINTER(BaOptions), ci, vp, vp]
     L.cosl_sba_motstr_levmar_x.argtypes = [ci] * 4 + [vp, vp, ci, ci, vp, ci, vp, ci, ci, vp, vp, ci]
     L.cosl_nccl_unique_id.argtypes = [vp]
     L.cosl_ba_comm_create.argtypes = [vp, ci, ci, ci, C.POINTER(vp)]
@@ -323,6 +324,15 @@ def ba_solve(prob, opt):
     info = np.zeros(COSL_BA_INFOSZ)
     s = prob.struct()
     _ck(LIB.cosl_ba_solve(C.byref(s), C.byref(opt), _ptr(info)))
+    return info
+
+
+def ba_solve_multi(prob, opt, n_gpus, devices=None):
+    """cosl_ba_solve_multi: the same drop-in on n_gpus devices of this process."""
+    info = np.zeros(COSL_BA_INFOSZ)
+    s = prob.struct()
+    dev = None if devices is None else np.ascontiguousarray(devices, np.int32)
+    _ck(LIB.cosl_ba_solve_multi(C.byref(s), C.byref(opt), int(n_gpus), _ptr(dev), _ptr(info)))
     return info
 
 

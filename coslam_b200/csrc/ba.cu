@@ -214,7 +214,8 @@ int dev_alloc(cudaStream_t st, T** p, size_t count) {
 
 // worker threads for host-side index building: affinity and cgroup quota (shared between the
 // local ranks), at most 16; COSLAM_B200_THREADS overrides
-static int host_threads() {
+static thread_local int t_rank_share = 1;  // ranks driven by threads of this process (cosl_ba_solve_multi)
+static int host_threads_all() {
   static const int n = [] {
     int c = 1;
     cpu_set_t set;
@@ -241,6 +242,7 @@ static int host_threads() {
   }();
   return n;
 }
+static int host_threads() { return std::max(1, host_threads_all() / std::max(1, t_rank_share)); }
 
 static bool ba_timing() {
   static const bool on = std::getenv("COSL_BA_TIMING") != nullptr;
@@ -1228,6 +1230,95 @@ int cosl_ba_solve(cosl_ba_problem* prob, const cosl_ba_options* opt,
     std::fprintf(stderr, "[ba timing] cosl_ba_solve: create %.1f  run %.1f  download %.1f  destroy %.1f ms\n",
                  1e3 * (t1 - t0), 1e3 * (t2 - t1), 1e3 * (t3 - t2), 1e3 * (now_s() - t3));
   return rc;
+}
+
+// Single-process multi-GPU drop-in (the reference's BA pthread is ONE process,
+// app/SL_CoSLAM.cpp:1702-1729): one host thread per device, points sharded by sum(k^2 + 8k) like
+// the multi-process path, NCCL communicator created here.  Same results as cosl_ba_solve.
+int cosl_ba_solve_multi(cosl_ba_problem* prob, const cosl_ba_options* opt, int n_gpus,
+                        const int* devices, double info[COSL_BA_INFOSZ]) {
+  if (!prob || !opt) return set_error(COSL_E_INVALID, "null argument");
+  if (n_gpus <= 1) {
+    cosl_ba_options o = *opt;
+    if (devices) o.device = devices[0];
+    return cosl_ba_solve(prob, &o, info);
+  }
+  if (!nccl().ok) return set_error(COSL_E_NCCL, "libnccl.so.2 could not be loaded");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < n_gpus)
+    return set_error(COSL_E_CUDA, "%d GPUs requested, %d visible", n_gpus, ndev);
+  const int R = n_gpus, n = prob->n;
+  // contiguous point ranges balanced by sum(k^2 + 8 k)
+  std::vector<int> bound(R + 1, 0);
+  {
+    std::vector<double> w((size_t)n + 1, 0.0);
+    for (int i = 0; i < n; ++i) {
+      const double k = (double)(prob->ptr[i + 1] - prob->ptr[i]);
+      w[i + 1] = w[i] + k * k + 8.0 * k;
+    }
+    for (int r = 1; r < R; ++r)
+      bound[r] = (int)(std::lower_bound(w.begin() + 1, w.end(), w[n] * r / R) - (w.begin() + 1));
+    bound[R] = n;
+    for (int r = 1; r <= R; ++r) bound[r] = std::max(bound[r], bound[r - 1]);
+  }
+  ncclUniqueId uid;
+  if (nccl().GetUniqueId(&uid) != 0) return set_error(COSL_E_NCCL, "ncclGetUniqueId failed");
+  std::vector<int> rc(R, COSL_OK);
+  std::vector<std::string> err(R);
+  std::vector<std::vector<double>> infos(R, std::vector<double>(COSL_BA_INFOSZ, 0.0));
+  std::vector<std::vector<double>> Rr(R), tr(R);
+  auto worker = [&](int r) {
+    t_rank_share = R;
+    const int dev = devices ? devices[r] : r;
+    const int lo = bound[r], hi = bound[r + 1];
+    const int64_t o0 = prob->ptr[lo], o1 = prob->ptr[hi];
+    std::vector<int64_t> ptr((size_t)(hi - lo) + 1);
+    for (int i = lo; i <= hi; ++i) ptr[i - lo] = prob->ptr[i] - o0;
+    // cameras are replicated: every rank works on its own copy of R, t
+    Rr[r].assign(prob->R, prob->R + 9 * (size_t)prob->m);
+    tr[r].assign(prob->t, prob->t + 3 * (size_t)prob->m);
+    cosl_ba_problem sp = *prob;
+    sp.n = hi - lo;
+    sp.nobs = o1 - o0;
+    sp.n_con = std::max(0, std::min(prob->n_con - lo, hi - lo));
+    sp.R = Rr[r].data();
+    sp.t = tr[r].data();
+    sp.X = prob->X + 3 * (size_t)lo;
+    sp.ptr = ptr.data();
+    sp.cam = prob->cam + o0;
+    sp.xy = prob->xy + 2 * o0;
+    sp.outlier = prob->outlier ? prob->outlier + o0 : nullptr;
+    cosl_ba_options o = *opt;
+    o.device = dev;
+    cosl_ba_comm* comm = nullptr;
+    cosl_ba_solver* sv = nullptr;
+    int c = cosl_ba_comm_create((const uint8_t*)uid.internal, r, R, dev, &comm);
+    if (c == COSL_OK) c = cosl_ba_solver_create(&sp, &o, comm, &sv);
+    if (c == COSL_OK) c = cosl_ba_solver_run(sv, infos[r].data());
+    if (c == COSL_OK) c = cosl_ba_solver_download(sv, &sp);
+    if (c != COSL_OK) err[r] = last_error_ref();
+    if (sv) cosl_ba_solver_destroy(sv);
+    if (comm) cosl_ba_comm_destroy(comm);
+    rc[r] = c;
+  };
+  std::vector<std::thread> th;
+  for (int r = 1; r < R; ++r) th.emplace_back(worker, r);
+  worker(0);
+  for (auto& x : th) x.join();
+  t_rank_share = 1;
+  for (int r = 0; r < R; ++r)
+    if (rc[r] != COSL_OK) return set_error(rc[r], "rank %d: %s", r, err[r].c_str());
+  std::memcpy(prob->R, Rr[0].data(), sizeof(double) * 9 * (size_t)prob->m);
+  std::memcpy(prob->t, tr[0].data(), sizeof(double) * 3 * (size_t)prob->m);
+  if (info) {
+    for (int k = 0; k < COSL_BA_INFOSZ; ++k) info[k] = infos[0][k];
+    if (prob->outlier) {
+      long long c = 0;
+      for (long long o = 0; o < prob->nobs; ++o) c += prob->outlier[o] ? 1 : 0;
+      info[13] = (double)c;
+    }
+  }
+  return COSL_OK;
 }
 
 int cosl_sba_motstr_levmar_x(int n, int ncon, int m, int mcon, const char* vmask, double* p,

@@ -20,7 +20,7 @@
 template<class MatT, class Pt3T, class MeasT>
 void bundleAdjustRobust(int nCamsCon, std::vector<MatT>& Ks, std::vector<MatT>& Rs, std::vector<MatT>& Ts,
 		int nPtsCon, std::vector<Pt3T>& pts, std::vector<std::vector<MeasT> >& meas, double maxErr, int maxIter,
-		int nInnerMaxIter, int device = 0) {
+		int nInnerMaxIter, int device = 0, int nGpus = 1) {
 	const int m = (int) Ks.size(), n = (int) pts.size();
 	std::vector<double> K(9 * (size_t) m), R(9 * (size_t) m), t(3 * (size_t) m), X(3 * (size_t) n);
 	for (int j = 0; j < m; ++j) {
@@ -70,7 +70,8 @@ void bundleAdjustRobust(int nCamsCon, std::vector<MatT>& Ks, std::vector<MatT>& 
 	o.inner_iters = nInnerMaxIter;
 	o.device = device;
 	double info[COSL_BA_INFOSZ];
-	const int rc = cosl_ba_solve(&p, &o, info);
+	// nGpus > 1: devices 0 .. nGpus-1 of this process, map points sharded over them (global BA)
+	const int rc = (nGpus > 1) ? cosl_ba_solve_multi(&p, &o, nGpus, 0, info) : cosl_ba_solve(&p, &o, info);
 	if (rc != COSL_OK)
 		throw std::runtime_error(std::string("bundleAdjustRobust: ") + cosl_last_error());
 	for (int j = 0; j < m; ++j) {

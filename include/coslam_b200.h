@@ -229,6 +229,12 @@ void cosl_ba_options_default(cosl_ba_options* o);
 
 /* Single-GPU solve, HOST arrays in/out (the drop-in for bundleAdjustRobust). */
 int cosl_ba_solve(cosl_ba_problem* prob, const cosl_ba_options* opt, double info[COSL_BA_INFOSZ]);
+/* The same call on n_gpus devices of THIS process (devices = CUDA ordinals, NULL = 0..n_gpus-1):
+ * one host thread per device, map points sharded over them, one NCCL all-reduce of the reduced
+ * camera system per LM trial.  n_gpus <= 1 is cosl_ba_solve.  opt->device is
+ * ignored when devices is given. */
+int cosl_ba_solve_multi(cosl_ba_problem* prob, const cosl_ba_options* opt, int n_gpus,
+                        const int* devices, double info[COSL_BA_INFOSZ]);
 
 /* sba_motstr_levmar_x specialised to the KRTS projection (app/SL_CoSLAMBA.cpp:360-363).  Same
  * argument meaning as sba-1.6: n points, ncon fixed, m cameras, mcon fixed, vmask[n*m],

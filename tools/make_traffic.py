@@ -1,6 +1,6 @@
 """profiles/traffic.json: DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of
 the kernels captured with `ncu --set full`, parsed from profiles/<prefix>_<kernel>.summary.txt.
-bench.py reads it to fill roofline.traffic.  usage: python tools/make_traffic.py r1"""
+bench.py reads it to fill roofline.traffic.  usage: python tools/make_traffic.py r1 r2d"""
 import glob
 import json
 import os
@@ -9,9 +9,9 @@ import sys
 
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles")
-prefix = sys.argv[1] if len(sys.argv) > 1 else "r1"
+prefixes = sys.argv[1:] if len(sys.argv) > 1 else ["r1"]  # later prefixes override earlier ones
 out = {}
-for path in sorted(glob.glob(os.path.join(root, f"{prefix}_*.summary.txt"))):
+for prefix, path in [(p, f) for p in prefixes for f in sorted(glob.glob(os.path.join(root, f"{p}_*.summary.txt")))]:
     name = os.path.basename(path)[len(prefix) + 1:-len(".summary.txt")]
     tot = 0.0
     for line in open(path):
