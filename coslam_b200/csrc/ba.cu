@@ -632,8 +632,11 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   td.trace = nullptr;
   // small systems (local BA) are factored inside one CTA (ns*ns doubles of shared memory)
   const size_t smallBytes = sizeof(double) * (size_t)s->ns * s->ns;
-  s->smallSolve = (smallBytes <= 200 * 1024) && s->ns <= 1024;
-  if (std::getenv("COSL_BA_NO_SMALL")) s->smallSolve = false;
+  // Measured (profiles/r2f_bench.json): the one-CTA dense kernel needs 100 us for the 72 x 72
+  // system of the c3 local BA (72 pivots x 3 CTA barriers); the task kernel does the same two
+  // blocks in about half of that, so it is the default everywhere.  COSL_BA_SMALL_KERNEL=1 selects
+  // the dense kernel.
+  s->smallSolve = (smallBytes <= 200 * 1024) && s->ns <= 1024 && std::getenv("COSL_BA_SMALL_KERNEL") != nullptr;
   // (the kernel also has ~8 KB of static shared memory, so opt in well below the 48 KB default)
   if (s->smallSolve && smallBytes > 32 * 1024)
     COSL_CUDA(cudaFuncSetAttribute(ba_tile_small, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -13,6 +13,7 @@
 #include "klt_kernels.cuh"
 #include "klt_track.cuh"
 #include "klt_front.cuh"
+#include "klt_pyr_tma.cuh"
 
 using namespace coslam;
 
@@ -74,6 +75,10 @@ struct cosl_klt {
   bool foldAdvance = false, advanceDone = false;
   int detXlo = 0, detXhi = -1, detYlo = 0, detYhi = -1;  // detector window in pixels
   int verBase = 0;
+  // TMA descriptors of every pyramid level of both buffers: [buffer][level], load box (source of
+  // level + 1) and store box (destination of level - 1 -> level); klt_pyr_tma.cuh
+  CUtensorMap tmLoad[2][8], tmStore[2][8];
+  bool tmaOK = false;
   SectionTimer timer;
   int secPyr = 0, secTrack = 0, secDetect = 0, secSelect = 0;
 };
@@ -199,6 +204,35 @@ int alloc_group(cosl_klt* g) {
     COSL_CUDA(cudaMalloc(&g->d_ver, sizeof(unsigned long long) * 2 * (size_t)T));
     COSL_CUDA(cudaMemset(g->d_ver, 0, sizeof(unsigned long long) * 2 * (size_t)T));
     g->verBase = 0;
+  }
+  // tensor maps for the TMA pyramid kernel (driver entry point through the runtime: no -lcuda)
+  g->tmaOK = false;
+  if (!std::getenv("COSL_KLT_NO_TMA") && g->L > 2) {
+    typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) == cudaSuccess && fn &&
+        qr == cudaDriverEntryPointSuccess) {
+      bool ok = true;
+      for (int b = 0; b < 2 && ok; ++b)
+        for (int l = 1; l < g->L && ok; ++l) {
+          // a level of the whole camera group: x = texels as pairs of 8-byte elements, y, camera
+          const cuuint64_t dims[3] = {2ull * g->lvW[l], (cuuint64_t)g->lvH[l], (cuuint64_t)C};
+          const cuuint64_t strides[2] = {16ull * g->lvW[l], 16ull * (cuuint64_t)g->pyrStride};
+          const cuuint32_t es[3] = {1, 1, 1};
+          const cuuint32_t boxL[3] = {2 * PT_SW, PT_SH, 1}, boxS[3] = {2 * PT_TW, PT_TH, 1};
+          void* base = (void*)(g->d_pyr[b] + g->lvOff[l]);
+          ok = ok && ((EncodeFn)fn)(&g->tmLoad[b][l], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, boxL,
+                                    es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+          ok = ok && ((EncodeFn)fn)(&g->tmStore[b][l], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, boxS,
+                                    es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+        }
+      g->tmaOK = ok;
+    }
   }
   // dynamic shared memory opt-ins
   COSL_CUDA(cudaFuncSetAttribute(klt_select_refill, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -344,8 +378,12 @@ int build_pyramid(cosl_klt* g, bool wantCorn) {
   g->cornValid = wantCorn;
   for (int l = 2; l < g->L; ++l) {
     dim3 gl(div_up(g->lvW[l], PD_TW), div_up(g->lvH[l], PD_TH), g->C);
-    COSL_LAUNCH(klt_pyr_down, gl, 256, 0, g->stream, P + g->lvOff[l - 1], P + g->lvOff[l],
-                g->pyrStride, g->lvW[l - 1], g->lvH[l - 1], g->lvW[l], g->lvH[l]);
+    if (g->tmaOK)  // source tile by TMA load, destination tile by TMA store (klt_pyr_tma.cuh)
+      COSL_LAUNCH(klt_pyr_down_tma, gl, 256, 0, g->stream, g->tmLoad[g->cur][l - 1], g->tmStore[g->cur][l],
+                  g->lvW[l - 1], g->lvH[l - 1]);
+    else
+      COSL_LAUNCH(klt_pyr_down, gl, 256, 0, g->stream, P + g->lvOff[l - 1], P + g->lvOff[l],
+                  g->pyrStride, g->lvW[l - 1], g->lvH[l - 1], g->lvW[l], g->lvH[l]);
   }
   g->timer.end(g->stream);
   COSL_CUDA(cudaGetLastError());
