@@ -520,7 +520,7 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   COSL_TRY(dev_alloc(s->stream, &s->d_Linv, (size_t)nb * BA_TILE));
   COSL_TRY(dev_alloc(s->stream, &s->d_y, rhsLen));
   COSL_TRY(dev_alloc(s->stream, &s->d_x, rhsLen));
-  COSL_TRY(dev_alloc(s->stream, &s->d_cnt, (size_t)P.nCounters + 2));
+  COSL_TRY(dev_alloc(s->stream, &s->d_cnt, (size_t)P.nCounters + 2 + P.tasks.size()));
   COSL_TRY(dev_alloc(s->stream, &s->d_tasks, P.tasks.size()));
   COSL_TRY(dev_alloc(s->stream, &s->d_bwd, P.bwdList.size()));
   COSL_TRY(dev_alloc(s->stream, &s->d_blkRows, (size_t)nb));
@@ -568,6 +568,29 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   const int nA = (int)s->taskOrder.size();
   for (const BaTask& t : P.tasks)
     if (!(t.type == BA_T_POTRF || t.type == BA_T_BWD)) s->taskOrder.push_back(t);
+  {
+    // hot successors of every POTRF(k): TRSM(j, k) and the diagonal UPD(j, j, k) of j = first block
+    // of struct(k) -- the next pivot of the dependency chain (ba_tile.cuh)
+    const bool hotOn = std::getenv("COSL_BA_NO_HOT") == nullptr;
+    std::vector<int> firstTrsm(P.nb, -1), firstRow(P.nb, 1 << 30);
+    for (int t = 0; t < (int)s->taskOrder.size(); ++t) {
+      const BaTask& k = s->taskOrder[t];
+      if (k.type == BA_T_TRSM && k.i < firstRow[k.k]) {
+        firstRow[k.k] = k.i;
+        firstTrsm[k.k] = t;
+      }
+    }
+    std::vector<int> diagUpd(P.nb, -1);
+    for (int t = 0; t < (int)s->taskOrder.size(); ++t) {
+      const BaTask& k = s->taskOrder[t];
+      if (k.type == BA_T_UPD && (k.flags & 1) && firstTrsm[k.k] >= 0 && k.i == firstRow[k.k]) diagUpd[k.k] = t;
+    }
+    for (BaTask& k : s->taskOrder)
+      if (k.type == BA_T_POTRF) {
+        k.l0 = hotOn ? firstTrsm[k.k] : -1;
+        k.l1 = hotOn ? diagUpd[k.k] : -1;
+      }
+  }
   if (!s->taskOrder.empty()) UP(s->d_tasks, s->taskOrder.data(), sizeof(BaTask) * s->taskOrder.size());
   if (!P.bwdList.empty()) UP(s->d_bwd, P.bwdList.data(), sizeof(BaBwdEntry) * P.bwdList.size());
   if (!P.sumList.empty()) UP(s->d_sum, P.sumList.data(), sizeof(BaSumEntry) * P.sumList.size());
@@ -759,7 +782,7 @@ int dense_solve(cosl_ba_solver* s) {
     COSL_LAUNCH(ba_tile_small, 1, 256, sizeof(double) * (size_t)ns * ns, s->stream, s->td,
                 s->d_tileIdx, s->d_blkRow0, ns);
   } else {
-    COSL_CUDA(cudaMemsetAsync(s->d_cnt, 0, sizeof(int) * ((size_t)s->td.nCounters + 2), s->stream));
+    COSL_CUDA(cudaMemsetAsync(s->d_cnt, 0, sizeof(int) * ((size_t)s->td.nCounters + 2 + s->td.nTasks), s->stream));
     COSL_LAUNCH(ba_tile_solve, s->solveGrid, BA_NTHREADS, BA_TILE_SMEM, s->stream, s->td);
   }
   s->timer.end(s->stream);
@@ -785,8 +808,16 @@ int solve_trial(cosl_ba_solver* s, double mu, bool* solved) {
         COSL_LAUNCH(ba_schur_rows, s->mf * s->rowSplits, 32 * BA_ROWS_WARPS, s->rowsSmem, s->stream, s->d,
                     s->d_cptrFree, s->d_visit, s->d_rowDst, s->nSlots, s->d_Vinv, s->d_solIdx, s->rowSplits);
     } else if (s->nItems) {
-      COSL_LAUNCH(ba_schur_pairs, div_up(s->nItems, 4), 128, 0, s->stream, s->d, s->d_items,
-                  s->nItems, s->d_entries, mu);
+      static const int minb = std::getenv("COSL_BA_SCHUR_MINB") ? std::atoi(std::getenv("COSL_BA_SCHUR_MINB")) : 4;
+      if (minb >= 8)
+        COSL_LAUNCH(ba_schur_pairs_t<8>, div_up(s->nItems, 4), 128, 0, s->stream, s->d, s->d_items,
+                    s->nItems, s->d_entries, mu);
+      else if (minb >= 6)
+        COSL_LAUNCH(ba_schur_pairs_t<6>, div_up(s->nItems, 4), 128, 0, s->stream, s->d, s->d_items,
+                    s->nItems, s->d_entries, mu);
+      else
+        COSL_LAUNCH(ba_schur_pairs_t<4>, div_up(s->nItems, 4), 128, 0, s->stream, s->d, s->d_items,
+                    s->nItems, s->d_entries, mu);
     }
   }
   s->timer.end(s->stream);

@@ -410,9 +410,12 @@ __device__ __forceinline__ void inv3sym_mu(const double* __restrict__ V, double 
   I[5] = (a * d - b * b) * r;
 }
 
-__global__ void __launch_bounds__(128)
-ba_schur_pairs(BaDev d, const BaPairItem* __restrict__ items, int nItems,
-               const int2* __restrict__ entries, double mu) {
+// MINB = CTAs per SM the register allocation must allow: the kernel is bound by gather latency, so
+// more resident warps can beat fewer, register-richer ones (measured both ways, see profiles/)
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB)
+ba_schur_pairs_t(BaDev d, const BaPairItem* __restrict__ items, int nItems,
+                 const int2* __restrict__ entries, double mu) {
   const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (item >= nItems) return;
   const int lane = threadIdx.x & 31;

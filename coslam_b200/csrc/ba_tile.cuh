@@ -30,7 +30,7 @@ struct BaTileDev {
   double* Linv;   // [nb][4096]
   double* y;      // [nb*64]
   double* x;      // [nb*64]
-  int* cnt;       // [nCounters + 2]; the last two are the task tickets of the two CTA roles
+  int* cnt;       // [nCounters + 2 + nTasks]: counters, the two task tickets of the CTA roles, claim flags
   const BaTask* tasks;
   const BaBwdEntry* bwd;
   const BaSumEntry* sum;
@@ -585,6 +585,53 @@ __device__ __forceinline__ void tile_bwd2(const double* __restrict__ sL, const d
   }
 }
 
+// UPDATE task body: C -= A B^T (first update of a scratch tile overwrites), diagonal tiles also
+// b_i -= A y_k.  staged: the operands (and y in sY) are already in shared memory.
+__device__ __forceinline__ void ba_upd_body(const BaTileDev& d, const BaTask& t, int ti, double* sA, double* sB,
+                                            double* sY, int bk, int tid, bool staged) {
+  double* gC = d.tiles + (size_t)t.tC * BA_TILE;
+  const bool over = (t.flags & 2) != 0;
+  double cold[2][4][2];
+  if (!over) {  // C prefetch (independent of the operand staging: one round trip for everything)
+#pragma unroll
+    for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+      for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          int r, c;
+          tile_acc_rc(tid, mi, ni, e, r, c);
+          cold[mi][ni][e] = __ldcg(gC + c * BA_TB + r);
+        }
+  }
+  if (!staged) {
+    tile_load2<BA_LDS>(d.tiles + (size_t)t.tA * BA_TILE, sA, d.tiles + (size_t)t.tB * BA_TILE, sB, tid);
+    if ((t.flags & 1) && tid < 64) sY[tid] = __ldcg(d.y + (size_t)t.k * BA_TB + tid);
+    __syncthreads();
+  }
+  if (d.trace && tid == 0) d.trace[8 * (size_t)ti + 4] = ba_globaltimer();
+  TileAcc acc;
+  tile_gemm_dmma(sA, sB, (bk + 3) & ~3, tid, acc);
+  if (d.trace && tid == 0) d.trace[8 * (size_t)ti + 5] = ba_globaltimer();
+#pragma unroll
+  for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+    for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        int r, c;
+        tile_acc_rc(tid, mi, ni, e, r, c);
+        gC[c * BA_TB + r] = (over ? 0.0 : cold[mi][ni][e]) - acc.c[mi][ni][e];
+      }
+  if ((t.flags & 1) && tid < 64) {
+    // b_i -= L_ik y_k (sequenced with the updates of the diagonal tile)
+    double sum = 0;
+    for (int p = 0; p < bk; ++p) sum = __fma_rn(sA[p * BA_LDS + tid], sY[p], sum);
+    double* b = (t.l0 >= 0) ? d.rhsS + (size_t)t.l0 * BA_TB + tid : d.rhs + (size_t)t.i * BA_TB + tid;
+    *b = (over ? 0.0 : __ldcg(b)) - sum;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // The persistent dataflow kernel.
 // ---------------------------------------------------------------------------------------------
@@ -598,8 +645,9 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
   double* sV = sM + 8 * BA_TB;             // [64]
   double* sY = sV + BA_TB;                 // [64]
   double* sD = sY + BA_TB;                 // [80] panel scratch of tile_potrf2
-  __shared__ int s_task, s_fail;
+  __shared__ int s_task, s_fail, s_flag;
   const int tid = threadIdx.x;
+  int* const claim = d.cnt + d.nCounters + 2;  // [nTasks]: 1 = somebody executes / executed the task
   const bool special = (int)blockIdx.x < d.nSpecial;
   int* const ticket = d.cnt + d.nCounters + (special ? 0 : 1);
   const int tBase = special ? 0 : d.nA, tCount = special ? d.nA : d.nTasks - d.nA;
@@ -638,6 +686,12 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
     }
     __syncthreads();
     const int bk = d.blkRows[t.k];
+    if (t.type == BA_T_TRSM || t.type == BA_T_UPD) {
+      // the CTA that factored the pivot block may already have run this task (hot successors)
+      if (tid == 0) s_flag = (atomicCAS(claim + ti, 0, 1) == 0) ? 1 : 0;
+      __syncthreads();
+      if (!s_flag) continue;
+    }
     if (t.type == BA_T_POTRF) {
       // stage the lower part (ld BA_LDS), identity on the padding; b into sV
       {
@@ -672,6 +726,73 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
         if (tid < 64) d.y[(size_t)t.k * BA_TB + tid] = sY[tid];
         if (tid == 0 && s_fail) d.sc[d.scFail] = 1.0;
       }
+      // ---- hot successors: the next pivot of the chain needs TRSM(j, k) and UPD(j, j, k) with
+      // j = first block of struct(k).  If their other operands are ready, this CTA runs them now
+      // with L_kk, the M_b and y_k still in shared memory: two hand-overs, two tile loads and
+      // two publish/acquire round trips less per step of the critical path.  Claimed BEFORE the
+      // factor is published so that no waiting CTA wins the race; conditions are monotone.
+      if (tid == 0) {
+        int hot = 0;
+        if (t.l0 >= 0) {
+          const BaTask ht = d.tasks[t.l0];
+          if (ld_acquire(d.cnt + ht.w0i) >= ht.w0v && atomicCAS(claim + t.l0, 0, 1) == 0) hot = 1;
+        }
+        if (hot && t.l1 >= 0) {
+          const BaTask hu = d.tasks[t.l1];
+          if (ld_acquire(d.cnt + hu.w0i) >= hu.w0v && atomicCAS(claim + t.l1, 0, 1) == 0) hot = 3;
+        }
+        s_flag = hot;
+      }
+      __threadfence();
+      __syncthreads();
+      const int hot = s_flag;
+      if (tid == 0) {
+        red_release_add(d.cnt + t.done, 1);
+        if (d.trace) d.trace[8 * (size_t)ti + 3] = ba_globaltimer();
+      }
+      if (hot & 1) {
+        const BaTask ht = d.tasks[t.l0];
+        double* gX = d.tiles + (size_t)ht.tC * BA_TILE;
+        if (d.trace && tid == 0) {
+          unsigned int smid;
+          asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+          d.trace[8 * (size_t)t.l0] = smid;
+          d.trace[8 * (size_t)t.l0 + 1] = d.trace[8 * (size_t)t.l0 + 2] = ba_globaltimer();
+        }
+        tile_load<BA_LDS>(gX, sB, tid);
+        __syncthreads();
+        tile_trsm2(sB, sA, sM, (bk + 7) >> 3, tid);  // L_kk is still staged in sA
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = 2 * (tid + BA_NTHREADS * u);
+          reinterpret_cast<double2*>(gX)[tid + BA_NTHREADS * u] =
+              *reinterpret_cast<const double2*>(sB + (e >> 6) * BA_LDS + (e & 63));
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+          red_release_add(d.cnt + ht.done, 1);
+          if (d.trace) d.trace[8 * (size_t)t.l0 + 3] = ba_globaltimer();
+        }
+        if (hot & 2) {
+          const BaTask hu = d.tasks[t.l1];
+          if (d.trace && tid == 0) {
+            unsigned int smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            d.trace[8 * (size_t)t.l1] = smid;
+            d.trace[8 * (size_t)t.l1 + 1] = d.trace[8 * (size_t)t.l1 + 2] = ba_globaltimer();
+          }
+          ba_upd_body(d, hu, t.l1, sB, sB, sY, bk, tid, true);  // X = L_jk staged in sB, y_k in sY
+          __threadfence();
+          __syncthreads();
+          if (tid == 0) {
+            red_release_add(d.cnt + hu.done, 1);
+            if (d.trace) d.trace[8 * (size_t)t.l1 + 3] = ba_globaltimer();
+          }
+        }
+      }
+      continue;
     } else if (t.type == BA_T_TRSM) {
       // L_ik = A_ik L_kk^-T by blocked substitution (tile_trsm2); every warp owns 8 rows
       double* gC = d.tiles + (size_t)t.tC * BA_TILE;
@@ -691,49 +812,7 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
             *reinterpret_cast<const double2*>(sA + (e >> 6) * BA_LDS + (e & 63));
       }
     } else if (t.type == BA_T_UPD) {
-      const bool upd = true;
-      double* gC = d.tiles + (size_t)t.tC * BA_TILE;
-      const double* gA = d.tiles + (size_t)t.tA * BA_TILE;
-      const double* gB = d.tiles + (size_t)t.tB * BA_TILE;
-      // C prefetch (independent of the operand staging: one round trip for everything)
-      const bool over = upd && (t.flags & 2);
-      double cold[2][4][2];
-      if (upd && !over) {
-#pragma unroll
-        for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-          for (int ni = 0; ni < 4; ++ni)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              int r, c;
-              tile_acc_rc(tid, mi, ni, e, r, c);
-              cold[mi][ni][e] = __ldcg(gC + c * BA_TB + r);
-            }
-      }
-      tile_load2<BA_LDS>(gA, sA, gB, sB, tid);
-      if (upd && (t.flags & 1) && tid < 64) sY[tid] = __ldcg(d.y + (size_t)t.k * BA_TB + tid);
-      __syncthreads();
-      if (d.trace && tid == 0) d.trace[8 * (size_t)ti + 4] = ba_globaltimer();
-      TileAcc acc;
-      tile_gemm_dmma(sA, sB, (bk + 3) & ~3, tid, acc);
-      if (d.trace && tid == 0) d.trace[8 * (size_t)ti + 5] = ba_globaltimer();
-#pragma unroll
-      for (int mi = 0; mi < 2; ++mi)
-#pragma unroll
-        for (int ni = 0; ni < 4; ++ni)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            int r, c;
-            tile_acc_rc(tid, mi, ni, e, r, c);
-            gC[c * BA_TB + r] = upd ? ((over ? 0.0 : cold[mi][ni][e]) - acc.c[mi][ni][e]) : acc.c[mi][ni][e];
-          }
-      if (upd && (t.flags & 1) && tid < 64) {
-        // b_i -= L_ik y_k (sequenced with the updates of the diagonal tile)
-        double s = 0;
-        for (int p = 0; p < bk; ++p) s = __fma_rn(sA[p * BA_LDS + tid], sY[p], s);
-        double* b = (t.l0 >= 0) ? d.rhsS + (size_t)t.l0 * BA_TB + tid : d.rhs + (size_t)t.i * BA_TB + tid;
-        *b = (over ? 0.0 : __ldcg(b)) - s;
-      }
+      ba_upd_body(d, t, ti, sA, sB, sY, bk, tid, false);
     } else if (t.type == BA_T_SUM) {
       // C += sum of the scratch tiles (fixed order); diagonal tiles also collect their rhs parts
       double2* gC = reinterpret_cast<double2*>(d.tiles + (size_t)t.tC * BA_TILE);
