@@ -119,7 +119,7 @@ struct cosl_ba_solver {
   size_t rowsSmem = 0;
   bool useRows = false;
   int rowSplits = 1;
-  int2* d_entries = nullptr;
+  int4* d_entries = nullptr;
   int nItems = 0;
   long long nEntries = 0;
   double* h_sc = nullptr;  // pinned
@@ -408,7 +408,7 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   std::vector<int> cptrFree(mf + 1, 0);
   std::vector<int4> visit;
   std::vector<BaPairItem> items;
-  std::vector<int2> entries;
+  std::vector<int4> entries;
   long long nEntries = 0;
   if (s->useRows) {
     rowDst.assign((size_t)mf * s->nSlots, BaRowDst{-1, 0, 0, 0});
@@ -453,7 +453,7 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
     std::vector<long long> fill(pcount.begin(), pcount.end() - 1);
     run_threads(T, [&](int t) {
       for_pairs(t, [&](size_t bucket, long long a, long long b) {
-        entries[fill[bucket]++] = make_int2((int)a, (int)b);
+        entries[fill[bucket]++] = make_int4((int)a, (int)b, pt[a], 0);
       });
     });
     const int chunk = 512;
@@ -560,7 +560,7 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   if (!rowDst.empty()) UP(s->d_rowDst, rowDst.data(), sizeof(BaRowDst) * rowDst.size());
   if (!visit.empty()) UP(s->d_visit, visit.data(), sizeof(int4) * visit.size());
   UP(s->d_cptrFree, cptrFree.data(), sizeof(int) * cptrFree.size());
-  if (nEntries) UP(s->d_entries, entries.data(), sizeof(int2) * (size_t)nEntries);
+  if (nEntries) UP(s->d_entries, entries.data(), sizeof(int4) * (size_t)nEntries);
   // two ticket lists (each keeps the critical-path-first order, hence stays topological)
   s->taskOrder.clear();
   for (const BaTask& t : P.tasks)
@@ -808,16 +808,9 @@ int solve_trial(cosl_ba_solver* s, double mu, bool* solved) {
         COSL_LAUNCH(ba_schur_rows, s->mf * s->rowSplits, 32 * BA_ROWS_WARPS, s->rowsSmem, s->stream, s->d,
                     s->d_cptrFree, s->d_visit, s->d_rowDst, s->nSlots, s->d_Vinv, s->d_solIdx, s->rowSplits);
     } else if (s->nItems) {
-      static const int minb = std::getenv("COSL_BA_SCHUR_MINB") ? std::atoi(std::getenv("COSL_BA_SCHUR_MINB")) : 4;
-      if (minb >= 8)
-        COSL_LAUNCH(ba_schur_pairs_t<8>, div_up(s->nItems, 4), 128, 0, s->stream, s->d, s->d_items,
-                    s->nItems, s->d_entries, mu);
-      else if (minb >= 6)
-        COSL_LAUNCH(ba_schur_pairs_t<6>, div_up(s->nItems, 4), 128, 0, s->stream, s->d, s->d_items,
-                    s->nItems, s->d_entries, mu);
-      else
-        COSL_LAUNCH(ba_schur_pairs_t<4>, div_up(s->nItems, 4), 128, 0, s->stream, s->d, s->d_items,
-                    s->nItems, s->d_entries, mu);
+      if (s->n) COSL_LAUNCH(ba_vinv_kernel, (unsigned)div_up64(s->n, 256), 256, 0, s->stream, s->d, mu, s->d_Vinv);
+      COSL_LAUNCH(ba_schur_pairs_t<4>, div_up(s->nItems, 4), 128, 0, s->stream, s->d, s->d_items,
+                  s->nItems, s->d_entries, s->d_Vinv);
     }
   }
   s->timer.end(s->stream);

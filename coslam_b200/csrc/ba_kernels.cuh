@@ -410,12 +410,13 @@ __device__ __forceinline__ void inv3sym_mu(const double* __restrict__ V, double 
   I[5] = (a * d - b * b) * r;
 }
 
-// MINB = CTAs per SM the register allocation must allow: the kernel is bound by gather latency, so
-// more resident warps can beat fewer, register-richer ones (measured both ways, see profiles/)
+// Entries carry the point index ({obsA, obsB, point, -}) and the damped inverses V*^-1 are computed
+// once per trial (ba_vinv_kernel), so the loads of an entry are ONE dependent level below the entry
+// itself; the next entry is fetched while the current one is processed.
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB)
 ba_schur_pairs_t(BaDev d, const BaPairItem* __restrict__ items, int nItems,
-                 const int2* __restrict__ entries, double mu) {
+                 const int4* __restrict__ entries, const double* __restrict__ Vinv) {
   const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (item >= nItems) return;
   const int lane = threadIdx.x & 31;
@@ -426,13 +427,18 @@ ba_schur_pairs_t(BaDev d, const BaPairItem* __restrict__ items, int nItems,
   for (int k = 0; k < 18; ++k) acc[k] = 0;
   double racc[3] = {0, 0, 0};
   const bool diag = (it.rowCam == it.colCam);
-  for (int e = it.begin + (lane >> 1); e < it.end; e += 16) {
-    const int2 ob = entries[e];
+  int e = it.begin + (lane >> 1);
+  int4 nxt = (e < it.end) ? __ldg(&entries[e]) : make_int4(0, 0, 0, 0);
+  for (; e < it.end; e += 16) {
+    const int4 ob = nxt;
+    if (e + 16 < it.end) nxt = __ldg(&entries[e + 16]);
     const double* Wa = d.W + 18 * (size_t)ob.x;
     const double* Wb = d.W + 18 * (size_t)ob.y;
-    const int i = d.pt[ob.x];
+    const int i = ob.z;
+    const double* Vi = Vinv + 6 * (size_t)i;
     double Iv[6];
-    inv3sym_mu(d.V + 6 * (size_t)i, mu, Iv);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) Iv[k] = Vi[k];
     double wa[18];
 #pragma unroll
     for (int k = 0; k < 18; ++k) wa[k] = Wa[k];

@@ -646,6 +646,7 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
   double* sY = sV + BA_TB;                 // [64]
   double* sD = sY + BA_TB;                 // [80] panel scratch of tile_potrf2
   __shared__ int s_task, s_fail, s_flag;
+  __shared__ BaTask s_ht, s_hu;  // hot successors of the POTRF in flight
   const int tid = threadIdx.x;
   int* const claim = d.cnt + d.nCounters + 2;  // [nTasks]: 1 = somebody executes / executed the task
   const bool special = (int)blockIdx.x < d.nSpecial;
@@ -693,6 +694,8 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
       if (!s_flag) continue;
     }
     if (t.type == BA_T_POTRF) {
+      if (tid == 255 && t.l0 >= 0) s_ht = d.tasks[t.l0];
+      if (tid == 254 && t.l1 >= 0) s_hu = d.tasks[t.l1];
       // stage the lower part (ld BA_LDS), identity on the padding; b into sV
       {
         const double* g = d.tiles + (size_t)t.tC * BA_TILE;
@@ -733,14 +736,11 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
       // factor is published so that no waiting CTA wins the race; conditions are monotone.
       if (tid == 0) {
         int hot = 0;
-        if (t.l0 >= 0) {
-          const BaTask ht = d.tasks[t.l0];
-          if (ld_acquire(d.cnt + ht.w0i) >= ht.w0v && atomicCAS(claim + t.l0, 0, 1) == 0) hot = 1;
-        }
-        if (hot && t.l1 >= 0) {
-          const BaTask hu = d.tasks[t.l1];
-          if (ld_acquire(d.cnt + hu.w0i) >= hu.w0v && atomicCAS(claim + t.l1, 0, 1) == 0) hot = 3;
-        }
+        // (descriptors were fetched into shared memory while the factorisation ran)
+        const bool rT = t.l0 >= 0 && ld_acquire(d.cnt + s_ht.w0i) >= s_ht.w0v;
+        const bool rU = t.l1 >= 0 && ld_acquire(d.cnt + s_hu.w0i) >= s_hu.w0v;
+        if (rT && atomicCAS(claim + t.l0, 0, 1) == 0) hot = 1;
+        if (hot && rU && atomicCAS(claim + t.l1, 0, 1) == 0) hot = 3;
         s_flag = hot;
       }
       __threadfence();
@@ -751,7 +751,7 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
         if (d.trace) d.trace[8 * (size_t)ti + 3] = ba_globaltimer();
       }
       if (hot & 1) {
-        const BaTask ht = d.tasks[t.l0];
+        const BaTask ht = s_ht;
         double* gX = d.tiles + (size_t)ht.tC * BA_TILE;
         if (d.trace && tid == 0) {
           unsigned int smid;
@@ -763,20 +763,9 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
         __syncthreads();
         tile_trsm2(sB, sA, sM, (bk + 7) >> 3, tid);  // L_kk is still staged in sA
         __syncthreads();
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int e = 2 * (tid + BA_NTHREADS * u);
-          reinterpret_cast<double2*>(gX)[tid + BA_NTHREADS * u] =
-              *reinterpret_cast<const double2*>(sB + (e >> 6) * BA_LDS + (e & 63));
-        }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) {
-          red_release_add(d.cnt + ht.done, 1);
-          if (d.trace) d.trace[8 * (size_t)t.l0 + 3] = ba_globaltimer();
-        }
         if (hot & 2) {
-          const BaTask hu = d.tasks[t.l1];
+          // the diagonal update first: it is what the next pivot waits for; L_jk is published after
+          const BaTask hu = s_hu;
           if (d.trace && tid == 0) {
             unsigned int smid;
             asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -790,6 +779,18 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
             red_release_add(d.cnt + hu.done, 1);
             if (d.trace) d.trace[8 * (size_t)t.l1 + 3] = ba_globaltimer();
           }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = 2 * (tid + BA_NTHREADS * u);
+          reinterpret_cast<double2*>(gX)[tid + BA_NTHREADS * u] =
+              *reinterpret_cast<const double2*>(sB + (e >> 6) * BA_LDS + (e & 63));
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+          red_release_add(d.cnt + ht.done, 1);
+          if (d.trace) d.trace[8 * (size_t)t.l0 + 3] = ba_globaltimer();
         }
       }
       continue;
