@@ -809,8 +809,13 @@ int solve_trial(cosl_ba_solver* s, double mu, bool* solved) {
                     s->d_cptrFree, s->d_visit, s->d_rowDst, s->nSlots, s->d_Vinv, s->d_solIdx, s->rowSplits);
     } else if (s->nItems) {
       if (s->n) COSL_LAUNCH(ba_vinv_kernel, (unsigned)div_up64(s->n, 256), 256, 0, s->stream, s->d, mu, s->d_Vinv);
-      COSL_LAUNCH(ba_schur_pairs_t<4>, div_up(s->nItems, 4), 128, 0, s->stream, s->d, s->d_items,
-                  s->nItems, s->d_entries, s->d_Vinv);
+      static const bool simt = std::getenv("COSL_BA_SCHUR_SIMT") != nullptr;
+      if (simt)
+        COSL_LAUNCH(ba_schur_pairs_t<4>, div_up(s->nItems, 4), 128, 0, s->stream, s->d, s->d_items,
+                    s->nItems, s->d_entries, s->d_Vinv);
+      else  // fp64 tensor cores (DMMA): the reduced-camera contraction of north_star
+        COSL_LAUNCH(ba_schur_mma, div_up(s->nItems, 4), 128, 0, s->stream, s->d, s->d_items, s->nItems,
+                    s->d_entries, s->d_Vinv);
     }
   }
   s->timer.end(s->stream);

@@ -494,6 +494,109 @@ ba_schur_pairs_t(BaDev d, const BaPairItem* __restrict__ items, int nItems,
 }
 
 // ------------------------------------------------------------------------------------------
+// Schur contraction on the fp64 tensor cores (DMMA m8n8k4).  Same work items as ba_schur_pairs_t
+// (one warp per run of <= 512 entries of one camera pair); the 6x6 block
+//     sum_i W_ia V*_i^-1 W_ib^T  =  [W_ia]_(6 x 3n) . [V*_i^-1 W_ib^T]_(3n x 6)
+// is ONE dense contraction with the entries stacked along k.  Per chunk of 16 entries:
+//   1. the rows W_a, W_b (144 B each), V*^-1 (48 B) and e_b of the entries are staged in shared
+//      memory with 16-byte loads of contiguous segments (the scalar gathers of the SIMT kernel are
+//      what bound it: L1TEX wavefronts, see profiles/);
+//   2. T_i = V*_i^-1 W_ib^T (3 x 6) and the right-hand-side column V*_i^-1 e_b,i are formed in place;
+//   3. 12 DMMAs accumulate C(8x8) += A(8x4) B(4x8): A(r, k) = W_ia(r, c) with k = 3 i + c (rows 6, 7
+//      are zero), B(k, n) = T_i(c, n) for n < 6 and B(k, 6) = (V*^-1 e_b)(c): column 6 of the
+//      accumulator is the right-hand side of diagonal items for free.
+// ------------------------------------------------------------------------------------------
+constexpr int BA_MMA_CHUNK = 16;                      // entries per chunk
+constexpr int BA_MMA_ESTRIDE = 18 + 24 + 2;           // doubles per entry: W_a | T (3 x 8) | pad
+
+__device__ __forceinline__ void ba_dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(128, 6)
+ba_schur_mma(BaDev d, const BaPairItem* __restrict__ items, int nItems, const int4* __restrict__ entries,
+             const double* __restrict__ Vinv) {
+  __shared__ __align__(16) double s_e[4][BA_MMA_CHUNK * BA_MMA_ESTRIDE];  // per warp
+  __shared__ __align__(16) double s_wb[4][BA_MMA_CHUNK * 28];             // W_b (18) | Vinv (6) | e_b (3) | pad
+  __shared__ int4 s_ob[4][BA_MMA_CHUNK];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * 4 + w;
+  if (item >= nItems) return;
+  const BaPairItem it = items[item];
+  const bool diag = (it.rowCam == it.colCam);
+  double* se = s_e[w];
+  double* sb = s_wb[w];
+  double c0 = 0.0, c1 = 0.0;
+  const int lr = lane >> 2, lk = lane & 3;
+  for (int e0 = it.begin; e0 < it.end; e0 += BA_MMA_CHUNK) {
+    const int ne = min(BA_MMA_CHUNK, it.end - e0);
+    // ---- 1. stage: 21 (+2) 16-byte segments per entry: W_a (9), W_b (9), Vinv (3), e_b (1.5)
+    if (lane < BA_MMA_CHUNK) s_ob[w][lane] = (lane < ne) ? __ldg(&entries[e0 + lane]) : make_int4(0, 0, 0, 0);
+    __syncwarp();
+#pragma unroll 4
+    for (int t = lane; t < BA_MMA_CHUNK * 23; t += 32) {
+      const int j = t / 23, part = t - 23 * j;
+      double2 v = make_double2(0.0, 0.0);
+      if (j < ne) {
+        const int4 ob = s_ob[w][j];
+        if (part < 9) v = *reinterpret_cast<const double2*>(d.W + 18 * (size_t)ob.x + 2 * part);
+        else if (part < 18) v = *reinterpret_cast<const double2*>(d.W + 18 * (size_t)ob.y + 2 * (part - 9));
+        else if (part < 21) v = *reinterpret_cast<const double2*>(Vinv + 6 * (size_t)ob.z + 2 * (part - 18));
+        else if (diag) {
+          const double* eb = d.eb + 3 * (size_t)ob.z;
+          v = (part == 21) ? make_double2(eb[0], eb[1]) : make_double2(eb[2], 0.0);
+        }
+      }
+      if (part < 9) *reinterpret_cast<double2*>(se + j * BA_MMA_ESTRIDE + 2 * part) = v;
+      else *reinterpret_cast<double2*>(sb + j * 28 + 2 * (part - 9)) = v;
+    }
+    __syncwarp();
+    // ---- 2. T_i(c, n) = sum_c' Vinv(c, c') W_b(n, c')  (n < 6),  T_i(c, 6) = (Vinv e_b)(c), T_i(c, 7) = 0
+    for (int t = lane; t < BA_MMA_CHUNK * 24; t += 32) {
+      const int j = t / 24, cn = t - 24 * j, c = cn >> 3, n = cn & 7;
+      const double* q = sb + j * 28;
+      const double* Vi = q + 18;
+      const double v0 = (c == 0) ? Vi[0] : (c == 1) ? Vi[1] : Vi[2];
+      const double v1 = (c == 0) ? Vi[1] : (c == 1) ? Vi[3] : Vi[4];
+      const double v2 = (c == 0) ? Vi[2] : (c == 1) ? Vi[4] : Vi[5];
+      double r = 0.0;
+      if (n < 6) r = v0 * q[3 * n] + v1 * q[3 * n + 1] + v2 * q[3 * n + 2];
+      else if (n == 6) r = v0 * q[24] + v1 * q[25] + v2 * q[26];
+      se[j * BA_MMA_ESTRIDE + 18 + cn] = r;
+    }
+    __syncwarp();
+    // ---- 3. 12 k-steps of 4: k = 3 j + c
+#pragma unroll
+    for (int ks = 0; ks < 3 * BA_MMA_CHUNK / 4; ++ks) {
+      const int k = 4 * ks + lk, j = k / 3, c = k - 3 * j;
+      const double a = (lr < 6) ? se[j * BA_MMA_ESTRIDE + 3 * lr + c] : 0.0;  // W_a(r = lr, c)
+      const double b = se[j * BA_MMA_ESTRIDE + 18 + 8 * c + lr];             // T(c, n = lr)
+      ba_dmma884(c0, c1, a, b);
+    }
+    __syncwarp();
+  }
+  // C(r = lr, n = 2 lk, 2 lk + 1): block element (r, n) for n < 6; column 6 = rhs
+  if (lr < 6) {
+    double* T = d.tiles + it.dst;
+    const double cv[2] = {c0, c1};
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int n = 2 * lk + h2, r = lr;
+      if (n < 6) {
+        if (!diag || n >= r) {
+          const int col = it.cOff + (it.trans ? n : r), row = it.rOff + (it.trans ? r : n);
+          atomicAdd(&T[col * 64 + row], -cv[h2]);
+        }
+      } else if (n == 6 && diag) {
+        atomicAdd(&d.rhs[it.rhsIdx + r], -cv[h2]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Schur contraction, camera-row form (the default): CTA = one free camera a.  It walks a's
 // observations (camera-major list); for each point i it reads the point's W rows -- ONE contiguous
 // segment of the point-major W array -- and accumulates Y_a(i) W_b(i)^T for every free camera
