@@ -797,11 +797,17 @@ int solve_trial(cosl_ba_solver* s, double mu, bool* solved) {
   const bool r0 = rank_of(s) == 0;
   COSL_TRY(zero_sc(s, SC_DP_L2, 3));
   COSL_TRY(zero_sc(s, SC_FAIL, 1));
-  s->timer.begin(s->secSchur, s->stream);
+  static const bool fineSchur = std::getenv("COSL_BA_TIMING_FINE") != nullptr;  // diagnostic: init / contraction apart
+  const int secInit = fineSchur ? s->timer.section("ba_schur_init") : s->secSchur;
+  s->timer.begin(secInit, s->stream);
   const long long ns = s->ns;
   if (ns) {
     COSL_LAUNCH(ba_tile_init, std::max(1, s->plan.nTiles), 256, 0, s->stream, s->d, mu, r0 ? 1 : 0,
                 s->d_diagBlk, s->d_blkCam0, s->d_order);
+    if (fineSchur) {
+      s->timer.end(s->stream);
+      s->timer.begin(s->secSchur, s->stream);
+    }
     if (s->useRows) {
       if (s->n) COSL_LAUNCH(ba_vinv_kernel, (unsigned)div_up64(s->n, 256), 256, 0, s->stream, s->d, mu, s->d_Vinv);
       if (s->Nc)
