@@ -815,13 +815,16 @@ int solve_trial(cosl_ba_solver* s, double mu, bool* solved) {
                     s->d_cptrFree, s->d_visit, s->d_rowDst, s->nSlots, s->d_Vinv, s->d_solIdx, s->rowSplits);
     } else if (s->nItems) {
       if (s->n) COSL_LAUNCH(ba_vinv_kernel, (unsigned)div_up64(s->n, 256), 256, 0, s->stream, s->d, mu, s->d_Vinv);
-      static const bool simt = std::getenv("COSL_BA_SCHUR_SIMT") != nullptr;
-      if (simt)
-        COSL_LAUNCH(ba_schur_pairs_t<4>, div_up(s->nItems, 4), 128, 0, s->stream, s->d, s->d_items,
-                    s->nItems, s->d_entries, s->d_Vinv);
-      else  // fp64 tensor cores (DMMA): the reduced-camera contraction of north_star
+      // fp64 tensor-core variant (ba_schur_mma, DMMA m8n8k4 over smem-staged entry rows): correct and
+      // parity-tested, tensor pipe 3.3 % active, but 1.78 ms vs 0.47 ms at c4 -- its staging spends
+      // ~100 instructions per entry on index arithmetic (profiles/r2i_ba_schur_mma.summary.txt).
+      // COSL_BA_SCHUR_MMA=1 selects it; the SIMT kernel is the default.
+      if (std::getenv("COSL_BA_SCHUR_MMA") != nullptr)
         COSL_LAUNCH(ba_schur_mma, div_up(s->nItems, 4), 128, 0, s->stream, s->d, s->d_items, s->nItems,
                     s->d_entries, s->d_Vinv);
+      else
+        COSL_LAUNCH(ba_schur_pairs_t<4>, div_up(s->nItems, 4), 128, 0, s->stream, s->d, s->d_items,
+                    s->nItems, s->d_entries, s->d_Vinv);
     }
   }
   s->timer.end(s->stream);

@@ -178,6 +178,13 @@ def test_ba_schur_camera_row_kernel(api, orc, monkeypatch):
     monkeypatch.setenv("COSL_BA_SCHUR_ROWS", "1")
     i_rows = api.ba_solve(p_rows, opt)
     monkeypatch.delenv("COSL_BA_SCHUR_ROWS")
+    # the fp64 tensor-core (DMMA) contraction
+    p_mma = prob.copy()
+    monkeypatch.setenv("COSL_BA_SCHUR_MMA", "1")
+    i_mma = api.ba_solve(p_mma, opt)
+    monkeypatch.delenv("COSL_BA_SCHUR_MMA")
+    assert i_mma[10] == i_pairs[10] and abs(i_mma[1] - i_pairs[1]) <= 1e-10 * i_pairs[1]
+    assert np.abs(p_mma.X - p_pairs.X).max() < 1e-8
     assert i_rows[10] == i_pairs[10]
     assert abs(i_rows[1] - i_pairs[1]) <= 1e-10 * i_rows[1]
     assert np.abs(p_rows.X - p_pairs.X).max() < 1e-8
