@@ -206,6 +206,32 @@ static void pool_keep(int device) {
   }
 }
 
+// Pinned 128-byte slots for the per-trial scalar read-back.  cudaMallocHost / cudaFreeHost cost
+// milliseconds each; a drop-in call creates and destroys a solver, so the slots are pooled.
+struct PinnedSlots {
+  std::mutex mu;
+  std::vector<double*> free_;
+  double* get() {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!free_.empty()) {
+      double* p = free_.back();
+      free_.pop_back();
+      return p;
+    }
+    double* p = nullptr;
+    if (cudaMallocHost(&p, sizeof(double) * 16) != cudaSuccess) return nullptr;
+    return p;
+  }
+  void put(double* p) {
+    std::lock_guard<std::mutex> lk(mu);
+    free_.push_back(p);
+  }
+};
+static PinnedSlots& pinned_slots() {
+  static PinnedSlots* p = new PinnedSlots();  // never destroyed: outlives the CUDA context teardown order
+  return *p;
+}
+
 template <typename T>
 int dev_alloc(cudaStream_t st, T** p, size_t count) {
   COSL_CUDA(cudaMallocAsync((void**)p, sizeof(T) * (count ? count : 1), st));
@@ -285,12 +311,13 @@ void free_solver(cosl_ba_solver* s) {
   for (void* b : bufs)
     if (b) cudaFreeAsync(b, s->stream);
   if (s->stream) cudaStreamSynchronize(s->stream);
-  if (s->h_sc) cudaFreeHost(s->h_sc);
+  if (s->h_sc) pinned_slots().put(s->h_sc);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
 }
 
 int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
+  const double tBuild0 = now_s();
   const int m = p->m, n = p->n, mcon = p->m_con, ncon = p->n_con;
   const long long N = p->nobs;
   s->m = m;
@@ -327,6 +354,7 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
         ccam[q] = cam[o];
       }
   }
+  if (ba_timing()) std::fprintf(stderr, "[ba timing] observation index lists %.1f ms\n", 1e3 * (now_s() - tBuild0));
   // camera co-visibility (which pairs of free cameras share a free point) -> plan of the
   // reduced-system solve (ordering, tiles, task DAG) and the work lists of the Schur contraction.
   // In the multi-GPU case every rank must derive the SAME structure although it only sees the
@@ -370,7 +398,9 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   {
     int ndDepth = -1;
     if (const char* e = std::getenv("COSL_BA_ND_DEPTH")) ndDepth = std::atoi(e);
+    const double tPlan0 = now_s();
     s->plan = ba_make_plan(mf, adj, ndDepth);
+    if (ba_timing()) std::fprintf(stderr, "[ba timing] plan %.1f ms\n", 1e3 * (now_s() - tPlan0));
     if (s->plan.nb < 0) return set_error(COSL_E_INVALID, "solve plan: dependency cycle (internal error)");
   }
   const BaPlan& P = s->plan;
@@ -432,17 +462,19 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
     // order inside a bucket (by point index) does not depend on the number of workers.
     std::vector<long long> pcount((size_t)mf * mf + 1, 0);
     const int T = (mf >= 64) ? host_threads() : 1;
+    // worker t walks the camera-major observation lists of ITS cameras (cobs keeps the point order
+    // inside a camera), so no worker scans observations it does not own
     auto for_pairs = [&](int t, auto&& emit) {
       const int ja0 = (int)((long long)mf * t / T), ja1 = (int)((long long)mf * (t + 1) / T);
-      for (int i = ncon; i < n; ++i) {
+      for (long long q = cptr[ja0 + mcon]; q < cptr[ja1 + mcon]; ++q) {
+        const long long a = cobs[q];
+        const int i = pt[a];
+        if (i < ncon) continue;
+        const int ja = cam[a] - mcon;
         const long long o0 = p->ptr[i], o1 = p->ptr[i + 1];
-        for (long long a = o0; a < o1; ++a) {
-          const int ja = cam[a] - mcon;
-          if (ja < ja0 || ja >= ja1) continue;
-          for (long long b = o0; b < o1; ++b) {
-            const int jb = cam[b] - mcon;
-            if (jb > ja || (jb == ja && b >= a)) emit((size_t)ja * mf + jb, a, b);
-          }
+        for (long long b = o0; b < o1; ++b) {
+          const int jb = cam[b] - mcon;
+          if (jb > ja || (jb == ja && b >= a)) emit((size_t)ja * mf + jb, a, b);
         }
       }
     };
@@ -510,6 +542,7 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   COSL_TRY(dev_alloc(s->stream, &s->d_V, (size_t)n * 6));
   COSL_TRY(dev_alloc(s->stream, &s->d_eb, (size_t)n * 3));
   COSL_TRY(dev_alloc(s->stream, &s->d_Uea, (size_t)m * 27));
+  const double tAlloc0 = now_s();
   const int nb = std::max(1, P.nb), nTiles = std::max(1, P.nTiles);
   const size_t rhsLen = (size_t)nb * BA_TB;
   s->reduceCount = (long long)rhsLen + (long long)P.nTilesOrig * BA_TILE;
@@ -544,7 +577,9 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   COSL_TRY(dev_alloc(s->stream, &s->d_cptrFree, cptrFree.size()));
   COSL_TRY(dev_alloc(s->stream, &s->d_Vinv, (size_t)n * 6));
   COSL_TRY(dev_alloc(s->stream, &s->d_entries, (size_t)nEntries));
-  COSL_CUDA(cudaMallocHost(&s->h_sc, sizeof(double) * SC_NTOT));
+  static_assert(SC_NTOT <= 16, "pinned slot size");
+  s->h_sc = pinned_slots().get();
+  if (!s->h_sc) return set_error(COSL_E_NOMEM, "pinned host allocation failed");
 #define UP(dst, src, bytes) \
   COSL_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s->stream))
   UP(s->d_camK, camK.data(), sizeof(double) * 5 * m);
@@ -605,6 +640,7 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   UP(s->d_solIdx, h_solIdx.data(), sizeof(int) * std::max(1, mf));
 #undef UP
   COSL_CUDA(cudaStreamSynchronize(s->stream));
+  if (ba_timing()) std::fprintf(stderr, "[ba timing] allocations + uploads %.1f ms\n", 1e3 * (now_s() - tAlloc0));
   BaDev& d = s->d;
   d.m = m;
   d.n = n;
