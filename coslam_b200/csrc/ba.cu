@@ -361,30 +361,52 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   // pairs of its own point shard: the presence bitmap is all-reduced (max) first.
   const int mf = s->mf;
   const double tPair0 = now_s();
-  std::vector<uint8_t> adj((size_t)mf * mf, 0);
+  // the observation index arrays go to the device first: the pair buckets are counted there
+  COSL_TRY(dev_alloc(s->stream, &s->d_cam, (size_t)N));
+  COSL_TRY(dev_alloc(s->stream, &s->d_pt, (size_t)N));
+  COSL_TRY(dev_alloc(s->stream, &s->d_ptr, (size_t)n + 1));
+  COSL_TRY(dev_alloc(s->stream, &s->d_cobs, (size_t)Nc));
+  COSL_TRY(dev_alloc(s->stream, &s->d_ccam, (size_t)Nc));
+  const size_t nBuckets = (size_t)mf * mf;
+  unsigned *d_pcnt = nullptr, *d_poff = nullptr;
+  COSL_TRY(dev_alloc(s->stream, &d_pcnt, nBuckets + 1));
+  COSL_TRY(dev_alloc(s->stream, &d_poff, nBuckets + 1));
+  COSL_CUDA(cudaMemcpyAsync(s->d_cam, cam.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, s->stream));
+  COSL_CUDA(cudaMemcpyAsync(s->d_pt, pt.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, s->stream));
+  COSL_CUDA(cudaMemcpyAsync(s->d_ptr, p->ptr, sizeof(long long) * ((size_t)n + 1), cudaMemcpyHostToDevice, s->stream));
+  if (Nc) {
+    COSL_CUDA(cudaMemcpyAsync(s->d_cobs, cobs.data(), sizeof(int) * (size_t)Nc, cudaMemcpyHostToDevice, s->stream));
+    COSL_CUDA(cudaMemcpyAsync(s->d_ccam, ccam.data(), sizeof(int) * (size_t)Nc, cudaMemcpyHostToDevice, s->stream));
+  }
+  BaDev db;  // just what ba_pairs_build reads
+  std::memset(&db, 0, sizeof(db));
+  db.mcon = mcon;
+  db.ncon = ncon;
+  db.mf = mf;
+  db.Nc = Nc;
+  db.cam = s->d_cam;
+  db.pt = s->d_pt;
+  db.ptr = s->d_ptr;
+  db.cobs = s->d_cobs;
+  std::vector<unsigned> poff(nBuckets + 1, 0u);
+  COSL_CUDA(cudaMemsetAsync(d_pcnt, 0, sizeof(unsigned) * (nBuckets + 1), s->stream));
+  if (Nc && mf) {
+    COSL_LAUNCH(ba_pairs_build<false>, (unsigned)div_up64(Nc, 256), 256, 0, s->stream, db, d_pcnt, d_poff, nullptr);
+    COSL_LAUNCH(ba_scan_u32, 1, 1024, 0, s->stream, d_pcnt, d_poff, (long long)nBuckets);
+    COSL_CUDA(cudaMemcpyAsync(poff.data(), d_poff, sizeof(unsigned) * (nBuckets + 1), cudaMemcpyDeviceToHost, s->stream));
+  }
+  COSL_CUDA(cudaStreamSynchronize(s->stream));
+  std::vector<uint8_t> adj(nBuckets, 0);
+  for (int ja = 0; ja < mf; ++ja)
+    for (int jb = ja; jb < mf; ++jb)
+      if (poff[(size_t)ja * mf + jb + 1] > poff[(size_t)ja * mf + jb]) adj[(size_t)ja * mf + jb] = adj[(size_t)jb * mf + ja] = 1;
   auto run_threads = [&](int T, auto&& body) {
     std::vector<std::thread> th;
     for (int t = 1; t < T; ++t) th.emplace_back(body, t);
     body(0);
     for (auto& x : th) x.join();
   };
-  {
-    const int T = (n >= 4096) ? host_threads() : 1;
-    run_threads(T, [&](int t) {  // benign races: every writer stores 1
-      const int i0 = ncon + (int)((long long)(n - ncon) * t / T), i1 = ncon + (int)((long long)(n - ncon) * (t + 1) / T);
-      for (int i = i0; i < i1; ++i) {
-        const long long o0 = p->ptr[i], o1 = p->ptr[i + 1];
-        for (long long a = o0; a < o1; ++a) {
-          const int ja = cam[a] - mcon;
-          if (ja < 0) continue;
-          for (long long b = a; b < o1; ++b) {
-            const int jb = cam[b] - mcon;
-            if (jb >= 0) adj[(size_t)ja * mf + jb] = adj[(size_t)jb * mf + ja] = 1;
-          }
-        }
-      }
-    });
-  }
+  (void)run_threads;
   if (s->comm && s->comm->nranks > 1 && mf > 0) {
     uint8_t* d_adj = nullptr;
     COSL_TRY(dev_alloc(s->stream, &d_adj, adj.size()));
@@ -438,7 +460,6 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   std::vector<int> cptrFree(mf + 1, 0);
   std::vector<int4> visit;
   std::vector<BaPairItem> items;
-  std::vector<int4> entries;
   long long nEntries = 0;
   if (s->useRows) {
     rowDst.assign((size_t)mf * s->nSlots, BaRowDst{-1, 0, 0, 0});
@@ -456,42 +477,13 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
       visit[q] = make_int4(o, i, (int)p->ptr[i], (int)(p->ptr[i + 1] - p->ptr[i]));
     }
   } else {
-    // pair lists: for every free point, every pair (a <= b) of its free-camera observations,
-    // bucketed by camera pair (counting sort).  Worker t owns the camera pairs whose smaller
-    // camera lies in its range, so counting and filling need no synchronisation and the entry
-    // order inside a bucket (by point index) does not depend on the number of workers.
-    std::vector<long long> pcount((size_t)mf * mf + 1, 0);
-    const int T = (mf >= 64) ? host_threads() : 1;
-    // worker t walks the camera-major observation lists of ITS cameras (cobs keeps the point order
-    // inside a camera), so no worker scans observations it does not own
-    auto for_pairs = [&](int t, auto&& emit) {
-      const int ja0 = (int)((long long)mf * t / T), ja1 = (int)((long long)mf * (t + 1) / T);
-      for (long long q = cptr[ja0 + mcon]; q < cptr[ja1 + mcon]; ++q) {
-        const long long a = cobs[q];
-        const int i = pt[a];
-        if (i < ncon) continue;
-        const int ja = cam[a] - mcon;
-        const long long o0 = p->ptr[i], o1 = p->ptr[i + 1];
-        for (long long b = o0; b < o1; ++b) {
-          const int jb = cam[b] - mcon;
-          if (jb > ja || (jb == ja && b >= a)) emit((size_t)ja * mf + jb, a, b);
-        }
-      }
-    };
-    run_threads(T, [&](int t) { for_pairs(t, [&](size_t bucket, long long, long long) { pcount[bucket + 1]++; }); });
-    for (size_t k = 0; k < (size_t)mf * mf; ++k) pcount[k + 1] += pcount[k];
-    nEntries = pcount[(size_t)mf * mf];
-    entries.resize((size_t)nEntries);
-    std::vector<long long> fill(pcount.begin(), pcount.end() - 1);
-    run_threads(T, [&](int t) {
-      for_pairs(t, [&](size_t bucket, long long a, long long b) {
-        entries[fill[bucket]++] = make_int4((int)a, (int)b, pt[a], 0);
-      });
-    });
+    // pair lists: one bucket per camera pair (offsets counted on the device above); a work item is
+    // a run of <= 512 entries of one bucket; the entries themselves are placed by ba_pairs_build
+    nEntries = poff[nBuckets];
     const int chunk = 512;
     for (int ja = 0; ja < mf; ++ja)
       for (int jb = ja; jb < mf; ++jb) {
-        const long long b0 = pcount[(size_t)ja * mf + jb], b1 = pcount[(size_t)ja * mf + jb + 1];
+        const long long b0 = poff[(size_t)ja * mf + jb], b1 = poff[(size_t)ja * mf + jb + 1];
         if (b1 == b0) continue;
         BaPairItem it;
         std::memset(&it, 0, sizeof(it));
@@ -506,7 +498,13 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
           items.push_back(it);
         }
       }
+    COSL_TRY(dev_alloc(s->stream, &s->d_entries, (size_t)nEntries));
+    COSL_CUDA(cudaMemsetAsync(d_pcnt, 0, sizeof(unsigned) * (nBuckets + 1), s->stream));
+    if (nEntries)
+      COSL_LAUNCH(ba_pairs_build<true>, (unsigned)div_up64(Nc, 256), 256, 0, s->stream, db, d_pcnt, d_poff, s->d_entries);
   }
+  COSL_CUDA(cudaFreeAsync(d_pcnt, s->stream));
+  COSL_CUDA(cudaFreeAsync(d_poff, s->stream));
   s->nEntries = nEntries;
   s->nItems = (int)items.size();
   if (ba_timing())
@@ -531,13 +529,8 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   COSL_TRY(dev_alloc(s->stream, &s->d_pb, (size_t)n * 3));
   COSL_TRY(dev_alloc(s->stream, &s->d_nb, (size_t)n * 3));
   COSL_TRY(dev_alloc(s->stream, &s->d_dpb, (size_t)n * 3));
-  COSL_TRY(dev_alloc(s->stream, &s->d_cam, (size_t)N));
-  COSL_TRY(dev_alloc(s->stream, &s->d_pt, (size_t)N));
-  COSL_TRY(dev_alloc(s->stream, &s->d_cobs, (size_t)Nc));
-  COSL_TRY(dev_alloc(s->stream, &s->d_ccam, (size_t)Nc));
   COSL_TRY(dev_alloc(s->stream, &s->d_xy, (size_t)N * 2));
   COSL_TRY(dev_alloc(s->stream, &s->d_wgt, (size_t)N));
-  COSL_TRY(dev_alloc(s->stream, &s->d_ptr, (size_t)n + 1));
   COSL_TRY(dev_alloc(s->stream, &s->d_W, (size_t)N * 18));
   COSL_TRY(dev_alloc(s->stream, &s->d_V, (size_t)n * 6));
   COSL_TRY(dev_alloc(s->stream, &s->d_eb, (size_t)n * 3));
@@ -576,26 +569,17 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   COSL_TRY(dev_alloc(s->stream, &s->d_visit, visit.size()));
   COSL_TRY(dev_alloc(s->stream, &s->d_cptrFree, cptrFree.size()));
   COSL_TRY(dev_alloc(s->stream, &s->d_Vinv, (size_t)n * 6));
-  COSL_TRY(dev_alloc(s->stream, &s->d_entries, (size_t)nEntries));
   static_assert(SC_NTOT <= 16, "pinned slot size");
   s->h_sc = pinned_slots().get();
   if (!s->h_sc) return set_error(COSL_E_NOMEM, "pinned host allocation failed");
 #define UP(dst, src, bytes) \
   COSL_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s->stream))
   UP(s->d_camK, camK.data(), sizeof(double) * 5 * m);
-  UP(s->d_cam, cam.data(), sizeof(int) * (size_t)N);
-  UP(s->d_pt, pt.data(), sizeof(int) * (size_t)N);
-  if (Nc) {
-    UP(s->d_cobs, cobs.data(), sizeof(int) * (size_t)Nc);
-    UP(s->d_ccam, ccam.data(), sizeof(int) * (size_t)Nc);
-  }
   UP(s->d_xy, p->xy, sizeof(double) * 2 * (size_t)N);
-  UP(s->d_ptr, p->ptr, sizeof(long long) * ((size_t)n + 1));
   if (!items.empty()) UP(s->d_items, items.data(), sizeof(BaPairItem) * items.size());
   if (!rowDst.empty()) UP(s->d_rowDst, rowDst.data(), sizeof(BaRowDst) * rowDst.size());
   if (!visit.empty()) UP(s->d_visit, visit.data(), sizeof(int4) * visit.size());
   UP(s->d_cptrFree, cptrFree.data(), sizeof(int) * cptrFree.size());
-  if (nEntries) UP(s->d_entries, entries.data(), sizeof(int4) * (size_t)nEntries);
   // two ticket lists (each keeps the critical-path-first order, hence stays topological)
   s->taskOrder.clear();
   for (const BaTask& t : P.tasks)
