@@ -37,6 +37,11 @@ extern "C" const char* cosl_last_error(void) { return "mock failure"; }
     }                                                          \
   } while (0)
 
+extern "C" int cosl_ba_solve(cosl_ba_problem* p, const cosl_ba_options* o, double* info);
+// the shim's nGpus > 1 path: same checks, device list ignored by the mock
+extern "C" int cosl_ba_solve_multi(cosl_ba_problem* p, const cosl_ba_options* o, int, const int*, double* info) {
+  return cosl_ba_solve(p, o, info);
+}
 extern "C" int cosl_ba_solve(cosl_ba_problem* p, const cosl_ba_options* o, double* info) {
   if (o->device == 7) return COSL_E_CUDA;  // failure path
   EXPECT(p->m == 3 && p->n == 4 && p->nobs == 7 && p->m_con == 1 && p->n_con == 2);
