@@ -480,7 +480,9 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
     // pair lists: one bucket per camera pair (offsets counted on the device above); a work item is
     // a run of <= 512 entries of one bucket; the entries themselves are placed by ba_pairs_build
     nEntries = poff[nBuckets];
-    const int chunk = 512;
+    // <= 512 entries per work item (one warp); fewer when the problem is small (local BA: a few
+    // dozen camera pairs with thousands of entries each), so that the grid still fills the GPU
+    const int chunk = (int)std::max<long long>(64, std::min<long long>(512, nEntries / 4096));
     for (int ja = 0; ja < mf; ++ja)
       for (int jb = ja; jb < mf; ++jb) {
         const long long b0 = poff[(size_t)ja * mf + jb], b1 = poff[(size_t)ja * mf + jb + 1];
