@@ -6,7 +6,7 @@ ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -O3 -lineinfo -std=c++17 -ccbin $(HOSTCXX) -Xcompiler -fPIC,-Wall,-Wno-unknown-pragmas \
            -Xptxas -v --expt-relaxed-constexpr
 CSRC := coslam_b200/csrc
-OBJS := $(CSRC)/common.o $(CSRC)/klt.o $(CSRC)/pose.o $(CSRC)/ba.o
+OBJS := $(CSRC)/common.o $(CSRC)/klt.o $(CSRC)/pose.o $(CSRC)/ba.o $(CSRC)/posegraph.o
 LIB := coslam_b200/libcoslam_b200.so
 
 all: $(LIB) oracle

@@ -84,6 +84,7 @@ def _load():
     L.cosl_ba_solver_plan_info.argtypes = [vp, pint]
     L.cosl_ba_solver_trace.argtypes = [vp, ci, vp, vp, ci]
     L.cosl_ba_solver_tasks.argtypes = [vp, vp, ci, vp, ci]
+    L.cosl_posegraph_spread_chains.argtypes = [ci, vp, vp, vp, vp, vp, vp, vp, vp, ci]
     return L
 
 
@@ -334,6 +335,25 @@ def ba_solve_multi(prob, opt, n_gpus, devices=None):
     dev = None if devices is None else np.ascontiguousarray(devices, np.int32)
     _ck(LIB.cosl_ba_solve_multi(C.byref(s), C.byref(opt), int(n_gpus), _ptr(dev), _ptr(info)))
     return info
+
+
+def posegraph_spread_chains(chain_off, fixed, R, t, eR, et, device=0):
+    """cosl_posegraph_spread_chains: post-BA spreading of the non-key-frame poses of all cameras
+    (GlobalPoseGraph::computeNewCameraRotations + ::computeNewCameraTranslations on the chain
+    graphs of RobustBundleRTS::constructCameraGraphs).  chain_off[nChains+1]; fixed[N]; R (N,3,3);
+    t (N,3); eR (N,3,3), et (N,3): edge k = node k -> k+1.  Returns newR (N,3,3), newt (N,3)."""
+    off = np.ascontiguousarray(chain_off, np.int32)
+    N = int(off[-1])
+    fx = np.ascontiguousarray(fixed, np.uint8)
+    R = np.ascontiguousarray(R, np.float64).reshape(N, 3, 3)
+    t = np.ascontiguousarray(t, np.float64).reshape(N, 3)
+    eR = np.ascontiguousarray(eR, np.float64).reshape(N, 3, 3)
+    et = np.ascontiguousarray(et, np.float64).reshape(N, 3)
+    assert fx.size == N
+    nR, nt = np.empty((N, 3, 3)), np.empty((N, 3))
+    _ck(LIB.cosl_posegraph_spread_chains(len(off) - 1, _ptr(off), _ptr(fx), _ptr(R), _ptr(t),
+                                         _ptr(eR), _ptr(et), _ptr(nR), _ptr(nt), int(device)))
+    return nR, nt
 
 
 def nccl_unique_id():

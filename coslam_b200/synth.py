@@ -245,3 +245,55 @@ def make_pose_case(n_pts=192, width=1280, height=720, seed=BASE_SEED, noise_px=0
     R0 = _rodrigues(rng.normal(0, np.deg2rad(rot_deg) / np.sqrt(3), 3)) @ Rt
     t0 = tt + rng.normal(0, trans / np.sqrt(3), 3)
     return K, R0, t0, Ms, ms, Rt, tt
+
+
+def _rodrigues(w):
+    th = float(np.linalg.norm(w))
+    if th < 1e-300:
+        return np.eye(3)
+    k = np.asarray(w, np.float64) / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
+
+
+def make_pose_chains(lengths, key_every=8, seed=0, shift=0.03, lead_free=0, fixed_masks=None):
+    """Synthetic input of the post-BA pose-graph spreading (RobustBundleRTS::constructCameraGraphs,
+    reference app/SL_CoSLAMRobustBA.cpp:182-232): one chain of camera poses per camera, a smooth
+    trajectory; edge k = rigid transform from pose k to pose k+1 measured BEFORE bundle adjustment;
+    every `key_every`-th node is a key frame (fixed) and has then been moved by BA (rotation ~shift rad,
+    translation ~shift).  lead_free > 0 leaves that many free nodes before the first key frame.
+    Returns dict(chain_off, fixed, R, t, eR, et, id1, id2, eR_list, et_list): eR/et have one slot per
+    node (slot of a chain's last node zero), eR_list/et_list + id1/id2 are the same edges as a list."""
+    rng = np.random.default_rng(seed)
+    off = np.concatenate([[0], np.cumsum(lengths)]).astype(np.int32)
+    N = int(off[-1])
+    R, t = np.zeros((N, 3, 3)), np.zeros((N, 3))
+    eR, et = np.zeros((N, 3, 3)), np.zeros((N, 3))
+    fixed = np.zeros(N, np.uint8)
+    id1, id2 = [], []
+    for c, n in enumerate(lengths):
+        a = int(off[c])
+        if n == 0:
+            continue
+        R[a] = _rodrigues(rng.normal(size=3))
+        t[a] = rng.normal(size=3)
+        for k in range(1, n):
+            R[a + k] = _rodrigues(rng.normal(size=3) * 0.05) @ R[a + k - 1]
+            t[a + k] = t[a + k - 1] + rng.normal(size=3) * 0.1
+        for k in range(n - 1):
+            eR[a + k] = R[a + k + 1] @ R[a + k].T
+            et[a + k] = t[a + k + 1] - eR[a + k] @ t[a + k]
+            id1.append(a + k)
+            id2.append(a + k + 1)
+        if fixed_masks is not None:
+            fixed[a:a + n] = np.asarray(fixed_masks[c], np.uint8)
+        else:
+            fixed[a + lead_free:a + n:key_every] = 1
+        for k in np.nonzero(fixed[a:a + n])[0]:
+            R[a + k] = _rodrigues(rng.normal(size=3) * shift) @ R[a + k]
+            t[a + k] += rng.normal(size=3) * shift
+    id1 = np.asarray(id1, np.int32)
+    id2 = np.asarray(id2, np.int32)
+    return dict(chain_off=off, fixed=fixed, R=R, t=t, eR=eR, et=et, id1=id1, id2=id2,
+                eR_list=eR[id1] if len(id1) else np.zeros((0, 3, 3)),
+                et_list=et[id1] if len(id1) else np.zeros((0, 3)))

@@ -301,6 +301,25 @@ int cosl_ba_solver_trace(cosl_ba_solver* s, int enable, uint64_t* out, int32_t* 
  * pairs; returns the number of tasks. */
 int cosl_ba_solver_tasks(cosl_ba_solver* s, int32_t* tasks, int cap, int32_t* lists, int listCap);
 
+/* ================= post-BA pose-graph spreading =================
+ * Replaces, for chain graphs, GlobalPoseGraph::computeNewCameraRotations
+ * (slam/SL_GlobalPoseEstimation.cpp:52-218) followed by ::computeNewCameraTranslations (:220-359) as
+ * RobustBundleRTS::updateNonKeyCameraPoses calls them once per camera
+ * (app/SL_CoSLAMRobustBA.cpp:233-250) on the graphs constructCameraGraphs builds (:182-232): one
+ * chain per camera, node k -> node k+1, key-frame nodes fixed.  All chains are solved by ONE launch.
+ *   chainOff[nChains+1]  first node of each chain (chainOff[0] = 0), N = chainOff[nChains]
+ *   fixed[N]             1 = fixed node (CamPoseNode::fixed)
+ *   R[9N], t[3N]         node poses, row-major (CamPoseNode::R, ::t)
+ *   eR[9N], et[3N]       edge k = rigid transform from node k to node k+1 (CamPoseEdge::R, ::t);
+ *                        the slot of a chain's last node is not read
+ *   newR[9N], newt[3N]   out: CamPoseNode::newR, ::newt (fixed nodes: copies of R, t)
+ * Edges with uncertain scale and the constrained variants (:361-1281) are not on the post-BA path
+ * and not provided.  COSL_E_INVALID when a chain with free nodes has no fixed node (the reference's
+ * system is rank deficient there). */
+int cosl_posegraph_spread_chains(int nChains, const int* chainOff, const uint8_t* fixed,
+                                 const double* R, const double* t, const double* eR,
+                                 const double* et, double* newR, double* newt, int device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -54,6 +54,11 @@ void orc_so3_exp(const double w[3], double R[9]);
 void orc_project(const double K[9], const double R[9], const double t[3], const double M[3],
                  double m[2]);
 
+/* ---- post-BA pose-graph spreading (general edge set; mirrors cosl_posegraph_spread_chains) ---- */
+int orc_posegraph_spread(int nNodes, const int* fixed, const double* R, const double* t, int nEdges,
+                         const int* id1, const int* id2, const double* eR, const double* et,
+                         double* newR, double* newt);
+
 /* ---- BA (mirrors cosl_ba_solve / cosl_sba_motstr_levmar_x) ---- */
 int orc_ba_solve(cosl_ba_problem* prob, const cosl_ba_options* opt, double info[COSL_BA_INFOSZ]);
 /* Exactly `trials` LM trials without stop tests (the bench unit), weights from the start point. */

@@ -77,6 +77,7 @@ def lib():
     L.orc_sba_motstr_levmar_x.argtypes = [C.c_int] * 4 + [C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                                           C.c_void_p, C.c_int, C.c_void_p, C.c_int,
                                                           C.c_int, C.c_void_p, C.c_void_p]
+    L.orc_posegraph_spread.argtypes = [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 6
     L.orc_set_lapack.argtypes = [C.c_char_p]
     L.orc_set_threads.argtypes = [C.c_int]
     L.orc_set_threads.restype = None
@@ -232,6 +233,26 @@ def pose_intracam(K, R0, t0, Ms, ms, tau, prev_errs=None, opt=None):
     ok = L.orc_pose_intracam(_ptr(K), _ptr(R0), _ptr(t0), len(Ms), _ptr(pe), _ptr(Ms), _ptr(ms),
                              float(tau), _ptr(R), _ptr(t), C.byref(opt))
     return bool(ok), R.reshape(3, 3), t, opt
+
+
+def posegraph_spread(fixed, R, t, id1, id2, eR, et):
+    """Post-BA pose-graph spreading on a general edge set (posegraph_oracle.cpp).  Returns newR,
+    newt; raises when a system is rank deficient."""
+    fx = np.ascontiguousarray(fixed, np.int32)
+    n = fx.size
+    R = np.ascontiguousarray(R, np.float64).reshape(n, 3, 3)
+    t = np.ascontiguousarray(t, np.float64).reshape(n, 3)
+    id1 = np.ascontiguousarray(id1, np.int32)
+    id2 = np.ascontiguousarray(id2, np.int32)
+    ne = id1.size
+    eR = np.ascontiguousarray(eR, np.float64).reshape(ne, 3, 3)
+    et = np.ascontiguousarray(et, np.float64).reshape(ne, 3)
+    nR, nt = np.empty((n, 3, 3)), np.empty((n, 3))
+    rc = lib().orc_posegraph_spread(n, _ptr(fx), _ptr(R), _ptr(t), ne, _ptr(id1), _ptr(id2), _ptr(eR),
+                                    _ptr(et), _ptr(nR), _ptr(nt))
+    if rc != 0:
+        raise RuntimeError("orc_posegraph_spread: rank-deficient system")
+    return nR, nt
 
 
 def ba_solve(prob, opt):

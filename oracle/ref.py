@@ -56,3 +56,35 @@ def so3_exp(w):
     R = np.empty(9)
     lib().ref_getSO3ExpMap(_p(w), _p(R))
     return R.reshape(3, 3)
+
+
+# ---- post-BA pose-graph spreading: the UNMODIFIED slam/SL_GlobalPoseEstimation.cpp ----
+PATH_PG = os.path.join(HERE, "_ref", "libposegraph_ref.so")
+_lib_pg = None
+
+
+def posegraph_available():
+    return os.path.exists(PATH_PG)
+
+
+def posegraph_spread(fixed, R, t, id1, id2, eR, et):
+    """GlobalPoseGraph::computeNewCameraRotations + ::computeNewCameraTranslations of the reference
+    (slam/SL_GlobalPoseEstimation.cpp:52-359) on the graph (nodes fixed/R/t, edges id1->id2 with
+    eR/et), built the way RobustBundleRTS::constructCameraGraphs does.  Returns newR, newt."""
+    global _lib_pg
+    if _lib_pg is None:
+        _lib_pg = C.CDLL(PATH_PG)
+        _lib_pg.ref_posegraph_spread.argtypes = [C.c_int] + [C.c_void_p] * 3 + [C.c_int] + [C.c_void_p] * 6
+        _lib_pg.ref_posegraph_spread.restype = None
+    fx = np.ascontiguousarray(fixed, np.int32)
+    n = fx.size
+    R = np.ascontiguousarray(R, np.float64).reshape(n, 3, 3)
+    t = np.ascontiguousarray(t, np.float64).reshape(n, 3)
+    id1 = np.ascontiguousarray(id1, np.int32)
+    id2 = np.ascontiguousarray(id2, np.int32)
+    ne = id1.size
+    eR = np.ascontiguousarray(eR, np.float64).reshape(ne, 3, 3)
+    et = np.ascontiguousarray(et, np.float64).reshape(ne, 3)
+    nR, nt = np.empty((n, 3, 3)), np.empty((n, 3))
+    _lib_pg.ref_posegraph_spread(n, _p(fx), _p(R), _p(t), ne, _p(id1), _p(id2), _p(eR), _p(et), _p(nR), _p(nt))
+    return nR, nt

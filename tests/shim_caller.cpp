@@ -6,10 +6,12 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <vector>
 
 #include "v3d_gpuklt.h"
 #include "SL_IntraCamPose.h"
+#include "SL_GlobalPoseEstimation.h"
 
 struct Mat_d {  // rows, cols, data -- as LibVisualSLAM's Mat_d is used by CoSLAM
 	int rows, cols;
@@ -110,6 +112,36 @@ static int run() {
 		return 1;
 	}
 	std::printf("ba: point 5 -> (%.4f %.4f %.4f), truth (%.4f %.4f %.4f)\n", pts[5].x, pts[5].y, pts[5].z, Ms[15], Ms[16], Ms[17]);
+	// --- post-BA spreading as RobustBundleRTS::constructCameraGraphs / updateNonKeyCameraPoses call it:
+	// a straight-line trajectory whose last key frame BA moved by +0.3 in x -> the free nodes between the
+	// two key frames take up i/6 of the shift each (least squares spreads the residual uniformly)
+	GlobalPoseGraph graph;
+	graph.reserve(7, 7);
+	for (int k = 0; k < 7; ++k) {
+		const double tk[3] = {0.1 * k, 0, 0};
+		CamPoseNode* node = graph.newNode();
+		node->set(k, 0, R0, tk);
+	}
+	graph.poseNodes[0].fixed = true;
+	graph.poseNodes[6].fixed = true;
+	for (int k = 1; k < 7; ++k) {
+		const double dt[3] = {0.1, 0, 0};
+		graph.addEdge()->set(k - 1, k, R0, dt);
+	}
+	graph.poseNodes[6].t[0] += 0.3;
+	bool pgOk = true;
+	try {
+		graph.computeNewCameraRotations();
+		graph.computeNewCameraTranslations();
+		for (int k = 1; k < 6; ++k)
+			pgOk = pgOk && std::fabs(graph.poseNodes[k].newt[0] - (0.1 * k + 0.3 * k / 6.0)) < 1e-12
+					&& std::fabs(graph.poseNodes[k].newR[0] - 1.0) < 1e-12;
+	} catch (const std::exception& e) {
+		std::printf("posegraph: %s\n", e.what());
+		pgOk = false;
+	}
+	std::printf("posegraph: %s node 3 x = %.6f\n", pgOk ? "ok" : "FAILED", graph.poseNodes[3].newt[0]);
+	if (!pgOk) return 5;
 	if (!ok) return 2;
 	if (nDet <= 0 || tracked <= 0) return 3;
 	// the two fixed points pin a slightly perturbed gauge, so the free points settle near (not on)

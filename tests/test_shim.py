@@ -32,6 +32,7 @@ def test_shims_run_on_gpu(tmp_path):
     out = subprocess.run([exe, "run"], capture_output=True, text=True)
     assert out.returncode == 0, f"rc={out.returncode}\n{out.stdout}{out.stderr}"
     assert "klt:" in out.stdout and "pose: ok 1" in out.stdout and "ba:" in out.stdout
+    assert "posegraph: ok" in out.stdout
 
 
 def test_ba_shim_host_logic_with_a_mock_abi(tmp_path):
@@ -66,3 +67,15 @@ def test_pose_shim_host_logic_with_a_mock_abi(tmp_path):
                            "-I", os.path.join(ROOT, "coslam_b200", "shim"), src, "-o", exe])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and "MOCK_POSE_SHIM_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_posegraph_shim_host_logic_with_a_mock_abi(tmp_path):
+    """CPU: GlobalPoseGraph flattens nodes / edges for cosl_posegraph_spread_chains, keeps the
+    reference's newR / newt semantics across the two method calls with ONE ABI call, refuses
+    non-chain graphs and turns ABI failures into exceptions."""
+    exe = os.path.join(str(tmp_path), "mock_posegraph_shim")
+    src = os.path.join(ROOT, "tests", "stubs", "mock_posegraph_shim.cpp")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-I", os.path.join(ROOT, "include"),
+                           "-I", os.path.join(ROOT, "coslam_b200", "shim"), src, "-o", exe])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and "MOCK_POSEGRAPH_SHIM_OK" in out.stdout, out.stdout + out.stderr

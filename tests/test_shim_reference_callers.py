@@ -43,3 +43,12 @@ def test_pose_probe_compiles_against_the_reference_header():
 def test_pose_probe_compiles_against_the_shim_header():
     _syntax_only(os.path.join(STUBS, "probe_pose.cpp"), "-include",
                  os.path.join(SHIM, "SL_IntraCamPose.h"))
+
+
+def test_posegraph_probe_compiles_against_the_reference_header():
+    _syntax_only(os.path.join(STUBS, "probe_posegraph.cpp"))
+
+
+def test_posegraph_probe_compiles_against_the_shim_header():
+    _syntax_only(os.path.join(STUBS, "probe_posegraph.cpp"), "-include",
+                 os.path.join(SHIM, "SL_GlobalPoseEstimation.h"))
