@@ -356,6 +356,26 @@ def run_cuda(args):
         mspg = 1e3 * (time.perf_counter() - tpg)
         e2e_pageable = {"value": KLT_C * F * K / (mspg * 1e-3), "unit": "features/s", "ms_per_step": mspg / K,
                         "note": "pageable host frames (plain numpy), rank 0 only"}
+    # frame-pipelined ingest (cosl_klt_group_submit / _collect): frame n+1 is submitted before frame n
+    # is collected, so its upload runs under frame n's kernels; every frame's result is still read back
+    e2e_pipelined = None
+    if rank == 0:
+        grp.submit_raw(host_args[fidx(i)])
+        i += 1
+        for _ in range(3):
+            grp.submit_raw(host_args[fidx(i)])
+            grp.collect()
+            i += 1
+        tpl = time.perf_counter()
+        for _ in range(K):
+            grp.submit_raw(host_args[fidx(i)])
+            grp.collect()
+            i += 1
+        mspl = 1e3 * (time.perf_counter() - tpl)
+        grp.collect()
+        e2e_pipelined = {"value": KLT_C * F * K / (mspl * 1e-3), "unit": "features/s", "ms_per_step": mspl / K,
+                         "note": "pinned host frames, cosl_klt_group_submit(n+1) before _collect(n): one frame of "
+                                 "latency, same bytes per step; rank 0 only"}
     clk = clocks.stop()  # sampled across the device-resident, profiled and end-to-end regions
     barrier()
     klt_value = world * KLT_C * F * K / (ms_val * 1e-3)
@@ -436,6 +456,7 @@ def run_cuda(args):
         g2c.close()
         lb2, _ = run_local_ba(api, synth, BaOptions, torch, local, "c2", 2, 5000, 640, 480, args.no_cpu)
         extra["c2"] = {"klt": k2, "local_ba": lb2}
+        extra["posegraph"] = run_posegraph(api, synth, local, args.no_cpu)
     if not args.quick:
         # c5: 8 cameras 1920x1080, 4 k features/camera; camera c -> GPU c mod N (replicas only)
         ncam5 = max(1, 8 // world)
@@ -505,6 +526,8 @@ def run_cuda(args):
             line["klt_parity"] = klt_parity
         if e2e_pageable is not None:
             line["e2e"]["pageable"] = e2e_pageable
+        if e2e_pipelined is not None:
+            line["e2e"]["pipelined"] = e2e_pipelined
         line.update(extra)
         line["peaks"] = {"hbm_gbs": hbm_peak, "hbm_source": peak_src, **pipe_peaks()}
         emit(line)
@@ -773,6 +796,39 @@ def run_klt_leg(api, synth, torch, local, name, C, W, H, fw, fh, K, seed0, frame
                         "peak": hbm_peak, "unit": "GB/s", "peak_source": src,
                         "frac": grp.algorithmic_bytes() / (ms / K * 1e-3) / 1e9 / hbm_peak}}
     return out, grp, seqs, host_args
+
+
+def run_posegraph(api, synth, local, no_cpu, n_cams=8, n_frames=4000, key_every=20, reps=20):
+    """Post-BA pose-graph spreading: all cameras' chains in ONE cosl_posegraph_spread_chains
+    call with host arrays (H2D + kernel + D2H inside the timed region).  Parity of the same call on a
+    smaller graph against the oracle (pinned to the compiled reference) is reported beside it."""
+    g = synth.make_pose_chains([n_frames] * n_cams, key_every=key_every, seed=77, shift=0.05)
+    args = (g["chain_off"], g["fixed"], g["R"], g["t"], g["eR"], g["et"])
+    for _ in range(3):
+        api.posegraph_spread_chains(*args, device=local)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        api.posegraph_spread_chains(*args, device=local)
+    ms = 1e3 * (time.perf_counter() - t0) / reps
+    N = n_cams * n_frames
+    out = {"metric": "posegraph_nodes_per_s", "value": N / (ms * 1e-3), "unit": "nodes/s", "ms_per_call": ms,
+           "config": {"workload": f"{n_cams} camera chains x {n_frames} frames, key frame every {key_every}, "
+                                  "host arrays through cosl_posegraph_spread_chains"},
+           "h2d_bytes_per_call": N * (72 + 24 + 72 + 24 + 1), "d2h_bytes_per_call": N * 96}
+    if not no_cpu:
+        from oracle import orc as _orc
+        gs = synth.make_pose_chains([200], key_every=key_every, seed=78, shift=0.05)
+        t0 = time.perf_counter()
+        oR, ot = _orc.posegraph_spread(gs["fixed"], gs["R"], gs["t"], gs["id1"], gs["id2"], gs["eR_list"], gs["et_list"])
+        cpu_ms = 1e3 * (time.perf_counter() - t0)
+        nR, nt = api.posegraph_spread_chains(gs["chain_off"], gs["fixed"], gs["R"], gs["t"], gs["eR"], gs["et"],
+                                             device=local)
+        out["parity_max_abs_diff_vs_oracle"] = float(max(np.abs(nR - oR).max(), np.abs(nt - ot).max()))
+        out["cpu_baseline"] = {"value": 200 / (cpu_ms * 1e-3), "unit": "nodes/s", "cores": 1, "kind": "port",
+                               "sample": "one 200-node chain; the port solves DENSE least squares (the reference's "
+                                         "sparse solver is in the absent LibVisualSLAM), so this is not a "
+                                         "like-for-like speed baseline"}
+    return out
 
 
 def run_pipeline(api, synth, BaOptions, torch, local, grp, seqs, host_args, ba_prob, n_frames=60, kf_every=10):

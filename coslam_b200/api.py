@@ -47,6 +47,8 @@ def _load():
     L.cosl_klt_group_next_dev.argtypes = [vp, vp, C.c_size_t]
     L.cosl_klt_group_fetch.argtypes = [vp, vp, vp]
     L.cosl_klt_group_sync.argtypes = [vp]
+    L.cosl_klt_group_submit.argtypes = [vp, vp, C.c_size_t]
+    L.cosl_klt_group_collect.argtypes = [vp, vp, vp]
     L.cosl_klt_stream.argtypes = [vp]
     L.cosl_klt_stream.restype = vp
     L.cosl_klt_debug_pyramid.argtypes = [vp, ci, ci, ci, vp, pint, pint]
@@ -256,6 +258,18 @@ class KltGroup:
 
     def sync(self):
         _ck(LIB.cosl_klt_group_sync(self.h))
+
+    def submit_raw(self, ptrs_pitch):
+        """cosl_klt_group_submit: enqueue one frame (pointer array from host_ptrs()) and return."""
+        _ck(LIB.cosl_klt_group_submit(self.h, ptrs_pitch[0], ptrs_pitch[1]))
+
+    def submit(self, imgs):
+        self.submit_raw(self._imgs(imgs))
+
+    def collect(self):
+        """cosl_klt_group_collect: wait for the oldest submitted frame, return its tables."""
+        _ck(LIB.cosl_klt_group_collect(self.h, self._dest, _ptr(self.counts)))
+        return self.feats, self.counts
 
     def stream(self):
         return LIB.cosl_klt_stream(self.h)

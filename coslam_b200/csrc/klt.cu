@@ -61,6 +61,12 @@ struct cosl_klt {
   cosl_klt_feature* h_feat = nullptr;
   int* h_counters = nullptr;
   float4* h_present = nullptr;
+  // frame-pipelined ingest (cosl_klt_group_submit / _collect): two result slots, completion events
+  cosl_klt_feature* h_featQ[2] = {nullptr, nullptr};
+  int* h_cntQ[2] = {nullptr, nullptr};
+  cudaEvent_t evDone[2] = {nullptr, nullptr};
+  unsigned subSeq = 0;
+  int nInFlight = 0;
   bool havePrev = false;
   bool cornValid = false;  // cornerness of the current frame already produced by klt_front
   // persistent fused gain tracker (klt_gain_fused)
@@ -280,6 +286,11 @@ void free_group(cosl_klt* g) {
   cudaFreeHost(g->h_feat);
   cudaFreeHost(g->h_counters);
   cudaFreeHost(g->h_present);
+  for (int i = 0; i < 2; ++i) {
+    if (g->h_featQ[i]) cudaFreeHost(g->h_featQ[i]);
+    if (g->h_cntQ[i]) cudaFreeHost(g->h_cntQ[i]);
+    if (g->evDone[i]) cudaEventDestroy(g->evDone[i]);
+  }
   if (g->stream) cudaStreamDestroy(g->stream);
   delete g;
 }
@@ -928,6 +939,51 @@ int cosl_klt_group_fetch(cosl_klt* h, cosl_klt_feature* const* dest, int* nNew) 
   for (int c = 0; c < h->C; ++c) {
     if (dest && dest[c]) copy_out(h, c, dest[c]);
     if (nNew) nNew[c] = h->h_counters[8 * c + 2];
+  }
+  return COSL_OK;
+}
+
+// Frame-pipelined ingest (the upload half): submit() enqueues the H2D copy of frame
+// n + 1, its kernels and the D2H copy of its feature table and returns; collect() waits for the OLDEST
+// submitted frame.  With submit(n+1) called before collect(n), the image upload of frame n + 1 runs on
+// the copy stream under the tracker / detector kernels of frame n (it only waits for frame n's front
+// pass, which is the last reader of the image buffer).
+int cosl_klt_group_submit(cosl_klt* h, const uint8_t* const* imgs, size_t pitch) {
+  KLT_ENTER(h)
+  if (!imgs || pitch < (size_t)h->W) return set_error(COSL_E_INVALID, "group_submit: bad argument");
+  if (h->nInFlight >= 2) return set_error(COSL_E_STATE, "group_submit: two frames in flight, collect one first");
+  const int slot = (int)(h->subSeq & 1u);
+  if (!h->h_featQ[slot]) {
+    COSL_CUDA(cudaMallocHost(&h->h_featQ[slot], sizeof(cosl_klt_feature) * (size_t)h->F * h->C));
+    COSL_CUDA(cudaMallocHost(&h->h_cntQ[slot], sizeof(int) * 8 * h->C));
+    COSL_CUDA(cudaEventCreateWithFlags(&h->evDone[slot], cudaEventDisableTiming));
+  }
+  COSL_TRY(upload_images(h, imgs, pitch, cudaMemcpyHostToDevice));
+  h->foldAdvance = true;
+  const int rcDet = do_redetect(h);
+  h->foldAdvance = false;
+  if (rcDet != COSL_OK) return rcDet;
+  COSL_TRY(advance(h));
+  COSL_CUDA(cudaMemcpyAsync(h->h_featQ[slot], h->d_feat, sizeof(cosl_klt_feature) * (size_t)h->F * h->C,
+                            cudaMemcpyDeviceToHost, h->stream));
+  COSL_CUDA(cudaMemcpyAsync(h->h_cntQ[slot], h->d_counters, sizeof(int) * 8 * h->C, cudaMemcpyDeviceToHost,
+                            h->stream));
+  COSL_CUDA(cudaEventRecord(h->evDone[slot], h->stream));
+  ++h->subSeq;
+  ++h->nInFlight;
+  return COSL_OK;
+}
+
+int cosl_klt_group_collect(cosl_klt* h, cosl_klt_feature* const* dest, int* nNew) {
+  KLT_ENTER(h)
+  if (h->nInFlight <= 0) return set_error(COSL_E_STATE, "group_collect: nothing submitted");
+  const int slot = (int)((h->subSeq - (unsigned)h->nInFlight) & 1u);
+  COSL_CUDA(cudaEventSynchronize(h->evDone[slot]));
+  --h->nInFlight;
+  for (int c = 0; c < h->C; ++c) {
+    if (dest && dest[c])
+      std::memcpy(dest[c], h->h_featQ[slot] + (size_t)c * h->F, sizeof(cosl_klt_feature) * h->F);
+    if (nNew) nNew[c] = h->h_cntQ[slot][8 * c + 2];
   }
   return COSL_OK;
 }

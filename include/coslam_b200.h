@@ -132,6 +132,15 @@ int cosl_klt_group_first(cosl_klt* h, const uint8_t* const* imgs, size_t pitch,
                          cosl_klt_feature* const* dest, int* nDetected);
 int cosl_klt_group_fetch(cosl_klt* h, cosl_klt_feature* const* dest, int* nNew);
 int cosl_klt_group_sync(cosl_klt* h);
+/* Frame-pipelined form of cosl_klt_group_next (ingest half of SURVEY.md 8f-4; what
+ * SingleSLAM::grabReadFrame + GPUKLT::next become when the next frame is already decoded,
+ * app/SL_SingleSLAM.cpp:317-327, tracking/GPUKLT.cpp:144-161): submit() enqueues upload, kernels and
+ * the read-back of one frame and returns at once; collect() blocks for the OLDEST submitted frame
+ * and hands out its feature tables.  At most two frames may be in flight; calling submit(n+1)
+ * before collect(n) overlaps the upload of frame n+1 with the kernels of frame n.  The image
+ * buffers of a submitted frame must stay untouched until that frame has been collected. */
+int cosl_klt_group_submit(cosl_klt* h, const uint8_t* const* imgs, size_t pitch);
+int cosl_klt_group_collect(cosl_klt* h, cosl_klt_feature* const* dest, int* nNew);
 /* CUDA stream (cudaStream_t as void*) the group launches on; lets callers time with events. */
 void* cosl_klt_stream(cosl_klt* h);
 

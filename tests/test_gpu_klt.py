@@ -119,6 +119,39 @@ def test_group_matches_single(api):
             assert np.array_equal(fs["pos"].view(np.uint32), f[c]["pos"].view(np.uint32))
 
 
+def test_pipelined_submit_collect_equals_next(api):
+    """cosl_klt_group_submit / _collect (frame-pipelined ingest, 8f-4): with frame n+1 submitted before
+    frame n is collected the tables are bit-identical to the synchronous cosl_klt_group_next sequence,
+    for a multi-camera group (copy stream) and a single camera; call-order errors are reported."""
+    W, H = 640, 480
+    cfg = live_cfg(min_corner=1500.0)
+    for C in (3, 1):
+        seqs = [seq(H, W, 60 + c, n=6) for c in range(C)]
+        a = api.KltGroup(cfg, C, W, H, 6, 32, 32)
+        b = api.KltGroup(cfg, C, W, H, 6, 32, 32)
+        a.first([s.frames[0] for s in seqs])
+        b.first([s.frames[0] for s in seqs])
+        want = []
+        for k in range(1, 6):
+            f, n = a.next([s.frames[k] for s in seqs])
+            want.append((f.copy(), n.copy()))
+        with pytest.raises(api.CoslError, match="nothing submitted"):
+            b.collect()
+        b.submit([s.frames[1] for s in seqs])
+        for k in range(2, 6):
+            b.submit([s.frames[k] for s in seqs])
+            if k == 2:
+                with pytest.raises(api.CoslError, match="two frames in flight"):
+                    b.submit([s.frames[k] for s in seqs])
+            f, n = b.collect()
+            assert np.array_equal(n, want[k - 2][1]), (C, k)
+            assert np.array_equal(f.view(np.uint8), want[k - 2][0].view(np.uint8)), (C, k)
+        f, n = b.collect()
+        assert np.array_equal(n, want[4][1]) and np.array_equal(f.view(np.uint8), want[4][0].view(np.uint8))
+        a.close()
+        b.close()
+
+
 def test_full_size_known_answer_flow(api):
     """BASELINE c3 shape (4 x 1280x720, F=2000): tracked features follow the known synthetic flow."""
     W, H, F = 1280, 720, (50, 40)
