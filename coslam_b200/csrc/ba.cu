@@ -992,14 +992,19 @@ int run_robust(cosl_ba_solver* s, int fixed_trials, double info[COSL_BA_INFOSZ])
     if (first_e0 < 0) first_e0 = sinfo[0];
     total_trials += (int)sinfo[9];
   }
-  int nout = 0;
-  if (s->opt.max_err > 0 && s->N) {
-    COSL_LAUNCH(ba_residual_kernel, (unsigned)div_up64(s->N, 256), 256, 0, s->stream, s->d, s->d_pa,
-                s->d_pb, 2, s->opt.max_err, s->d_outlier);
+  double nout = 0;
+  if (s->opt.max_err > 0) {  // the same branch on every rank (options are global): collective inside
+    COSL_TRY(zero_sc(s, SC_COST, 1));
+    if (s->N)
+      COSL_LAUNCH(ba_residual_kernel, (unsigned)div_up64(s->N, 256), 256, 0, s->stream, s->d, s->d_pa,
+                  s->d_pb, 2, s->opt.max_err, s->d_outlier);
+    COSL_TRY(allreduce(s, s->d_sc, SC_NSUM, ncclSum));
+    COSL_TRY(read_sc(s));
+    nout = s->h_sc[SC_COST];  // outliers over ALL ranks' observations
   } else {
     COSL_CUDA(cudaMemsetAsync(s->d_outlier, 0, (size_t)s->N ? (size_t)s->N : 1, s->stream));
+    COSL_CUDA(cudaStreamSynchronize(s->stream));
   }
-  COSL_CUDA(cudaStreamSynchronize(s->stream));
   const auto t1 = std::chrono::steady_clock::now();
   if (info) {
     for (int k = 0; k < COSL_BA_INFOSZ; ++k) info[k] = 0;

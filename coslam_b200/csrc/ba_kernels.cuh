@@ -180,7 +180,8 @@ __device__ __forceinline__ double tukey_w(double e, double s) {
 
 // ------------------------------------------------------------------------------------------
 // cost / weights / outliers: one observation per thread
-// mode 0: sc[SC_COST] += w |e|^2 ; mode 1: wgt = tukey(|e|, maxErr) ; mode 2: outlier = |e|>=maxErr
+// mode 0: sc[SC_COST] += w |e|^2 ; mode 1: wgt = tukey(|e|, maxErr) ; mode 2: outlier = |e|>=maxErr,
+// sc[SC_COST] += number of outliers
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 ba_residual_kernel(BaDev d, const double* __restrict__ pa, const double* __restrict__ pb, int mode,
@@ -200,8 +201,14 @@ ba_residual_kernel(BaDev d, const double* __restrict__ pa, const double* __restr
     } else if (mode == 1) {
       d.wgt[o] = tukey_w(sqrt(e2), maxErr);
     } else {
-      outlier[o] = (sqrt(e2) >= maxErr) ? 1 : 0;
+      const int isOut = (sqrt(e2) >= maxErr) ? 1 : 0;
+      outlier[o] = (unsigned char)isOut;
+      c = (double)isOut;
     }
+  }
+  if (mode == 2) {  // number of outliers -> sc[SC_COST] (info[13] of the solver entry points)
+    const double t = block_sum_1(c, s_red);
+    if (threadIdx.x == 0 && t != 0) atomicAdd(&d.sc[SC_COST], t);
   }
   if (mode == 0) {
     const double t = block_sum_1(c, s_red);

@@ -847,7 +847,7 @@ int cosl_klt_feed(cosl_klt* h, int npts, const float* pts3, int* trackIds, int* 
                             h->stream));
   COSL_CUDA(cudaMemsetAsync(h->d_feedids, 0xff, sizeof(int) * (npts + 1), h->stream));
   COSL_LAUNCH(klt_feed_kill, div_up(h->F, 256), 256, 0, h->stream, h->d_dst, h->F, h->d_feedpts,
-              npts);
+              npts, (h->cfg.compat & COSL_KLT_COMPAT_FEED_STRIDE2) ? 2 : 3);
   COSL_LAUNCH(klt_feed_place, 1, 32, 0, h->stream, h->d_dst, h->F, h->d_feedpts, npts,
               h->d_feedids, h->d_feedids + npts);
   std::vector<int> ids(npts + 1);

@@ -680,14 +680,15 @@ __global__ void klt_copy_f4(const float4* __restrict__ a, float4* __restrict__ b
 // feedExternFeaturePoints (v3d_gpuklt.cpp:808-855): (1) kill KLT points within normalised
 // distance^2 < 1e-4 of any fed point, (2) place fed points into dead slots in increasing index.
 // ------------------------------------------------------------------------------------------
+// stride = 3 (default) or 2 (COSL_KLT_COMPAT_FEED_STRIDE2: the reference's reads at :826-827)
 __global__ void klt_feed_kill(float4* __restrict__ buf, int F, const float* __restrict__ pts3,
-                              int npts) {
+                              int npts, int stride) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= F) return;
   float4 c = buf[i];
   if (c.x < 0.f) return;
   for (int k = 0; k < npts; ++k) {
-    const double dx = (double)(pts3[3 * k] - c.x), dy = (double)(pts3[3 * k + 1] - c.y);
+    const double dx = (double)(pts3[stride * k] - c.x), dy = (double)(pts3[stride * k + 1] - c.y);
     if (dx * dx + dy * dy < 1e-4) {
       c.x = -1.0f;
       buf[i] = c;

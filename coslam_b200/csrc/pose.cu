@@ -437,7 +437,9 @@ int cosl_pose_intracam_batch(int C, const double* K9, const double* R0, const do
   cfg.tau = tau;
   for (int c = 1; c < C; ++c)
     if (opts[c].lambda0 != opts[0].lambda0 || opts[c].maxIterLM != opts[0].maxIterLM ||
-        opts[c].maxIterRW != opts[0].maxIterRW)
+        opts[c].maxIterRW != opts[0].maxIterRW || opts[c].epsErrorChangeLM != opts[0].epsErrorChangeLM ||
+        opts[c].epsParamChangeLM != opts[0].epsParamChangeLM ||
+        opts[c].epsErrorChangeRW != opts[0].epsErrorChangeRW)
       return set_error(COSL_E_INVALID, "batched pose solve needs identical options per camera");
   // per-device workspace, reused across calls: the solve is latency-bound, a cudaMalloc/cudaFree
   // pair per call would cost more than the kernel

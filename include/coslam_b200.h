@@ -65,7 +65,12 @@ typedef struct cosl_klt_config {
 /* bit 1 (COSL_KLT_PASS_KERNELS, diagnostic): run the gain tracker as one kernel launch per
  * (level, iteration) pass like the reference's draw calls, instead of the single persistent
  * kernel; results are bit-identical, only slower. */
-enum { COSL_KLT_COMPAT_ITER5 = 1, COSL_KLT_PASS_KERNELS = 2 };
+enum { COSL_KLT_COMPAT_ITER5 = 1, COSL_KLT_PASS_KERNELS = 2, COSL_KLT_COMPAT_FEED_STRIDE2 = 4 };
+/* bit 2 (COSL_KLT_COMPAT_FEED_STRIDE2, parity runs): feedExternFeaturePoints' proximity test reads
+ * the fed points as featPts[2k], featPts[2k+1] although the array holds 3 floats per point
+ * (v3d_gpuklt.cpp:826-827 vs :841-842).  The default uses stride 3 in both loops (the evident
+ * intent); with this bit the kill test reproduces the reference's stride-2 reads, so the same
+ * tracks die and the same trackIds come back as from the reference for the same input. */
 
 /* Mirrors V3D_GPU::KLT_TrackedFeature (v3d_gpuklt.h:166-176): 20 bytes. */
 typedef struct cosl_klt_feature {
@@ -186,7 +191,9 @@ void cosl_pose_opt_default(cosl_pose_opt* opt);
 int cosl_pose_intracam(const double K[9], const double R0[9], const double t0[3], int npts,
                        const double* prevErrs /* nullable */, const double* Ms, const double* ms,
                        double tau, double R_opt[9], double t_opt[3], cosl_pose_opt* opt, int* ok);
-/* Batched over C cameras in one launch (one warp per camera).  K9/R0/t0/R_opt/t_opt are C
+/* Batched over C cameras in one launch (one 128-thread CTA per camera; the option
+ * fields maxIterLM, maxIterRW, lambda0 and the three eps* must be equal for all cameras, else
+ * COSL_E_INVALID).  K9/R0/t0/R_opt/t_opt are C
  * consecutive blocks; Ms[c]/ms[c]/prevErrs[c] per-camera HOST arrays (prevErrs or prevErrs[c]
  * may be NULL); opts has C entries; ok has C entries. */
 int cosl_pose_intracam_batch(int C, const double* K9, const double* R0, const double* t0,

@@ -683,16 +683,19 @@ int orc_klt_redetect(orc_klt* h, const uint8_t* img, size_t pitch, cosl_klt_feat
   return COSL_OK;
 }
 
-// KLT_SequenceTracker::feedExternFeaturePoints (v3d_gpuklt.cpp:808-855), stride 3 throughout
+// KLT_SequenceTracker::feedExternFeaturePoints (v3d_gpuklt.cpp:808-855): stride 3 throughout by
+// default; with COSL_KLT_COMPAT_FEED_STRIDE2 the proximity test reads featPts[2k], featPts[2k+1]
+// exactly as :826-827 do.
 int orc_klt_feed(orc_klt* h, int npts, const float* pts3, int* trackIds, int* nFed) {
   const int F = h->F;
+  const int st = (h->cfg.compat & COSL_KLT_COMPAT_FEED_STRIDE2) ? 2 : 3;
   const double radius2 = 1e-4;
   std::vector<float>& c = h->dst;
   for (int k = 0; k < npts; ++k)
     for (int i = 0; i < F; ++i) {
       if (c[3 * i] < 0) continue;
-      double dx = (double)(pts3[3 * k] - c[3 * i]);
-      double dy = (double)(pts3[3 * k + 1] - c[3 * i + 1]);
+      double dx = (double)(pts3[st * k] - c[3 * i]);
+      double dy = (double)(pts3[st * k + 1] - c[3 * i + 1]);
       if (dx * dx + dy * dy < radius2) c[3 * i] = -1.0f;
     }
   int k = 0;

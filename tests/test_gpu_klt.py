@@ -72,10 +72,12 @@ def test_sequence_parity(api, orc, gain, W, H, fw, fh):
         assert (fo["status"] == 0).sum() > 0.5 * (fo["status"] >= 0).sum()
 
 
-def test_track_only_cadence_and_feed(api, orc):
+@pytest.mark.parametrize("compat_bit", [0, 4])  # 4 = COSL_KLT_COMPAT_FEED_STRIDE2 (reference's stride-2 kill test)
+def test_track_only_cadence_and_feed(api, orc, compat_bit):
     W, H = 640, 480
     s = seq(H, W, 22, n=3)
     cfg = live_cfg(gain=True, min_corner=1500.0)
+    cfg.compat |= compat_bit
     g, o = _pair(api, orc, cfg, W, H, 6, 32, 32)
     g.first(s.frames[0])
     o.first(s.frames[0])

@@ -100,6 +100,12 @@ def test_ba_c3_properties(api):
     kept = ~p.outlier.astype(bool)
     assert p.rms(kept) < 0.8
     assert (p.outlier.astype(bool) & truth["is_outlier"]).sum() > 0.95 * truth["is_outlier"].sum()
+    # info[13] is counted on the device by the solver handle as well (not only patched by cosl_ba_solve)
+    s = api.BaSolver(prob.copy(), opt)
+    info_s = s.run()
+    ps = s.download()
+    assert info_s[13] == ps.outlier.sum() > 0
+    s.close()
 
 
 def test_sba_signature_wrapper(api, orc):

@@ -152,3 +152,29 @@ def test_cross_check_against_opencv_lk(orc):
     ours = f1["pos"][tr] * [W, H] - 0.5
     d = np.hypot(*(p1.reshape(-1, 2)[ok] - ours[ok]).T)
     assert np.median(d) < 0.25
+
+
+def test_feed_stride2_compat_bit_reproduces_the_reference_reads(orc):
+    """COSL_KLT_COMPAT_FEED_STRIDE2: the kill test of feedExternFeaturePoints reads featPts[2k],
+    featPts[2k+1] (v3d_gpuklt.cpp:826-827) although points are 3 floats apart.  Known answer: feed two
+    points, the SECOND one sitting on a live KLT point.  Stride 3 (default) kills that KLT point and
+    reuses its slot; stride 2 tests (pts[2], pts[3]) = (0, x1) for k = 1 instead, which is outside the
+    border margin every KLT point keeps, so the point survives and only dead slots are handed out."""
+    W, H = 320, 240
+    s = seq(H, W, 14, n=2)
+    for bit in (0, 4):
+        cfg = live_cfg(min_corner=1000.0)
+        cfg.compat |= bit
+        k = orc.OracleKlt(cfg, W, H, 4, 16, 16)
+        f0, n0 = k.first(s.frames[0])
+        live = np.nonzero(f0["status"] >= 0)[0]
+        dead_before = np.nonzero(f0["status"] < 0)[0]
+        assert len(dead_before) >= 2 and live[0] < dead_before[1]
+        victim = live[0]
+        pts = np.zeros((2, 3), np.float32)
+        pts[0, :2] = (0.003, 0.003)
+        pts[1, :2] = f0["pos"][victim]
+        ids, nfed = k.feed(pts)
+        assert nfed == 2
+        expect = sorted(list(dead_before) + ([victim] if bit == 0 else []))[:2]
+        assert list(ids[:2]) == expect, (bit, ids, expect)

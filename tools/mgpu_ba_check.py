@@ -46,7 +46,8 @@ if rank == 0:
     dX = np.abs(X - ref.X).max(); dR = np.abs(shard.R - ref.R).max(); dt = np.abs(shard.t - ref.t).max()
     print(f"multi-GPU ({world}) vs single GPU: max|dX| {dX:.3e} max|dR| {dR:.3e} max|dt| {dt:.3e} "
           f"cost {info[1]:.9g} vs {info1[1]:.9g} trials {info[10]} vs {info1[10]} "
-          f"outliers equal {np.array_equal(out, ref.outlier)}")
+          f"outliers equal {np.array_equal(out, ref.outlier)} info[13] {info[13]:.0f} vs flags {int(out.sum())}")
+    assert info[13] == out.sum(), "info[13] of cosl_ba_solver_run must count the outliers of ALL ranks"
     ok = dX < 1e-6 and dR < 1e-8 and abs(info[1] - info1[1]) < 1e-8 * info1[1] and info[10] == info1[10]
     print("MGPU_PARITY_OK" if ok else "MGPU_PARITY_FAIL")
 dist.barrier()
