@@ -118,6 +118,7 @@ struct cosl_ba_solver {
   int nSlots = 1;
   size_t rowsSmem = 0;
   bool useRows = false;
+  bool schurSimt = false;  // COSL_BA_SCHUR_SIMT=1: scalar-gather pair kernel instead of the staged one
   int rowSplits = 1;
   int4* d_entries = nullptr;
   int nItems = 0;
@@ -482,7 +483,10 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
     nEntries = poff[nBuckets];
     // <= 512 entries per work item (one warp); fewer when the problem is small (local BA: a few
     // dozen camera pairs with thousands of entries each), so that the grid still fills the GPU
-    const int chunk = (int)std::max<long long>(64, std::min<long long>(512, nEntries / 4096));
+    s->schurSimt = std::getenv("COSL_BA_SCHUR_SIMT") != nullptr;
+    // the staged kernel works in batches of 32 entries and sums 32 lanes per item: multiples of 32, >= 128
+    const int chunk = s->schurSimt ? (int)std::max<long long>(64, std::min<long long>(512, nEntries / 4096))
+                                   : (int)(32 * std::max<long long>(4, std::min<long long>(16, nEntries / (4096 * 32))));
     for (int ja = 0; ja < mf; ++ja)
       for (int jb = ja; jb < mf; ++jb) {
         const long long b0 = poff[(size_t)ja * mf + jb], b1 = poff[(size_t)ja * mf + jb + 1];
@@ -688,6 +692,7 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
                                    (int)smallBytes));
   COSL_CUDA(cudaFuncSetAttribute(ba_tile_solve, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  BA_TILE_SMEM));
+  COSL_CUDA(cudaFuncSetAttribute(ba_schur_pairs_st, cudaFuncAttributeMaxDynamicSharedMemorySize, BA_ST_SMEM));
   if (s->useRows && s->rowsSmem > 40 * 1024)
     COSL_CUDA(cudaFuncSetAttribute(ba_schur_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)s->rowsSmem));
@@ -844,9 +849,12 @@ int solve_trial(cosl_ba_solver* s, double mu, bool* solved) {
       if (std::getenv("COSL_BA_SCHUR_MMA") != nullptr)
         COSL_LAUNCH(ba_schur_mma, div_up(s->nItems, 4), 128, 0, s->stream, s->d, s->d_items, s->nItems,
                     s->d_entries, s->d_Vinv);
-      else
+      else if (s->schurSimt)
         COSL_LAUNCH(ba_schur_pairs_t<4>, div_up(s->nItems, 4), 128, 0, s->stream, s->d, s->d_items,
                     s->nItems, s->d_entries, s->d_Vinv);
+      else
+        COSL_LAUNCH(ba_schur_pairs_st, div_up(s->nItems, BA_ST_WARPS), 32 * BA_ST_WARPS, BA_ST_SMEM, s->stream,
+                    s->d, s->d_items, s->nItems, s->d_entries, s->d_Vinv);
     }
   }
   s->timer.end(s->stream);

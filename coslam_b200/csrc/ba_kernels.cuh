@@ -501,6 +501,153 @@ ba_schur_pairs_t(BaDev d, const BaPairItem* __restrict__ items, int nItems,
 }
 
 // ------------------------------------------------------------------------------------------
+// Staged variant of the pair-list contraction (default).  ba_schur_pairs_t gathers the rows of an entry
+// with scalar 8-byte loads issued by the lanes that consume them: 33 load instructions per 16 entries,
+// each touching ~16 different 128-byte lines -> ~33 L1TEX wavefronts per entry, which is what bounds it
+// (0.47 ms at c4 for 1.7 GFLOP).  Here a warp works on 32 entries at a time:
+//   1. STAGE: the 21 16-byte segments of every entry -- W_a (9), W_b (9), V*^-1 (3) -- are copied with
+//      cp.async in SEGMENT-major order (consecutive lanes copy consecutive segments of the same row, so
+//      one instruction touches ~8 lines instead of 32: ~5 wavefronts per entry), into a row of 42
+//      doubles per entry (336 B = 21 x 16 B, an odd multiple of 16 B: conflict-free 16-byte reads);
+//   2. CONTRACT: lane j owns entry j, reads its row with 21 LDS.128 and accumulates the whole 6x6 block
+//      (+ the 6 right-hand-side terms of diagonal items) in registers: 162 DFMA per entry;
+//   3. the next batch is in flight (second buffer) while the current one is contracted;
+//   4. at the end of the item the 32 partial blocks are summed through the (now free) staging buffer:
+//      lane k adds up element k of all lanes -- 36 + 6 elements, one atomic each.
+// ------------------------------------------------------------------------------------------
+constexpr int BA_ST_WARPS = 4;
+constexpr int BA_ST_ROW = 42;                                   // doubles per staged entry
+constexpr int BA_ST_BUF = 32 * BA_ST_ROW;                       // doubles per batch buffer (10752 B)
+constexpr int BA_ST_SMEM = BA_ST_WARPS * 2 * BA_ST_BUF * 8;     // 86016 B per CTA (dynamic)
+
+__device__ __forceinline__ void ba_cp_async16(double* smemDst, const double* gsrc) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smemDst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gsrc) : "memory");
+}
+
+// copy the rows of the batch whose entry descriptors the lanes hold (lane j: entry j; ne valid entries)
+__device__ __forceinline__ void ba_st_stage(const BaDev& d, const double* __restrict__ Vinv, int4 ob, int ne,
+                                            int lane, double* buf) {
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {  // W_a and W_b: 32 rows x 9 segments each
+    const int sidx = t * 32 + lane, j = sidx / 9, part = sidx - 9 * j;
+    const int oa = __shfl_sync(0xffffffffu, ob.x, j), obb = __shfl_sync(0xffffffffu, ob.y, j);
+    if (j < ne) {
+      ba_cp_async16(buf + j * BA_ST_ROW + 2 * part, d.W + 18 * (size_t)oa + 2 * part);
+      ba_cp_async16(buf + j * BA_ST_ROW + 18 + 2 * part, d.W + 18 * (size_t)obb + 2 * part);
+    }
+  }
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {  // V*^-1: 32 rows x 3 segments
+    const int sidx = t * 32 + lane, j = sidx / 3, part = sidx - 3 * j;
+    const int pi = __shfl_sync(0xffffffffu, ob.z, j);
+    if (j < ne) ba_cp_async16(buf + j * BA_ST_ROW + 36 + 2 * part, Vinv + 6 * (size_t)pi + 2 * part);
+  }
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+
+__global__ void __launch_bounds__(32 * BA_ST_WARPS, 2)
+ba_schur_pairs_st(BaDev d, const BaPairItem* __restrict__ items, int nItems, const int4* __restrict__ entries,
+                  const double* __restrict__ Vinv) {
+  extern __shared__ __align__(16) double s_st[];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * BA_ST_WARPS + w;
+  if (item >= nItems) return;
+  const BaPairItem it = items[item];
+  const bool diag = (it.rowCam == it.colCam);
+  double* buf0 = s_st + (size_t)w * 2 * BA_ST_BUF;
+  double acc[36], racc[6];
+#pragma unroll
+  for (int k = 0; k < 36; ++k) acc[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; ++k) racc[k] = 0.0;
+  const int nb = (it.end - it.begin + 31) >> 5;
+  const int4 zero4 = make_int4(0, 0, 0, 0);
+  int4 cur = (it.begin + lane < it.end) ? __ldg(&entries[it.begin + lane]) : zero4;
+  int4 nxt = (it.begin + 32 + lane < it.end) ? __ldg(&entries[it.begin + 32 + lane]) : zero4;
+  ba_st_stage(d, Vinv, cur, min(32, it.end - it.begin), lane, buf0);
+  for (int b = 0; b < nb; ++b) {
+    const int e0 = it.begin + 32 * b;
+    const int4 mine = cur;  // descriptor of this lane's entry in batch b (point index for e_b)
+    cur = nxt;
+    if (b + 1 < nb) {
+      nxt = (e0 + 64 + lane < it.end) ? __ldg(&entries[e0 + 64 + lane]) : zero4;
+      ba_st_stage(d, Vinv, cur, min(32, it.end - (e0 + 32)), lane, buf0 + ((b + 1) & 1) * BA_ST_BUF);
+      asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    }
+    __syncwarp();
+    if (e0 + lane < it.end) {
+      const double* row = buf0 + (b & 1) * BA_ST_BUF + lane * BA_ST_ROW;
+      double wa[18], wb[18], Iv[6];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const double2 v = *reinterpret_cast<const double2*>(row + 2 * k);
+        wa[2 * k] = v.x;
+        wa[2 * k + 1] = v.y;
+      }
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const double2 v = *reinterpret_cast<const double2*>(row + 18 + 2 * k);
+        wb[2 * k] = v.x;
+        wb[2 * k + 1] = v.y;
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double2 v = *reinterpret_cast<const double2*>(row + 36 + 2 * k);
+        Iv[2 * k] = v.x;
+        Iv[2 * k + 1] = v.y;
+      }
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const double b0 = wb[3 * c], b1 = wb[3 * c + 1], b2 = wb[3 * c + 2];
+        const double t0 = Iv[0] * b0 + Iv[1] * b1 + Iv[2] * b2;
+        const double t1 = Iv[1] * b0 + Iv[3] * b1 + Iv[4] * b2;
+        const double t2 = Iv[2] * b0 + Iv[4] * b1 + Iv[5] * b2;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) acc[6 * r + c] += wa[3 * r] * t0 + wa[3 * r + 1] * t1 + wa[3 * r + 2] * t2;
+      }
+      if (diag) {
+        const double* eb = d.eb + 3 * (size_t)mine.z;
+        const double e0v = eb[0], e1v = eb[1], e2v = eb[2];
+        const double t0 = Iv[0] * e0v + Iv[1] * e1v + Iv[2] * e2v;
+        const double t1 = Iv[1] * e0v + Iv[3] * e1v + Iv[4] * e2v;
+        const double t2 = Iv[2] * e0v + Iv[4] * e1v + Iv[5] * e2v;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) racc[r] += wa[3 * r] * t0 + wa[3 * r + 1] * t1 + wa[3 * r + 2] * t2;
+      }
+    }
+    __syncwarp();  // the buffer of batch b is free again (restaged at iteration b + 1)
+  }
+  // ---- sum over the 32 lanes through shared memory: red[k * 33 + lane]
+  double* red = buf0;  // 42 x 33 doubles = 11088 B <= 2 buffers
+#pragma unroll
+  for (int k = 0; k < 36; ++k) red[k * 33 + lane] = acc[k];
+  if (diag) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) red[(36 + k) * 33 + lane] = racc[k];
+  }
+  __syncwarp();
+  double* T = d.tiles + it.dst;
+  for (int k = lane; k < (diag ? 42 : 36); k += 32) {
+    double sum = 0.0;
+#pragma unroll 8
+    for (int l = 0; l < 32; ++l) sum += red[k * 33 + l];
+    if (k < 36) {
+      const int r = k / 6, c = k - 6 * r;
+      // only the lower part (row >= col of the tile, i.e. c >= r) of diagonal blocks is kept
+      if (!diag || c >= r) {
+        const int col = it.cOff + (it.trans ? c : r), row = it.rOff + (it.trans ? r : c);
+        atomicAdd(&T[col * 64 + row], -sum);
+      }
+    } else {
+      atomicAdd(&d.rhs[it.rhsIdx + (k - 36)], -sum);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Pair work lists built on the device (solver set-up).  For every free observation a = (camera ja,
 // point i) of the camera-major list and every observation b of the same point with camera jb > ja,
 // or jb == ja and b >= a: one entry in bucket (ja, jb).  Pass 1 counts per bucket, ba_scan_u32 turns

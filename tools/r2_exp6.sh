@@ -1,6 +1,7 @@
 #!/bin/bash
-O=gpurun_out/r2f; mkdir -p $O
-timeout 900 python bench.py > $O/bench.json 2> $O/bench.err; echo "bench rc=$?"; tail -5 $O/bench.err
-head -c 1500 $O/bench.json; echo
-timeout 300 python bench.py --impl reference --steps 20 --warmup 5 > $O/bench_reference.json 2> $O/bench_reference.err; head -c 400 $O/bench_reference.json; echo
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5 | tee $O/pytest_gpu.txt
+O=gpurun_out/r2n; mkdir -p $O
+timeout 300 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_pose_ba.py -x -q -k "local_parity_c2 or intercam" 2>&1 | tail -12 | tee $O/sanitizer.txt
+timeout 900 python -m pytest tests/test_gpu_pose_ba.py tests/test_gpu_klt.py -x -q 2>&1 | tail -8 | tee $O/pytest.txt
+timeout 400 python tools/r2_ba_exp.py -1 2>&1 | tee $O/ba_exp_st.txt
+COSL_BA_SCHUR_SIMT=1 timeout 400 python tools/r2_ba_exp.py -1 2>&1 | tee $O/ba_exp_simt.txt
+python tools/r2_local_ba.py 2>&1 | grep "{}" | tee $O/local.txt
