@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "ba_kernels.cuh"
+#include "ba_schur_blk.cuh"
 #include "ba_tile.cuh"
 #include "common.cuh"
 
@@ -118,6 +119,12 @@ struct cosl_ba_solver {
   int nSlots = 1;
   size_t rowsSmem = 0;
   bool useRows = false;
+  bool useBlk = false;     // camera-block DMMA contraction (COSL_BA_SCHUR_BLK=1)
+  BaVisit* d_bvis = nullptr;
+  BaBlkItem* d_bitems = nullptr;
+  BaBlkDst* d_btabs = nullptr;
+  int nBItems = 0;
+  long long nVisits = 0;
   bool schurSimt = false;  // COSL_BA_SCHUR_SIMT=1: scalar-gather pair kernel instead of the staged one
   int rowSplits = 1;
   int4* d_entries = nullptr;
@@ -308,7 +315,8 @@ void free_solver(cosl_ba_solver* s) {
                   s->d_V, s->d_eb, s->d_Uea, s->d_S, s->d_y, s->d_x, s->d_sc, s->d_outlier,
                   s->d_items, s->d_entries, s->d_Linv, s->d_cnt, s->d_tasks, s->d_bwd, s->d_blkRows,
                   s->d_blkRow0, s->d_tileIdx, s->d_diagBlk, s->d_blkCam0, s->d_order, s->d_solIdx,
-                  s->d_trace, s->d_sum, s->d_rhsS, s->d_rowDst, s->d_cptrFree, s->d_Vinv, s->d_visit};
+                  s->d_trace, s->d_sum, s->d_rhsS, s->d_rowDst, s->d_cptrFree, s->d_Vinv, s->d_visit,
+                  s->d_bvis, s->d_bitems, s->d_btabs};
   for (void* b : bufs)
     if (b) cudaFreeAsync(b, s->stream);
   if (s->stream) cudaStreamSynchronize(s->stream);
@@ -477,7 +485,139 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
       const int o = cobs[q], i = pt[o];
       visit[q] = make_int4(o, i, (int)p->ptr[i], (int)(p->ptr[i + 1] - p->ptr[i]));
     }
-  } else {
+  }
+  // camera-block visits (ba_schur_blk.cuh): default contraction unless a point touches too many blocks
+  // Measured at c4 (profiles/r2n_*): correct, tensor pipe 29 % active, but 0.70 ms vs 0.34 ms for the staged
+  // pair lists -- in the benchmark scene a point is seen by ~13 of ~36 candidate cameras, so even with
+  // co-visibility blocking a visit holds only 3.5 of 16 possible pairs (DMMAs mostly multiply zeros and
+  // the per-visit staging overhead dominates).  COSL_BA_SCHUR_BLK=1 selects it; pair lists stay the default.
+  s->useBlk = !s->useRows && mf > 0 && std::getenv("COSL_BA_SCHUR_BLK") != nullptr;
+  if (s->useBlk) {
+    // blocks of <= BA_CB cameras by co-visibility: seed = first unassigned camera, then repeatedly the
+    // unassigned camera sharing the most points with the block so far (pair counts from the bucket scan)
+    std::vector<int> camBlock(mf, -1), camSlot(mf, 0), blkCams;
+    auto pairCnt = [&](int a, int b) -> long long {
+      if (a > b) std::swap(a, b);
+      return (long long)poff[(size_t)a * mf + b + 1] - (long long)poff[(size_t)a * mf + b];
+    };
+    int nB = 0;
+    {
+      std::vector<long long> score(mf);
+      for (int j = 0; j < mf; ++j) {
+        if (camBlock[j] >= 0) continue;
+        camBlock[j] = nB;
+        camSlot[j] = 0;
+        blkCams.push_back(j);
+        std::fill(score.begin(), score.end(), 0);
+        int last = j;
+        int filled = 1;
+        for (; filled < BA_CB; ++filled) {
+          long long best = 0;
+          int bestK = -1;
+          for (int k = 0; k < mf; ++k) {
+            if (camBlock[k] >= 0) continue;
+            score[k] += pairCnt(last, k);
+            if (score[k] > best) {
+              best = score[k];
+              bestK = k;
+            }
+          }
+          if (bestK < 0) break;
+          camBlock[bestK] = nB;
+          camSlot[bestK] = filled;
+          blkCams.push_back(bestK);
+          last = bestK;
+        }
+        for (; filled < BA_CB; ++filled) blkCams.push_back(-1);
+        ++nB;
+      }
+    }
+    int *d_camBlock = nullptr, *d_camSlot = nullptr;
+    COSL_TRY(dev_alloc(s->stream, &d_camBlock, (size_t)mf));
+    COSL_TRY(dev_alloc(s->stream, &d_camSlot, (size_t)mf));
+    COSL_CUDA(cudaMemcpyAsync(d_camBlock, camBlock.data(), sizeof(int) * mf, cudaMemcpyHostToDevice, s->stream));
+    COSL_CUDA(cudaMemcpyAsync(d_camSlot, camSlot.data(), sizeof(int) * mf, cudaMemcpyHostToDevice, s->stream));
+    const size_t nBB = (size_t)nB * nB;
+    unsigned *d_vcnt = nullptr, *d_voff = nullptr;
+    int* d_ovf = nullptr;
+    COSL_TRY(dev_alloc(s->stream, &d_vcnt, nBB + 1));
+    COSL_TRY(dev_alloc(s->stream, &d_voff, nBB + 1));
+    COSL_TRY(dev_alloc(s->stream, &d_ovf, (size_t)1));
+    COSL_CUDA(cudaMemsetAsync(d_vcnt, 0, sizeof(unsigned) * (nBB + 1), s->stream));
+    COSL_CUDA(cudaMemsetAsync(d_ovf, 0, sizeof(int), s->stream));
+    BaDev dv = db;
+    dv.n = n;
+    std::vector<unsigned> voff(nBB + 1, 0u);
+    int ovf = 0;
+    if (n > ncon) {
+      COSL_LAUNCH(ba_visits_build<false>, (unsigned)div_up(n - ncon, 128), 128, 0, s->stream, dv, nB, d_camBlock, d_camSlot,
+                  d_vcnt, d_voff, nullptr, d_ovf);
+      COSL_LAUNCH(ba_scan_u32, 1, 1024, 0, s->stream, d_vcnt, d_voff, (long long)nBB);
+      COSL_CUDA(cudaMemcpyAsync(voff.data(), d_voff, sizeof(unsigned) * (nBB + 1), cudaMemcpyDeviceToHost, s->stream));
+      COSL_CUDA(cudaMemcpyAsync(&ovf, d_ovf, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    }
+    COSL_CUDA(cudaStreamSynchronize(s->stream));
+    if (ovf) {
+      s->useBlk = false;  // a point seen from > BA_VIS_MAXB camera blocks: pair lists handle any structure
+    } else {
+      s->nVisits = voff[nBB];
+      // a work item = a run of visits of one block pair (one warp); aim at >= ~8 items per SM-resident warp
+      const long long chunkV = 4 * std::max<long long>(8, std::min<long long>(64, s->nVisits / (4096 * 4)));
+      std::vector<BaBlkItem> bitems;
+      std::vector<BaBlkDst> btabs;
+      for (int A = 0; A < nB; ++A)
+        for (int B = A; B < nB; ++B) {
+          const long long b0 = voff[(size_t)A * nB + B], b1 = voff[(size_t)A * nB + B + 1];
+          if (b1 == b0) continue;
+          BaBlkDst tab;
+          for (int a = 0; a < BA_CB; ++a) {
+            const int ja = blkCams[(size_t)A * BA_CB + a];
+            tab.rhsIdx[a] = ja >= 0 ? P.camBlk[ja] * BA_TB + P.camOff[ja] : -1;
+            for (int b = 0; b < BA_CB; ++b) {
+              const int jb = blkCams[(size_t)B * BA_CB + b], t = a * BA_CB + b;
+              tab.dst[t] = -1;
+              tab.rOff[t] = tab.cOff[t] = tab.trans[t] = 0;
+              if (ja < 0 || jb < 0 || (A == B && a > b) || !adj[(size_t)ja * mf + jb]) continue;
+              if (!pair_dst(ja, jb, tab.dst[t], tab.rOff[t], tab.cOff[t], tab.trans[t]))
+                return set_error(COSL_E_INVALID, "solve plan: missing tile");
+            }
+          }
+          BaBlkItem it;
+          std::memset(&it, 0, sizeof(it));
+          it.A = A;
+          it.B = B;
+          it.tab = (int)btabs.size();
+          btabs.push_back(tab);
+          for (long long b = b0; b < b1; b += chunkV) {
+            it.begin = (int)b;
+            it.end = (int)std::min(b1, b + chunkV);
+            bitems.push_back(it);
+          }
+        }
+      s->nBItems = (int)bitems.size();
+      COSL_TRY(dev_alloc(s->stream, &s->d_bvis, (size_t)std::max<long long>(1, s->nVisits)));
+      COSL_TRY(dev_alloc(s->stream, &s->d_bitems, std::max<size_t>(1, bitems.size())));
+      COSL_TRY(dev_alloc(s->stream, &s->d_btabs, std::max<size_t>(1, btabs.size())));
+      if (!bitems.empty()) {
+        COSL_CUDA(cudaMemcpyAsync(s->d_bitems, bitems.data(), sizeof(BaBlkItem) * bitems.size(), cudaMemcpyHostToDevice, s->stream));
+        COSL_CUDA(cudaMemcpyAsync(s->d_btabs, btabs.data(), sizeof(BaBlkDst) * btabs.size(), cudaMemcpyHostToDevice, s->stream));
+        COSL_CUDA(cudaMemsetAsync(d_vcnt, 0, sizeof(unsigned) * (nBB + 1), s->stream));
+        COSL_LAUNCH(ba_visits_build<true>, (unsigned)div_up(n - ncon, 128), 128, 0, s->stream, dv, nB, d_camBlock, d_camSlot,
+                    d_vcnt, d_voff, s->d_bvis, d_ovf);
+        COSL_CUDA(cudaStreamSynchronize(s->stream));  // bitems / btabs are host vectors of this scope
+      }
+      nEntries = poff[nBuckets];
+    }
+    COSL_CUDA(cudaFreeAsync(d_vcnt, s->stream));
+    COSL_CUDA(cudaFreeAsync(d_voff, s->stream));
+    COSL_CUDA(cudaFreeAsync(d_ovf, s->stream));
+    COSL_CUDA(cudaFreeAsync(d_camBlock, s->stream));
+    COSL_CUDA(cudaFreeAsync(d_camSlot, s->stream));
+    if (ba_timing())
+      std::fprintf(stderr, "[ba timing] camera-block visits: %d blocks, %lld visits (%.2f pair entries per visit), %d items\n",
+                   nB, s->nVisits, s->nVisits ? (double)poff[nBuckets] / (double)s->nVisits : 0.0, s->nBItems);
+  }
+  if (!s->useRows && !s->useBlk) {
     // pair lists: one bucket per camera pair (offsets counted on the device above); a work item is
     // a run of <= 512 entries of one bucket; the entries themselves are placed by ba_pairs_build
     nEntries = poff[nBuckets];
@@ -693,6 +833,7 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   COSL_CUDA(cudaFuncSetAttribute(ba_tile_solve, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  BA_TILE_SMEM));
   COSL_CUDA(cudaFuncSetAttribute(ba_schur_pairs_st, cudaFuncAttributeMaxDynamicSharedMemorySize, BA_ST_SMEM));
+  COSL_CUDA(cudaFuncSetAttribute(ba_schur_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, BA_BLK_SMEM));
   if (s->useRows && s->rowsSmem > 40 * 1024)
     COSL_CUDA(cudaFuncSetAttribute(ba_schur_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)s->rowsSmem));
@@ -840,6 +981,11 @@ int solve_trial(cosl_ba_solver* s, double mu, bool* solved) {
       if (s->Nc)
         COSL_LAUNCH(ba_schur_rows, s->mf * s->rowSplits, 32 * BA_ROWS_WARPS, s->rowsSmem, s->stream, s->d,
                     s->d_cptrFree, s->d_visit, s->d_rowDst, s->nSlots, s->d_Vinv, s->d_solIdx, s->rowSplits);
+    } else if (s->useBlk) {
+      if (s->n) COSL_LAUNCH(ba_vinv_kernel, (unsigned)div_up64(s->n, 256), 256, 0, s->stream, s->d, mu, s->d_Vinv);
+      if (s->nBItems)
+        COSL_LAUNCH(ba_schur_blk, div_up(s->nBItems, BA_BLK_WARPS), 32 * BA_BLK_WARPS, BA_BLK_SMEM, s->stream, s->d,
+                    s->d_bitems, s->nBItems, s->d_bvis, s->d_btabs, s->d_Vinv);
     } else if (s->nItems) {
       if (s->n) COSL_LAUNCH(ba_vinv_kernel, (unsigned)div_up64(s->n, 256), 256, 0, s->stream, s->d, mu, s->d_Vinv);
       // fp64 tensor-core variant (ba_schur_mma, DMMA m8n8k4 over smem-staged entry rows): correct and

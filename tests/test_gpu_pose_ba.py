@@ -192,6 +192,14 @@ def test_ba_schur_camera_row_kernel(api, orc, monkeypatch):
     monkeypatch.delenv("COSL_BA_SCHUR_MMA")
     assert i_mma[10] == i_pairs[10] and abs(i_mma[1] - i_pairs[1]) <= 1e-10 * i_pairs[1]
     assert np.abs(p_mma.X - p_pairs.X).max() < 1e-8
+    # the camera-block DMMA contraction (ba_schur_blk.cuh) and the scalar-gather pair kernel
+    for env in ("COSL_BA_SCHUR_BLK", "COSL_BA_SCHUR_SIMT"):
+        p_v = prob.copy()
+        monkeypatch.setenv(env, "1")
+        i_v = api.ba_solve(p_v, opt)
+        monkeypatch.delenv(env)
+        assert i_v[10] == i_pairs[10] and abs(i_v[1] - i_pairs[1]) <= 1e-10 * i_pairs[1], env
+        assert np.abs(p_v.X - p_pairs.X).max() < 1e-8, env
     assert i_rows[10] == i_pairs[10]
     assert abs(i_rows[1] - i_pairs[1]) <= 1e-10 * i_rows[1]
     assert np.abs(p_rows.X - p_pairs.X).max() < 1e-8
