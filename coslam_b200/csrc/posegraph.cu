@@ -20,6 +20,7 @@
 // across the CTA in shared memory; newR/newt hold (P_k, q_k) between the two passes.
 // Algorithmic bytes / node: 216 read (R, t, edge R, edge t, flag) + 96 written.
 #include <cmath>
+#include <mutex>
 #include <vector>
 
 #include "common.cuh"
@@ -336,15 +337,30 @@ extern "C" int cosl_posegraph_spread_chains(int nChains, const int* chainOff, co
   // one device slab: [R 9N | t 3N | eR 9N | et 3N | newR 9N | newt 3N] doubles, [anchor 2N | off C+1 | status] ints, flags
   const size_t nd = (size_t)36 * N, ni = (size_t)2 * N + nChains + 2;
   const size_t bytes = nd * 8 + ni * 4 + (size_t)N;
+  // stream-ordered allocation from the device's default pool: after the first call the slab comes out of
+  // the pool without a device synchronisation (cudaMalloc / cudaFree cost more than the kernel)
+  {
+    static std::mutex mu;
+    static bool kept[64] = {};
+    std::lock_guard<std::mutex> lk(mu);
+    if (device >= 0 && device < 64 && !kept[device]) {
+      kept[device] = true;
+      cudaMemPool_t pool;
+      if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+      }
+    }
+  }
+  cudaStream_t s = cudaStreamPerThread;
   char* slab = nullptr;
-  COSL_CUDA(cudaMalloc(&slab, bytes));
+  COSL_CUDA(cudaMallocAsync(&slab, bytes, s));
   double* dR = reinterpret_cast<double*>(slab);
   double *dt = dR + 9 * (size_t)N, *deR = dt + 3 * (size_t)N, *det = deR + 9 * (size_t)N;
   double *dnR = det + 3 * (size_t)N, *dnt = dnR + 9 * (size_t)N;
   int* dAnchor = reinterpret_cast<int*>(dnt + 3 * (size_t)N);
   int *dOff = dAnchor + 2 * (size_t)N, *dStatus = dOff + nChains + 1;
   unsigned char* dFixed = reinterpret_cast<unsigned char*>(dStatus + 1);
-  cudaStream_t s = 0;
   int rc = COSL_OK;
   auto fail = [&](cudaError_t e, const char* what) {
     rc = set_error(COSL_E_CUDA, "cosl_posegraph_spread_chains: %s: %s", what, cudaGetErrorString(e));
@@ -370,7 +386,7 @@ extern "C" int cosl_posegraph_spread_chains(int nChains, const int* chainOff, co
   if (rc == COSL_OK && (e = cudaMemcpyAsync(newt, dnt, 24 * (size_t)N, cudaMemcpyDeviceToHost, s)) != cudaSuccess) fail(e, "D2H");
   if (rc == COSL_OK && (e = cudaMemcpyAsync(&status, dStatus, 4, cudaMemcpyDeviceToHost, s)) != cudaSuccess) fail(e, "D2H");
   if (rc == COSL_OK && (e = cudaStreamSynchronize(s)) != cudaSuccess) fail(e, "sync");
-  cudaFree(slab);
+  cudaFreeAsync(slab, s);
   if (rc != COSL_OK) return rc;
   if (status != 0)
     return set_error(COSL_E_INVALID, "cosl_posegraph_spread_chains: chain %d has no fixed node (rank-deficient system)",
