@@ -6,11 +6,14 @@
  * import it.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
  * legs use it.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or fixtures for these paths, its
- * KLT exists only as Cg shaders and its BA arithmetic lives in LibVisualSLAM/sba-1.6, which is not
- * in the tree.  The oracle is therefore pinned only against (i) closed-form
- * known-answer cases and (ii) independent cross-checks (scipy / numeric differentiation), see
- * tests/test_oracle_*.py.
+ * PINNING: pose (orc_pose_intracam) and pose-graph spreading (orc_posegraph_spread) are PINNED to the
+ * reference's own code: slam/SL_IntraCamPose.cpp and slam/SL_GlobalPoseEstimation.cpp are compiled
+ * unmodified into oracle/_ref/ (Makefile target `ref`) and compared live and through the vectors
+ * tests/golden/pose_ref.npz / posegraph_ref.npz they produced (tests/test_pose_ref.py,
+ * tests/test_posegraph.py).  KLT and BA are PARITY UNPINNED: the reference's KLT exists only as Cg
+ * shaders and its BA arithmetic lives in LibVisualSLAM/sba-1.6, which is not in the tree
+ * (SURVEY.md 8c); they are held by closed-form known-answer cases and independent cross-checks
+ * (scipy / numpy restatements / numeric differentiation), see tests/test_oracle_*.py.
  *
  * Struct layouts are shared with include/coslam_b200.h so the same ctypes structures drive both.
  */
