@@ -498,32 +498,35 @@ __device__ __forceinline__ void tile_potrf2(double* __restrict__ sT, double* __r
           sM[pb * 64 + q * 8 + cc] = m[q];
         }
       }
-      // trailing lower triangle right of the NEXT panel: rows ti + 16a, columns tj + 12b
-      const int ti = u & 15, tj = u >> 4;
-      if (c0 + 16 < 64) {
-        double xi[4][8];
-#pragma unroll
-        for (int aa = 0; aa < 4; ++aa)
-#pragma unroll
-          for (int q = 0; q < 8; ++q) xi[aa][q] = sT[(c0 + q) * BA_LDS + ti + 16 * aa];
-#pragma unroll
-        for (int b = 0; b < 6; ++b) {
-          const int j = tj + 12 * b;
-          if (j >= c0 + 16 && j < 64) {
-            double xj[8];
-#pragma unroll
-            for (int q = 0; q < 8; ++q) xj[q] = sT[(c0 + q) * BA_LDS + j];
-#pragma unroll
-            for (int aa = 0; aa < 4; ++aa) {
-              const int i = ti + 16 * aa;
-              if (i >= j) {
-                double s = sT[j * BA_LDS + i];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) s = __fma_rn(-xi[aa][q], xj[q], s);
-                sT[j * BA_LDS + i] = s;
-              }
-            }
+      // trailing lower triangle right of the NEXT panel (rows / columns >= c0 + 16), in 8x8 blocks on the
+      // fp64 tensor cores: C(R0.., C0..) -= X(R0.., c0..c0+7) X(C0.., c0..c0+7)^T = two DMMA.8x8x4 per block.
+      // (The scalar version -- a chain of 8 dependent DMULs/DFMAs per element, ~24 elements per thread one
+      // after the other -- made the UPDATE warps, not the pivot chain, the slow side of a panel.)
+      // Diagonal blocks are computed in full: their upper halves are never read as factor entries.
+      {
+        const int uw = (tid >> 5) - 2;              // update warp 0..5
+        const int lane = tid & 31, g = lane >> 2, kq = lane & 3;
+        const int t0 = pb + 2;                      // first 8-row block of the trailing part
+        const int nt = 8 - t0;                      // blocks per side
+        const int ntile = nt * (nt + 1) / 2;
+        const double* xk0 = sT + (c0 + kq) * BA_LDS;       // X(., c0 + kq)
+        const double* xk1 = sT + (c0 + 4 + kq) * BA_LDS;   // X(., c0 + 4 + kq)
+        for (int t = uw; t < ntile; t += 6) {
+          // t -> (bi >= bj) in the lower triangle of an nt x nt block grid, row by row
+          int bi = 0, rem = t;
+          while (rem > bi) {
+            rem -= bi + 1;
+            ++bi;
           }
+          const int R0 = 8 * (t0 + bi), C0 = 8 * (t0 + rem);
+          double* cp = sT + (C0 + 2 * kq) * BA_LDS + R0 + g;
+          double c0v = cp[0], c1v = cp[BA_LDS];
+          const double a0 = -xk0[R0 + g], a1 = -xk1[R0 + g];
+          const double b0 = xk0[C0 + g], b1 = xk1[C0 + g];
+          dmma884(c0v, c1v, a0, b0);
+          dmma884(c0v, c1v, a1, b1);
+          cp[0] = c0v;
+          cp[BA_LDS] = c1v;
         }
       }
     }
