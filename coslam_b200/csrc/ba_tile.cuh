@@ -63,18 +63,6 @@ __device__ __forceinline__ void red_release_add(int* p, int v) {
   asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-// 1/sqrt(d): single-precision seed + two Newton steps in fp64 (full double accuracy inside the
-// float range, which Gauss-Newton pivots always are); the library rsqrt() is ~3x longer and this
-// sits on the pivot-to-pivot critical path of the whole solve.
-__device__ __forceinline__ double ba_rsqrt_fast(double d) {
-  if (d < 1e-30 || d > 1e30) return rsqrt(d);
-  double y = (double)rsqrtf((float)d);
-  const double h = 0.5 * d;
-  y = __fma_rn(y, __fma_rn(-h * y, y, 0.5), y);
-  y = __fma_rn(y, __fma_rn(-h * y, y, 0.5), y);
-  return y;
-}
-
 // global column-major 64x64 tile -> shared [col][row] with leading dimension LD; all 8 loads of a
 // thread are in flight before the first shared store (one L2 round trip per tile)
 template <int LD>
@@ -155,178 +143,6 @@ __device__ __forceinline__ void tile_acc_rc(int tid, int mi, int ni, int e, int&
   const int lane = tid & 31, w = tid >> 5;
   r = (w & 3) * 16 + 8 * mi + (lane >> 2);
   c = (w >> 2) * 32 + 8 * ni + 2 * (lane & 3) + e;
-}
-
-// ---------------------------------------------------------------------------------------------
-// POTRF: factor the diagonal tile staged in sT (ld 65, lower part used, padding rows/cols made
-// identity), 8-column panels: the 64 row threads factor the 8x8 diagonal block redundantly in
-// registers and solve their own row of the panel (no communication inside a panel), then all 256
-// threads apply the rank-8 update to the trailing lower triangle.  2 barriers per 8 pivots.
-// ---------------------------------------------------------------------------------------------
-constexpr int BA_LDP = 65;
-
-__device__ __forceinline__ void tile_potrf(double* __restrict__ sT, int bs, int tid, int* s_fail,
-                                           double* __restrict__ sInv) {
-  for (int c0 = 0; c0 < bs; c0 += 8) {
-    if (tid < 64) {
-      const int r = tid;
-      double D[8][8], inv[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-#pragma unroll
-        for (int i = j; i < 8; ++i) D[i][j] = sT[(c0 + j) * BA_LDP + c0 + i];
-      bool bad = false;
-#pragma unroll
-      for (int p = 0; p < 8; ++p) {
-        double d = D[p][p];
-        if (!(d > 0) || !isfinite(d)) {
-          bad = true;
-          d = 1.0;
-        }
-        const double rs = ba_rsqrt_fast(d);
-        inv[p] = rs;
-        D[p][p] = d * rs;
-#pragma unroll
-        for (int i = p + 1; i < 8; ++i) D[i][p] *= rs;
-#pragma unroll
-        for (int j = p + 1; j < 8; ++j)
-#pragma unroll
-          for (int i = j; i < 8; ++i) D[i][j] = __fma_rn(-D[i][p], D[j][p], D[i][j]);
-      }
-      if (r == 0) {
-        if (bad) *s_fail = 1;
-#pragma unroll
-        for (int p = 0; p < 8; ++p) sInv[c0 + p] = inv[p];  // 1 / L(c0+p, c0+p)
-      }
-      if (r >= c0 + 8) {
-        double x[8];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) x[q] = sT[(c0 + q) * BA_LDP + r];
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          double s = x[q];
-#pragma unroll
-          for (int p = 0; p < q; ++p) s = __fma_rn(-x[p], D[q][p], s);
-          x[q] = s * inv[q];
-        }
-#pragma unroll
-        for (int q = 0; q < 8; ++q) sT[(c0 + q) * BA_LDP + r] = x[q];
-      } else if (r >= c0) {
-        const int a = r - c0;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          double v = 0.0;
-#pragma unroll
-          for (int aa = 0; aa < 8; ++aa)
-            if (aa == a && q <= aa) v = D[aa][q];
-          sT[(c0 + q) * BA_LDP + r] = v;
-        }
-      }
-    }
-    __syncthreads();
-    if (c0 + 8 < 64) {
-      // trailing update of the lower triangle right of the panel
-      const int ti = tid & 15, tj = tid >> 4;
-      double xi[4][8], xj[4][8];
-      bool any = false;
-#pragma unroll
-      for (int b = 0; b < 4; ++b) any = any || (tj + 16 * b >= c0 + 8);
-      if (any) {
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int q = 0; q < 8; ++q) xi[a][q] = sT[(c0 + q) * BA_LDP + ti + 16 * a];
-#pragma unroll
-        for (int b = 0; b < 4; ++b)
-#pragma unroll
-          for (int q = 0; q < 8; ++q) xj[b][q] = sT[(c0 + q) * BA_LDP + tj + 16 * b];
-#pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            const int i = ti + 16 * a, j = tj + 16 * b;
-            if (j >= c0 + 8 && i >= j) {
-              double s = sT[j * BA_LDP + i];
-#pragma unroll
-              for (int q = 0; q < 8; ++q) s = __fma_rn(-xi[a][q], xj[b][q], s);
-              sT[j * BA_LDP + i] = s;
-            }
-          }
-      }
-    }
-    __syncthreads();
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Inverse of the lower-triangular factor in sT (ld 65) -> sM (ld 65, full tile, zeros above the
-// diagonal), by recursive doubling: four 16x16 diagonal blocks by forward substitution (one thread
-// per column), then M21 = -M22 (L21 M11) on the 32- and the 64-level; sW is scratch (ld 65).
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tile_trinv(const double* __restrict__ sT, double* __restrict__ sM,
-                                           double* __restrict__ sW, const double* __restrict__ sInv,
-                                           int tid) {
-  for (int t = tid; t < 64 * 64; t += BA_NTHREADS) sM[(t >> 6) * BA_LDP + (t & 63)] = 0.0;
-  __syncthreads();
-  if (tid < 64) {
-    const int b0 = (tid >> 4) * 16, c = tid & 15;
-    double x[16];
-#pragma unroll
-    for (int r = 0; r < 16; ++r) {
-      double s = (r == c) ? 1.0 : 0.0;
-#pragma unroll
-      for (int p = 0; p < r; ++p) s = __fma_rn(-sT[(b0 + p) * BA_LDP + b0 + r], x[p], s);
-      x[r] = s * sInv[b0 + r];
-    }
-#pragma unroll
-    for (int r = 0; r < 16; ++r) sM[(b0 + c) * BA_LDP + b0 + r] = (r >= c) ? x[r] : 0.0;
-  }
-  __syncthreads();
-#pragma unroll 1
-  for (int h = 16; h <= 32; h <<= 1) {
-    // diagonal blocks of size 2h at offsets o: 11 = [o, o+h), 22 = [o+h, o+2h)
-    const int nblk = 64 / (2 * h);
-    // W = L21 * M11   (h x h per block)
-    for (int t = tid; t < nblk * h * h; t += BA_NTHREADS) {
-      const int blk = t / (h * h), e = t - blk * h * h, c = e / h, r = e - c * h;
-      const int o = blk * 2 * h;
-      double s = 0;
-      for (int p = c; p < h; ++p) s = __fma_rn(sT[(o + p) * BA_LDP + o + h + r], sM[(o + c) * BA_LDP + o + p], s);
-      sW[(o + c) * BA_LDP + o + h + r] = s;
-    }
-    __syncthreads();
-    // M21 = -M22 * W
-    for (int t = tid; t < nblk * h * h; t += BA_NTHREADS) {
-      const int blk = t / (h * h), e = t - blk * h * h, c = e / h, r = e - c * h;
-      const int o = blk * 2 * h;
-      double s = 0;
-      for (int p = 0; p <= r; ++p) s = __fma_rn(sM[(o + h + p) * BA_LDP + o + h + r], sW[(o + c) * BA_LDP + o + h + p], s);
-      sM[(o + c) * BA_LDP + o + h + r] = -s;
-    }
-    __syncthreads();
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// out[c] (-)= sum_r G[r, c] * v[r] for one global column-major tile G: 4 threads per column.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double tile_colT_dot(const double* __restrict__ G, const double* __restrict__ sv,
-                                                int tid) {
-  const int c = tid >> 2, q = tid & 3;
-  const double2* col = reinterpret_cast<const double2*>(G + c * BA_TB + 16 * q);
-  double2 v[8];
-#pragma unroll
-  for (int u = 0; u < 8; ++u) v[u] = __ldcg(col + u);
-  double s0 = 0, s1 = 0;
-#pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    s0 = __fma_rn(v[u].x, sv[16 * q + 2 * u], s0);
-    s1 = __fma_rn(v[u].y, sv[16 * q + 2 * u + 1], s1);
-  }
-  double s = s0 + s1;
-  s += __shfl_xor_sync(0xffffffffu, s, 1);
-  s += __shfl_xor_sync(0xffffffffu, s, 2);
-  return s;
 }
 
 // x = L^-T v for 64 threads (warps 0-1; named barrier 2): blocks last to first, right-looking --
@@ -564,29 +380,6 @@ __device__ __forceinline__ void tile_trsm2(double* __restrict__ sA, const double
   }
 }
 
-// x = L^-T v, one warp (call with the whole warp 0): sL staged tile (lower), sM the M_b, sv in/out.
-__device__ __forceinline__ void tile_bwd2(const double* __restrict__ sL, const double* __restrict__ sM,
-                                          double* __restrict__ sv, int nbk, int lane) {
-  const int q = lane >> 2, part = lane & 3;  // output q of the block, 4-way split of the dot
-  for (int b = nbk - 1; b >= 0; --b) {
-    // t_q = v(8b + q) - sum_{p >= 8b + 8} L(p, 8b + q) x(p)
-    double s = 0;
-    for (int p = 8 * b + 8 + part; p < 8 * nbk; p += 4) s = __fma_rn(sL[(8 * b + q) * BA_LDS + p], sv[p], s);
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    const double tq = sv[8 * b + q] - s;
-    // x_q = sum_{q' >= q} M(q', q) t_q'
-    double xq = 0;
-#pragma unroll
-    for (int qq = 0; qq < 8; ++qq) {
-      const double tv = __shfl_sync(0xffffffffu, tq, 4 * qq);
-      xq = __fma_rn(sM[b * 64 + qq * 8 + q], tv, xq);  // M is lower: entries with qq < q are zero
-    }
-    __syncwarp();
-    if (part == 0) sv[8 * b + q] = xq;
-    __syncwarp();
-  }
-}
 
 // UPDATE task body: C -= A B^T (first update of a scratch tile overwrites), diagonal tiles also
 // b_i -= A y_k.  staged: the operands (and y in sY) are already in shared memory.
