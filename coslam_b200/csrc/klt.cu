@@ -609,7 +609,8 @@ int run_detector(cosl_klt* g, int mode, int nPresentExt) {
   COSL_LAUNCH(klt_select_refill, g->C, 1024, g->smemKeys * sizeof(unsigned long long), g->stream,
               g->d_cand, g->candCap, g->plCap, g->d_counters, g->d_feat, g->d_dst,
               g->foldAdvance ? g->d_src : (float4*)nullptr, g->d_present,
-              nPresentExt, g->F, g->W, g->H, mode, g->cfg.trackWithGain ? 1 : 0, g->smemKeys);
+              nPresentExt, g->F, g->W, g->H, mode, g->cfg.trackWithGain ? 1 : 0, g->smemKeys,
+              (g->cfg.compat & COSL_KLT_COMPAT_HISTOPYR) ? 1 : 0);
   g->timer.end(g->stream);
   g->advanceDone = g->foldAdvance;
   COSL_CUDA(cudaGetLastError());

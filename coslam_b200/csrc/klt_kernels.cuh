@@ -538,12 +538,32 @@ __device__ __forceinline__ void bitonic_sort(unsigned long long* k, int n2) {
   __syncthreads();
 }
 
+// Morton code with x in the even bits: the extraction order of the reference's HistoPyramid traversal
+// (klt_detector_traverse_histpyr.cg:33-50 visits the children (x,y), (x+1,y), (x,y+1), (x+1,y+1) in that
+// order at every level; the 2x2 taps of the base level have the same order, v3d_gpuklt.cpp:42-57)
+__device__ __forceinline__ unsigned klt_part1by1(unsigned v) {
+  v &= 0xffffu;
+  v = (v | (v << 8)) & 0x00ff00ffu;
+  v = (v | (v << 4)) & 0x0f0f0f0fu;
+  v = (v | (v << 2)) & 0x33333333u;
+  v = (v | (v << 1)) & 0x55555555u;
+  return v;
+}
+__device__ __forceinline__ unsigned klt_compact1by1(unsigned v) {
+  v &= 0x55555555u;
+  v = (v | (v >> 1)) & 0x33333333u;
+  v = (v | (v >> 2)) & 0x0f0f0f0fu;
+  v = (v | (v >> 4)) & 0x00ff00ffu;
+  v = (v | (v >> 8)) & 0x0000ffffu;
+  return v;
+}
+
 __global__ void __launch_bounds__(1024)
 klt_select_refill(unsigned long long* __restrict__ cand, int candCap, int plCap,
                   int* __restrict__ counters, cosl_klt_feature* __restrict__ dest,
                   float4* __restrict__ dstbuf, float4* __restrict__ alsoSrc,
                   const float4* __restrict__ present, int nPresentExt,
-                  int F, int W, int H, int mode, int withGain, int smemKeys) {
+                  int F, int W, int H, int mode, int withGain, int smemKeys, int histo) {
   extern __shared__ unsigned long long s_keys[];
   __shared__ int s_scan[1024];
   __shared__ int s_base;
@@ -563,13 +583,56 @@ klt_select_refill(unsigned long long* __restrict__ cand, int candCap, int plCap,
     for (int i = nCand + threadIdx.x; i < n2; i += blockDim.x) keys[i] = ~0ull;
   }
   __syncthreads();
-  if (nCand > 1) bitonic_sort(keys, n2);
+  int nCandEff = nCand;
+  bool wantSort = true;
+  if (histo) {
+    // COSL_KLT_COMPAT_HISTOPYR: the reference's candidate list.  (1) the discriminator pass covers W/2 x H/2
+    // texels of 2x2 pixels (v3d_gpuklt.cpp:519-523): a last odd row / column is never seen; (2) the first
+    // plCap candidates in HistoPyramid extraction order (= Morton order) are read back (:752-757);
+    // (3) only if they exceed the free slots they are ordered by cornerness (:759-768), else they fill
+    // the slots in extraction order.
+    __shared__ int s_nvalid;
+    const unsigned Wc = 2u * (unsigned)(W / 2), Hc = 2u * (unsigned)(H / 2);
+    if (threadIdx.x == 0) s_nvalid = 0;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+      unsigned long long k = keys[i];
+      if (k != ~0ull) {
+        const unsigned x = (unsigned)(k & 0xffff), y = (unsigned)((k >> 16) & 0xffff);
+        if (x >= Wc || y >= Hc)
+          k = ~0ull;
+        else
+          k = ((unsigned long long)(klt_part1by1(x) | (klt_part1by1(y) << 1)) << 32) | (k >> 32);
+      }
+      keys[i] = k;
+    }
+    __syncthreads();
+    if (nCand > 1) bitonic_sort(keys, n2);
+    for (int i = threadIdx.x; i < n2; i += blockDim.x)
+      if (keys[i] != ~0ull && (i + 1 == n2 || keys[i + 1] == ~0ull)) s_nvalid = i + 1;
+    __syncthreads();
+    nCandEff = min(s_nvalid, plCap);
+    const int freeSlots = (mode == 0) ? F - nPresentExt : F - cnt[0];
+    wantSort = nCandEff > freeSlots;
+    for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+      unsigned long long k = keys[i];
+      if (i < nCandEff) {
+        const unsigned mc = (unsigned)(k >> 32);
+        const unsigned x = klt_compact1by1(mc), y = klt_compact1by1(mc >> 1);
+        k = ((k & 0xffffffffull) << 32) | ((unsigned long long)y << 16) | x;
+      } else {
+        k = ~0ull;
+      }
+      keys[i] = k;
+    }
+    __syncthreads();
+  }
+  if (nCand > 1 && wantSort) bitonic_sort(keys, n2);
   const float Wf = (float)W, Hf = (float)H;
   cosl_klt_feature* d = dest + (size_t)cam * F;
   float4* pb = dstbuf + (size_t)cam * F;
   float4* ps = alsoSrc ? alsoSrc + (size_t)cam * F : nullptr;  // advanceFrame copy folded in
   if (mode == 0) {
-    const int nDet = max(0, min(min(nCand, plCap), F - nPresentExt));
+    const int nDet = max(0, min(min(nCandEff, plCap), F - nPresentExt));
     for (int i = threadIdx.x; i < F; i += blockDim.x) {
       cosl_klt_feature f;
       float4 p;
@@ -608,7 +671,7 @@ klt_select_refill(unsigned long long* __restrict__ cand, int candCap, int plCap,
     }
   } else {
     const int nPresent = cnt[0];
-    const int nNew = max(0, min(min(nCand, plCap), F - nPresent));
+    const int nNew = max(0, min(min(nCandEff, plCap), F - nPresent));
     if (threadIdx.x == 0) s_base = 0;
     __syncthreads();
     // dead slots in increasing index get corner k = rank among dead slots

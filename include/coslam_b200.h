@@ -65,12 +65,22 @@ typedef struct cosl_klt_config {
 /* bit 1 (COSL_KLT_PASS_KERNELS, diagnostic): run the gain tracker as one kernel launch per
  * (level, iteration) pass like the reference's draw calls, instead of the single persistent
  * kernel; results are bit-identical, only slower. */
-enum { COSL_KLT_COMPAT_ITER5 = 1, COSL_KLT_PASS_KERNELS = 2, COSL_KLT_COMPAT_FEED_STRIDE2 = 4 };
+enum { COSL_KLT_COMPAT_ITER5 = 1, COSL_KLT_PASS_KERNELS = 2, COSL_KLT_COMPAT_FEED_STRIDE2 = 4,
+       COSL_KLT_COMPAT_HISTOPYR = 8 };
 /* bit 2 (COSL_KLT_COMPAT_FEED_STRIDE2, parity runs): feedExternFeaturePoints' proximity test reads
  * the fed points as featPts[2k], featPts[2k+1] although the array holds 3 floats per point
  * (v3d_gpuklt.cpp:826-827 vs :841-842).  The default uses stride 3 in both loops (the evident
  * intent); with this bit the kill test reproduces the reference's stride-2 reads, so the same
- * tracks die and the same trackIds come back as from the reference for the same input. */
+ * tracks die and the same trackIds come back as from the reference for the same input.
+ * bit 3 (COSL_KLT_COMPAT_HISTOPYR, parity runs): the reference's candidate list instead of "all
+ * non-max survivors, strongest first": the corners are read back in HistoPyramid extraction order
+ * (Morton order of the pixel, x in the even bits; klt_detector_traverse_histpyr.cg:33-50) and
+ * TRUNCATED to pointListWidth*pointListHeight entries before anything is ranked
+ * (v3d_gpuklt.cpp:660-661, 755-757), a last odd image row / column is never examined (:519-523),
+ * and the list is ordered by cornerness only when it exceeds the free slots (:662-665, 761-768),
+ * otherwise slots are filled in extraction order.  With the bit set the SET of new corners equals
+ * the reference's; when the list was cut by cornerness their ORDER is strongest-first, whereas the
+ * reference's std::nth_element leaves an implementation-defined order. */
 
 /* Mirrors V3D_GPU::KLT_TrackedFeature (v3d_gpuklt.h:166-176): 20 bytes. */
 typedef struct cosl_klt_feature {

@@ -486,6 +486,42 @@ void detect_corners(orc_klt* h, const Level& L0, int nPresent, const float* pres
   h->lastNumCand = (int)cands.size();
 }
 
+// COSL_KLT_COMPAT_HISTOPYR: the candidate list the reference actually reads back.
+//  * the discriminator pass renders W/2 x H/2 texels of 2x2 pixels (v3d_gpuklt.cpp:519-523): a last odd
+//    row / column never becomes a candidate;
+//  * extractCorners walks the HistoPyramid top-down visiting the children (x,y), (x+1,y), (x,y+1),
+//    (x+1,y+1) in that order (klt_detector_traverse_histpyr.cg:33-50; base-level taps in the same
+//    order, v3d_gpuklt.cpp:42-57): candidate k of the list is the k-th pixel in MORTON order;
+//  * only the first pointListWidth*pointListHeight entries are read back (:660-661, :755-757);
+//  * they are ranked by cornerness only if they exceed the free slots (:662-665, :761-768) -- the
+//    reference's std::nth_element keeps the same SET and leaves the order unspecified, the oracle
+//    (and the CUDA path) order that case strongest-first; otherwise extraction order is kept.
+unsigned part1by1(unsigned v) {
+  v &= 0xffffu;
+  v = (v | (v << 8)) & 0x00ff00ffu;
+  v = (v | (v << 4)) & 0x0f0f0f0fu;
+  v = (v | (v << 2)) & 0x33333333u;
+  v = (v | (v << 1)) & 0x55555555u;
+  return v;
+}
+void histopyr_list(const orc_klt* h, std::vector<Cand>& cands, int freeSlots) {
+  if (!(h->cfg.compat & COSL_KLT_COMPAT_HISTOPYR)) return;
+  const int Wc = 2 * (h->W / 2), Hc = 2 * (h->H / 2);
+  std::vector<Cand> in;
+  for (const Cand& c : cands)
+    if (c.px < Wc && c.py < Hc) in.push_back(c);
+  auto morton = [](const Cand& c) { return part1by1((unsigned)c.px) | (part1by1((unsigned)c.py) << 1); };
+  std::sort(in.begin(), in.end(), [&](const Cand& a, const Cand& b) { return morton(a) < morton(b); });
+  if ((int)in.size() > h->plCap) in.resize(h->plCap);
+  if ((int)in.size() > freeSlots)
+    std::sort(in.begin(), in.end(), [](const Cand& a, const Cand& b) {
+      if (a.c != b.c) return a.c > b.c;
+      if (a.py != b.py) return a.py < b.py;
+      return a.px < b.px;
+    });
+  cands.swap(in);
+}
+
 void run_tracker(orc_klt* h, float* out) {
   const std::vector<Level>& P0 = h->pyr[1 - h->cur];
   const std::vector<Level>& P1 = h->pyr[h->cur];
@@ -574,6 +610,7 @@ int orc_klt_detect(orc_klt* h, const uint8_t* img, size_t pitch, int nPresent,
   build_pyramid(h, img, pitch, h->pyr[h->cur]);
   std::vector<Cand> cands;
   detect_corners(h, h->pyr[h->cur][0], nPresent, present3, cands);
+  histopyr_list(h, cands, F - nPresent);
   int nDet = std::min((int)cands.size(), h->plCap);
   nDet = std::min(nDet, F - nPresent);
   for (int i = 0; i < F; ++i) {
@@ -657,6 +694,7 @@ int orc_klt_redetect(orc_klt* h, const uint8_t* img, size_t pitch, cosl_klt_feat
   }
   std::vector<Cand> cands;
   detect_corners(h, h->pyr[h->cur][0], F, present.data(), cands);
+  histopyr_list(h, cands, F - nPresent);
   int nNew = std::min((int)cands.size(), h->plCap);
   nNew = std::min(nNew, F - nPresent);
   int k = 0;

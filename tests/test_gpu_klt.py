@@ -154,6 +154,33 @@ def test_pipelined_submit_collect_equals_next(api):
         b.close()
 
 
+@pytest.mark.parametrize("W,H,fw,fh,plw,plh", [(640, 480, 16, 16, 12, 12), (327, 241, 8, 8, 6, 6), (640, 480, 8, 8, 16, 16)])
+def test_histopyr_compat_matches_oracle(api, orc, W, H, fw, fh, plw, plh):
+    """COSL_KLT_COMPAT_HISTOPYR: the reference's candidate list (Morton extraction order, truncation to
+    the point list before ranking, odd last row / column never examined) -- slot-for-slot against the
+    oracle, whose list is checked against an independent numpy statement on the CPU
+    (tests/test_oracle_klt.py).  Cases: point list smaller than the slots (extraction order kept),
+    odd image size, point list larger than the slots (ranked by cornerness)."""
+    s = seq(H, W, 23, n=3)
+    cfg = live_cfg(min_corner=600.0)
+    cfg.compat |= 8
+    g = api.KltTracker(cfg, W, H, 4, fw, fh, plw, plh)
+    o = orc.OracleKlt(cfg, W, H, 4, fw, fh, plw, plh)
+    fg, ng = g.first(s.frames[0])
+    fo, no = o.first(s.frames[0])
+    assert ng == no == min(fw * fh, plw * plh)
+    assert np.array_equal(fg["pos"].view(np.uint32), fo["pos"].view(np.uint32))
+    # not what the default mode selects
+    d = api.KltTracker(live_cfg(min_corner=600.0), W, H, 4, fw, fh, plw, plh)
+    fd, _ = d.first(s.frames[0])
+    assert not np.array_equal(fd["pos"].view(np.uint32), fg["pos"].view(np.uint32))
+    for k in (1, 2):
+        fg, ng = g.next(s.frames[k])
+        fo, no = o.next(s.frames[k])
+        st = compare_features(fo, fg, W, H)
+        assert st["flips"] == 0 and ng == no
+
+
 def test_full_size_known_answer_flow(api):
     """BASELINE c3 shape (4 x 1280x720, F=2000): tracked features follow the known synthetic flow."""
     W, H, F = 1280, 720, (50, 40)

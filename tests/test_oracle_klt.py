@@ -178,3 +178,54 @@ def test_feed_stride2_compat_bit_reproduces_the_reference_reads(orc):
         assert nfed == 2
         expect = sorted(list(dead_before) + ([victim] if bit == 0 else []))[:2]
         assert list(ids[:2]) == expect, (bit, ids, expect)
+
+
+def _morton(px, py):
+    def part(v):
+        v = v.astype(np.uint32) & 0xffff
+        v = (v | (v << 8)) & 0x00ff00ff
+        v = (v | (v << 4)) & 0x0f0f0f0f
+        v = (v | (v << 2)) & 0x33333333
+        v = (v | (v << 1)) & 0x55555555
+        return v
+    return part(px) | (part(py) << 1)
+
+
+def test_histopyr_compat_reproduces_the_reference_candidate_list(orc):
+    """COSL_KLT_COMPAT_HISTOPYR (v3d_gpuklt.cpp:660-665, 755-768 + klt_detector_traverse_histpyr.cg): the
+    corners are read back in HistoPyramid extraction order = Morton order of the pixel (x in the even
+    bits), truncated to pointListWidth*pointListHeight BEFORE ranking, ranked only if they exceed the
+    free slots, and an odd last row / column is never examined.  Checked against an independent numpy
+    statement built from the full candidate set of a default-mode tracker."""
+    W, H = 327, 241  # odd: the last column / row must disappear
+    s = seq(H, W, 31, n=1)
+    full = orc.OracleKlt(live_cfg(min_corner=800.0), W, H, 4, 40, 40, 64, 64)
+    f, n = full.first(s.frames[0])
+    allc = f[f["status"] >= 0]
+    assert 100 < len(allc) < 1600  # every candidate fits: this is the complete set, strongest first
+    px = np.floor(allc["pos"][:, 0] * W).astype(np.int64)
+    py = np.floor(allc["pos"][:, 1] * H).astype(np.int64)
+    keep = (px < 2 * (W // 2)) & (py < 2 * (H // 2))
+    px, py = px[keep], py[keep]
+    order = np.argsort(_morton(px, py), kind="stable")
+    # (a) 6x6 point list, 8x8 slots: the first 36 in Morton order fill the slots IN THAT ORDER
+    cfg = live_cfg(min_corner=800.0)
+    cfg.compat |= 8
+    k = orc.OracleKlt(cfg, W, H, 4, 8, 8, 6, 6)
+    g, ng = k.first(s.frames[0])
+    assert ng == 36
+    want = order[:36]
+    got_px = np.floor(g["pos"][:36, 0] * W).astype(np.int64)
+    got_py = np.floor(g["pos"][:36, 1] * H).astype(np.int64)
+    assert np.array_equal(got_px, px[want]) and np.array_equal(got_py, py[want])
+    # (b) 8x8 point list, 5x5 slots: the strongest 25 of the first 64 in Morton order
+    k2 = orc.OracleKlt(cfg, W, H, 4, 5, 5, 8, 8)
+    g2, n2 = k2.first(s.frames[0])
+    assert n2 == 25
+    sub = np.sort(order[:64])[:25]  # allc is strongest-first, so the smallest indices are the strongest
+    got = set(zip(np.floor(g2["pos"][:, 0] * W).astype(int), np.floor(g2["pos"][:, 1] * H).astype(int)))
+    assert got == set(zip(px[sub], py[sub]))
+    # the default mode would have picked the globally strongest instead
+    d = orc.OracleKlt(live_cfg(min_corner=800.0), W, H, 4, 5, 5, 8, 8)
+    g3, _ = d.first(s.frames[0])
+    assert set(zip(np.floor(g3["pos"][:, 0] * W).astype(int), np.floor(g3["pos"][:, 1] * H).astype(int))) != got
