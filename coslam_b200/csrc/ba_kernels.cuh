@@ -225,7 +225,7 @@ ba_residual_kernel(BaDev d, const double* __restrict__ pa, const double* __restr
 // Linearisation, point-major: per observation e, A (2x6), B (2x3) (scaled by sqrt(w)); stores
 // W_ij = A^T B; collapses V_i = sum B^T B and eb_i = sum B^T e per point with segmented shuffles.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 ba_linearize_points(BaDev d, const double* __restrict__ pa, const double* __restrict__ pb) {
   const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
