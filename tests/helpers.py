@@ -15,10 +15,13 @@ def seq(h, w, seed, n=4, **kw):
     return synth.ImageSequence(h, w, seed, n_frames=n, **kw)
 
 
-def compare_features(fa, fb, W, H, pos_tol_px=2e-3, gain_tol=2e-3, max_flip_frac=0.01):
+def compare_features(fa, fb, W, H, pos_tol_px=2e-3, gain_tol=1e-3, max_flip_frac=0.002):
     """Compare two cosl_klt_feature tables (oracle vs CUDA).  Returns dict of statistics and raises
     on violation.  Status flips are allowed for a small fraction of slots (threshold decisions on
-    fp32 sums that are reduced in a different order on the GPU)."""
+    fp32 sums that are reduced in a different order on the GPU).  Measured on B200: 0 flips and
+    max |dpos| <= 3.5e-4 px with the gain tracker, 1.2e-3 px with the 2x2 tracker (328x250 case); the
+    defaults leave a factor ~2 on the position and
+    at most max(1, 0.2 %) of the slots for a threshold decision."""
     assert len(fa) == len(fb)
     sa, sb = fa["status"], fb["status"]
     flips = sa != sb

@@ -99,7 +99,7 @@ def test_track_only_cadence_and_feed(api, orc, compat_bit):
     o.advance()
     fg, ng = g.track(s.frames[2])
     fo, no = o.track(s.frames[2])
-    compare_features(fo, fg, W, H, max_flip_frac=0.02)
+    compare_features(fo, fg, W, H, max_flip_frac=0.005)
 
 
 def test_group_matches_single(api):
