@@ -119,6 +119,7 @@ struct cosl_ba_solver {
   int nSlots = 1;
   size_t rowsSmem = 0;
   bool useRows = false;
+  unsigned long long scSeq = 0;  // sequence number of the last scalar read-back (ba_publish_sc)
   bool useBlk = false;     // camera-block DMMA contraction (COSL_BA_SCHUR_BLK=1)
   BaVisit* d_bvis = nullptr;
   BaBlkItem* d_bitems = nullptr;
@@ -227,7 +228,11 @@ struct PinnedSlots {
       return p;
     }
     double* p = nullptr;
-    if (cudaMallocHost(&p, sizeof(double) * 16) != cudaSuccess) return nullptr;
+    // 16 scalars + the sequence flag of ba_publish_sc; mapped + portable: every device of the process writes
+    // its scalars straight into this host memory (UVA: the host pointer is the device pointer)
+    if (cudaHostAlloc(&p, sizeof(double) * 32, cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess)
+      return nullptr;
+    std::memset(p, 0, sizeof(double) * 32);
     return p;
   }
   void put(double* p) {
@@ -718,6 +723,8 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   static_assert(SC_NTOT <= 16, "pinned slot size");
   s->h_sc = pinned_slots().get();
   if (!s->h_sc) return set_error(COSL_E_NOMEM, "pinned host allocation failed");
+  *reinterpret_cast<volatile unsigned long long*>(s->h_sc + SC_NTOT) = 0;  // a pooled slot keeps its last flag
+  s->scSeq = 0;
 #define UP(dst, src, bytes) \
   COSL_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, s->stream))
   UP(s->d_camK, camK.data(), sizeof(double) * 5 * m);
@@ -880,10 +887,44 @@ int zero_sc(cosl_ba_solver* s, int first, int count) {
   return COSL_OK;
 }
 
+// Scalars of a trial -> host.  Instead of a copy-engine transfer + stream synchronise (8-12 us of latency per
+// LM trial), a 32-thread kernel stores the 16 scalars into MAPPED pinned host memory, fences, and stores a
+// sequence number; the host spins on that word.  Falls back to a stream synchronise if the flag does not
+// arrive (error on the stream) or with COSL_BA_SYNC_READBACK=1.
+__global__ void ba_publish_sc(const double* __restrict__ sc, volatile double* host, unsigned long long seq) {
+  if (threadIdx.x < SC_NTOT) host[threadIdx.x] = sc[threadIdx.x];
+  __threadfence_system();
+  __syncwarp();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(host + SC_NTOT) = seq;
+  }
+}
+
 int read_sc(cosl_ba_solver* s) {
-  COSL_CUDA(cudaMemcpyAsync(s->h_sc, s->d_sc, sizeof(double) * SC_NTOT, cudaMemcpyDeviceToHost,
-                            s->stream));
-  COSL_CUDA(cudaStreamSynchronize(s->stream));
+  static const bool syncReadback = std::getenv("COSL_BA_SYNC_READBACK") != nullptr;
+  if (syncReadback) {
+    COSL_CUDA(cudaMemcpyAsync(s->h_sc, s->d_sc, sizeof(double) * SC_NTOT, cudaMemcpyDeviceToHost,
+                              s->stream));
+    COSL_CUDA(cudaStreamSynchronize(s->stream));
+    return COSL_OK;
+  }
+  const unsigned long long seq = ++s->scSeq;
+  COSL_LAUNCH(ba_publish_sc, 1, 32, 0, s->stream, s->d_sc, s->h_sc, seq);
+  volatile unsigned long long* flag = reinterpret_cast<volatile unsigned long long*>(s->h_sc + SC_NTOT);
+  for (long long spin = 0; *flag != seq; ++spin) {
+    if ((spin & 0xfff) == 0xfff) {
+      const cudaError_t q = cudaStreamQuery(s->stream);
+      if (q == cudaSuccess) break;  // everything ran: the stores are visible after the query
+      if (q != cudaErrorNotReady)
+        return set_error(COSL_E_CUDA, "scalar read-back: %s", cudaGetErrorString(q));
+    }
+  }
+  std::atomic_thread_fence(std::memory_order_acquire);
+  if (*flag != seq) {  // left through the query: make sure the stores have landed
+    COSL_CUDA(cudaStreamSynchronize(s->stream));
+    if (*flag != seq) return set_error(COSL_E_CUDA, "scalar read-back: flag missing after synchronise");
+  }
   return COSL_OK;
 }
 
@@ -1040,17 +1081,25 @@ int levmar(cosl_ba_solver* s, int itmax, const double opts[5], double info[10], 
   if (!finite) stop = 7;
   for (itno = 0; itno < itmax && !stop; ++itno) {
     COSL_TRY(linearize(s));
-    if (itno == 0 || !fixed_trials) {
-      // ginf/maxdiag are needed on the host only for mu0 and the eps1 test
+    // ginf / maxdiag are needed on the host for mu0 (first iteration) and for the eps1 stop test.  After
+    // the first iteration the test is evaluated one read-back LATE: the scalars stay in d_sc (nothing
+    // below touches SC_GINF / SC_MAXDIAG) and arrive with the read-back of the next trial, which is
+    // discarded if the test fires -- it only wrote the trial buffers.  Same decisions and counters as
+    // the oracle, one host synchronisation less per LM iteration.
+    bool ginfPending = false;
+    if (itno == 0) {
       COSL_TRY(read_sc(s));
       ginf = s->h_sc[SC_GINF];
       maxdiag = s->h_sc[SC_MAXDIAG];
+    } else if (!fixed_trials) {
+      ginfPending = true;
     }
-    if (!fixed_trials && ginf <= eps1) {
+    if (!fixed_trials && !ginfPending && ginf <= eps1) {
       stop = 1;
       break;
     }
     if (itno == 0) mu = tau * maxdiag;
+    bool lateStop = false;
     while (true) {
       bool solved = false, accepted = false;
       COSL_TRY(solve_trial(s, mu, &solved));
@@ -1065,6 +1114,18 @@ int levmar(cosl_ba_solver* s, int itmax, const double opts[5], double info[10], 
       s->timer.end(s->stream);
       COSL_TRY(allreduce(s, s->d_sc, SC_NSUM, ncclSum));
       COSL_TRY(read_sc(s));
+      if (ginfPending) {
+        ginfPending = false;
+        ginf = s->h_sc[SC_GINF];
+        maxdiag = s->h_sc[SC_MAXDIAG];
+        if (ginf <= eps1) {  // the eps1 test of this iteration: the trial just run never happened
+          --s->nlss;
+          --s->nfev;
+          stop = 1;
+          lateStop = true;
+          break;
+        }
+      }
       solved = (s->h_sc[SC_FAIL] == 0.0);
       if (solved) {
         dp_L2 = s->h_sc[SC_DP_L2];
@@ -1114,6 +1175,7 @@ int levmar(cosl_ba_solver* s, int itmax, const double opts[5], double info[10], 
       }
       nu = nu2;
     }
+    if (lateStop) break;
     if (!fixed_trials && p_eL2 <= eps3) stop = 3;
   }
   if (itno >= itmax && !stop) stop = 3;
