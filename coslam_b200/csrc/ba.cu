@@ -317,7 +317,7 @@ void free_solver(cosl_ba_solver* s) {
   s->timer.destroy();
   void* bufs[] = {s->d_camK, s->d_camR0, s->d_pa, s->d_na, s->d_dpa, s->d_pb, s->d_nb, s->d_dpb,
                   s->d_cam, s->d_pt, s->d_cobs, s->d_ccam, s->d_xy, s->d_wgt, s->d_ptr, s->d_W,
-                  s->d_V, s->d_eb, s->d_Uea, s->d_S, s->d_y, s->d_x, s->d_sc, s->d_outlier,
+                  s->d_V, s->d_S, s->d_y, s->d_x, s->d_sc, s->d_outlier,
                   s->d_items, s->d_entries, s->d_Linv, s->d_cnt, s->d_tasks, s->d_bwd, s->d_blkRows,
                   s->d_blkRow0, s->d_tileIdx, s->d_diagBlk, s->d_blkCam0, s->d_order, s->d_solIdx,
                   s->d_trace, s->d_sum, s->d_rhsS, s->d_rowDst, s->d_cptrFree, s->d_Vinv, s->d_visit,
@@ -683,9 +683,10 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   COSL_TRY(dev_alloc(s->stream, &s->d_xy, (size_t)N * 2));
   COSL_TRY(dev_alloc(s->stream, &s->d_wgt, (size_t)N));
   COSL_TRY(dev_alloc(s->stream, &s->d_W, (size_t)N * 18));
-  COSL_TRY(dev_alloc(s->stream, &s->d_V, (size_t)n * 6));
-  COSL_TRY(dev_alloc(s->stream, &s->d_eb, (size_t)n * 3));
-  COSL_TRY(dev_alloc(s->stream, &s->d_Uea, (size_t)m * 27));
+  // [V (n x 6) | e_b (n x 3) | U (m x 21) | e_a (m x 6)] in one slab: one memset per linearisation
+  COSL_TRY(dev_alloc(s->stream, &s->d_V, (size_t)n * 9 + (size_t)m * 27));
+  s->d_eb = s->d_V + (size_t)n * 6;
+  s->d_Uea = s->d_eb + (size_t)n * 3;
   const double tAlloc0 = now_s();
   const int nb = std::max(1, P.nb), nTiles = std::max(1, P.nTiles);
   const size_t rhsLen = (size_t)nb * BA_TB;
@@ -963,9 +964,7 @@ int compute_weights(cosl_ba_solver* s) {
 int linearize(cosl_ba_solver* s) {
   ++s->njev;
   s->timer.begin(s->secLin, s->stream);
-  COSL_CUDA(cudaMemsetAsync(s->d_V, 0, sizeof(double) * 6 * (size_t)s->n, s->stream));
-  COSL_CUDA(cudaMemsetAsync(s->d_eb, 0, sizeof(double) * 3 * (size_t)s->n, s->stream));
-  COSL_CUDA(cudaMemsetAsync(s->d_Uea, 0, sizeof(double) * 27 * (size_t)s->m, s->stream));
+  COSL_CUDA(cudaMemsetAsync(s->d_V, 0, sizeof(double) * (9 * (size_t)s->n + 27 * (size_t)s->m), s->stream));
   if (s->N)
     COSL_LAUNCH(ba_linearize_points, (unsigned)div_up64(s->N, 256), 256, 0, s->stream, s->d,
                 s->d_pa, s->d_pb);
@@ -974,7 +973,7 @@ int linearize(cosl_ba_solver* s) {
                 s->d_pa, s->d_pb);
   s->timer.end(s->stream);
   COSL_TRY(allreduce(s, s->d_Uea, (size_t)27 * s->m, ncclSum));
-  COSL_TRY(zero_sc(s, SC_GINF, 2));
+  if (!s->N) COSL_TRY(zero_sc(s, SC_GINF, 2));  // otherwise ba_linearize_points cleared them
   COSL_LAUNCH(ba_stats_kernel, (unsigned)div_up64((long long)s->n + s->m, 256), 256, 0, s->stream,
               s->d);
   COSL_TRY(allreduce(s, s->d_sc + SC_NSUM, 2, ncclMax));
@@ -991,7 +990,6 @@ int dense_solve(cosl_ba_solver* s) {
     COSL_LAUNCH(ba_tile_small, 1, 256, sizeof(double) * (size_t)ns * ns, s->stream, s->td,
                 s->d_tileIdx, s->d_blkRow0, ns);
   } else {
-    COSL_CUDA(cudaMemsetAsync(s->d_cnt, 0, sizeof(int) * ((size_t)s->td.nCounters + 2 + s->td.nTasks), s->stream));
     COSL_LAUNCH(ba_tile_solve, s->solveGrid, BA_NTHREADS, BA_TILE_SMEM, s->stream, s->td);
   }
   s->timer.end(s->stream);
@@ -1004,15 +1002,22 @@ int dense_solve(cosl_ba_solver* s) {
 int solve_trial(cosl_ba_solver* s, double mu, bool* solved) {
   ++s->nlss;
   const bool r0 = rank_of(s) == 0;
-  COSL_TRY(zero_sc(s, SC_DP_L2, 3));
-  COSL_TRY(zero_sc(s, SC_FAIL, 1));
+  const long long ns = s->ns;
+  if (!ns) {  // no free camera: nothing launches ba_tile_init, which clears the trial's scalars otherwise
+    COSL_TRY(zero_sc(s, SC_DP_L2, 3));
+    COSL_TRY(zero_sc(s, SC_FAIL, 1));
+    COSL_TRY(zero_sc(s, SC_COST, 1));
+    COSL_TRY(zero_sc(s, SC_NONFINITE, 1));
+  }
   static const bool fineSchur = std::getenv("COSL_BA_TIMING_FINE") != nullptr;  // diagnostic: init / contraction apart
   const int secInit = fineSchur ? s->timer.section("ba_schur_init") : s->secSchur;
   s->timer.begin(secInit, s->stream);
-  const long long ns = s->ns;
   if (ns) {
+    // also clears the scalars of this trial (|dp|^2, dL, |p|^2, fail, cost, non-finite) and the task
+    // counters of the solve: five memset nodes less per trial
     COSL_LAUNCH(ba_tile_init, std::max(1, s->plan.nTiles), 256, 0, s->stream, s->d, mu, r0 ? 1 : 0,
-                s->d_diagBlk, s->d_blkCam0, s->d_order);
+                s->d_diagBlk, s->d_blkCam0, s->d_order, s->smallSolve ? (int*)nullptr : s->d_cnt,
+                s->smallSolve ? 0 : s->td.nCounters + 2 + s->td.nTasks);
     if (fineSchur) {
       s->timer.end(s->stream);
       s->timer.begin(s->secSchur, s->stream);
@@ -1049,9 +1054,9 @@ int solve_trial(cosl_ba_solver* s, double mu, bool* solved) {
   if (ns && multi(s)) COSL_TRY(allreduce(s, s->d_S, (size_t)s->reduceCount, ncclSum));
   COSL_TRY(dense_solve(s));
   s->timer.begin(s->secBack, s->stream);
-  COSL_LAUNCH(ba_cam_update, div_up(6 * s->m, 256), 256, 0, s->stream, s->d, s->d_pa, s->d_x,
-              s->d_dpa, s->d_na, mu, r0 ? 1 : 0);
-  COSL_CUDA(cudaMemsetAsync(s->d_nb, 0, sizeof(double) * 3 * (size_t)s->n, s->stream));
+  // (also zeroes the accumulator of the point back-substitution, d_nb)
+  COSL_LAUNCH(ba_cam_update, std::max(div_up(6 * s->m, 256), (int)std::min<long long>(148, div_up64(3LL * s->n, 1024))),
+              256, 0, s->stream, s->d, s->d_pa, s->d_x, s->d_dpa, s->d_na, mu, r0 ? 1 : 0, s->d_nb, 3LL * s->n);
   if (s->N)
     COSL_LAUNCH(ba_back_subst, (unsigned)div_up64(s->N, 256), 256, 0, s->stream, s->d, s->d_dpa,
                 s->d_nb);
@@ -1104,9 +1109,7 @@ int levmar(cosl_ba_solver* s, int itmax, const double opts[5], double info[10], 
       bool solved = false, accepted = false;
       COSL_TRY(solve_trial(s, mu, &solved));
       // trial cost, merged scalar all-reduce
-      ++s->nfev;
-      COSL_TRY(zero_sc(s, SC_COST, 1));
-      COSL_TRY(zero_sc(s, SC_NONFINITE, 1));
+      ++s->nfev;  // (cost / non-finite scalars were cleared by solve_trial)
       s->timer.begin(s->secCost, s->stream);
       if (s->N)
         COSL_LAUNCH(ba_residual_kernel, (unsigned)div_up64(s->N, 256), 256, 0, s->stream, s->d,

@@ -227,6 +227,7 @@ ba_residual_kernel(BaDev d, const double* __restrict__ pa, const double* __restr
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 2)
 ba_linearize_points(BaDev d, const double* __restrict__ pa, const double* __restrict__ pb) {
+  if (blockIdx.x == 0 && threadIdx.x < 2) d.sc[SC_GINF + threadIdx.x] = 0.0;  // |g|_inf, max diag: set by ba_stats_kernel
   const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31;
   double acc[9];
@@ -356,8 +357,13 @@ __global__ void __launch_bounds__(256) ba_stats_kernel(BaDev d) {
 // as identity).
 __global__ void __launch_bounds__(256)
 ba_tile_init(BaDev d, double mu, int addU, const int* __restrict__ diagBlk,
-             const int* __restrict__ blkCam0, const int* __restrict__ order) {
+             const int* __restrict__ blkCam0, const int* __restrict__ order, int* __restrict__ cnt, int nCnt) {
   const int t = blockIdx.x;
+  for (int q = blockIdx.x * 256 + threadIdx.x; q < nCnt; q += gridDim.x * 256) cnt[q] = 0;
+  if (blockIdx.x == 0 && threadIdx.x < 6) {
+    const int slot[6] = {SC_DP_L2, SC_DL, SC_P_L2, SC_FAIL, SC_COST, SC_NONFINITE};
+    d.sc[slot[threadIdx.x]] = 0.0;
+  }
   double2* tile = reinterpret_cast<double2*>(d.tiles + (size_t)t * 4096);
   const double2 z = make_double2(0.0, 0.0);
 #pragma unroll
@@ -1008,9 +1014,11 @@ ba_back_finish(BaDev d, const double* __restrict__ pb, double* __restrict__ nb,
 // addSums: only one rank contributes the (replicated) camera-side sums.
 __global__ void __launch_bounds__(256)
 ba_cam_update(BaDev d, const double* __restrict__ pa, const double* __restrict__ sol,
-              double* __restrict__ dpa, double* __restrict__ na, double mu, int addSums) {
+              double* __restrict__ dpa, double* __restrict__ na, double mu, int addSums,
+              double* __restrict__ zeroBuf, long long zeroCount) {
   __shared__ double s_red[8];
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long q = t; q < zeroCount; q += (long long)gridDim.x * blockDim.x) zeroBuf[q] = 0.0;
   double dp2 = 0, dl = 0, p2 = 0;
   if (t < 6 * d.m) {
     const int j = t / 6, r = t - 6 * j;
