@@ -119,6 +119,7 @@ struct cosl_ba_solver {
   int nSlots = 1;
   size_t rowsSmem = 0;
   bool useRows = false;
+  bool statsPending = false;     // |g|_inf / max diag of the last linearisation still to be computed (prep kernel)
   unsigned long long scSeq = 0;  // sequence number of the last scalar read-back (ba_publish_sc)
   bool useBlk = false;     // camera-block DMMA contraction (COSL_BA_SCHUR_BLK=1)
   BaVisit* d_bvis = nullptr;
@@ -961,7 +962,9 @@ int compute_weights(cosl_ba_solver* s) {
 }
 
 // Jacobians, U, V, W, ea, eb at (pa, pb); ginf / maxdiag land in h_sc
-int linearize(cosl_ba_solver* s) {
+// statsNow: |g|_inf / max diag are wanted before the next solve (first iteration: mu0); otherwise they are
+// computed by the prep kernel of the next trial (solve_trial) and arrive with that trial's scalars
+int linearize(cosl_ba_solver* s, bool statsNow, bool statsLater) {
   ++s->njev;
   s->timer.begin(s->secLin, s->stream);
   COSL_CUDA(cudaMemsetAsync(s->d_V, 0, sizeof(double) * (9 * (size_t)s->n + 27 * (size_t)s->m), s->stream));
@@ -974,9 +977,14 @@ int linearize(cosl_ba_solver* s) {
   s->timer.end(s->stream);
   COSL_TRY(allreduce(s, s->d_Uea, (size_t)27 * s->m, ncclSum));
   if (!s->N) COSL_TRY(zero_sc(s, SC_GINF, 2));  // otherwise ba_linearize_points cleared them
-  COSL_LAUNCH(ba_stats_kernel, (unsigned)div_up64((long long)s->n + s->m, 256), 256, 0, s->stream,
-              s->d);
-  COSL_TRY(allreduce(s, s->d_sc + SC_NSUM, 2, ncclMax));
+  s->statsPending = false;
+  if (statsNow || (statsLater && !s->ns)) {
+    COSL_LAUNCH(ba_stats_kernel, (unsigned)div_up64((long long)s->n + s->m, 256), 256, 0, s->stream,
+                s->d);
+    COSL_TRY(allreduce(s, s->d_sc + SC_NSUM, 2, ncclMax));
+  } else if (statsLater) {
+    s->statsPending = true;
+  }
   COSL_CUDA(cudaGetLastError());
   return COSL_OK;
 }
@@ -1015,25 +1023,26 @@ int solve_trial(cosl_ba_solver* s, double mu, bool* solved) {
   if (ns) {
     // also clears the scalars of this trial (|dp|^2, dL, |p|^2, fail, cost, non-finite) and the task
     // counters of the solve: five memset nodes less per trial
-    COSL_LAUNCH(ba_tile_init, std::max(1, s->plan.nTiles), 256, 0, s->stream, s->d, mu, r0 ? 1 : 0,
-                s->d_diagBlk, s->d_blkCam0, s->d_order, s->smallSolve ? (int*)nullptr : s->d_cnt,
-                s->smallSolve ? 0 : s->td.nCounters + 2 + s->td.nTasks);
+    const int nTilesInit = std::max(1, s->plan.nTiles);
+    const bool doStats = s->statsPending;
+    s->statsPending = false;
+    COSL_LAUNCH(ba_prep_kernel, nTilesInit + (unsigned)div_up64((long long)s->n + s->m, 256), 256, 0, s->stream, s->d,
+                mu, r0 ? 1 : 0, s->d_diagBlk, s->d_blkCam0, s->d_order, s->smallSolve ? (int*)nullptr : s->d_cnt,
+                s->smallSolve ? 0 : s->td.nCounters + 2 + s->td.nTasks, nTilesInit, s->d_Vinv, doStats ? 1 : 0);
+    if (doStats) COSL_TRY(allreduce(s, s->d_sc + SC_NSUM, 2, ncclMax));
     if (fineSchur) {
       s->timer.end(s->stream);
       s->timer.begin(s->secSchur, s->stream);
     }
     if (s->useRows) {
-      if (s->n) COSL_LAUNCH(ba_vinv_kernel, (unsigned)div_up64(s->n, 256), 256, 0, s->stream, s->d, mu, s->d_Vinv);
       if (s->Nc)
         COSL_LAUNCH(ba_schur_rows, s->mf * s->rowSplits, 32 * BA_ROWS_WARPS, s->rowsSmem, s->stream, s->d,
                     s->d_cptrFree, s->d_visit, s->d_rowDst, s->nSlots, s->d_Vinv, s->d_solIdx, s->rowSplits);
     } else if (s->useBlk) {
-      if (s->n) COSL_LAUNCH(ba_vinv_kernel, (unsigned)div_up64(s->n, 256), 256, 0, s->stream, s->d, mu, s->d_Vinv);
       if (s->nBItems)
         COSL_LAUNCH(ba_schur_blk, div_up(s->nBItems, BA_BLK_WARPS), 32 * BA_BLK_WARPS, BA_BLK_SMEM, s->stream, s->d,
                     s->d_bitems, s->nBItems, s->d_bvis, s->d_btabs, s->d_Vinv);
     } else if (s->nItems) {
-      if (s->n) COSL_LAUNCH(ba_vinv_kernel, (unsigned)div_up64(s->n, 256), 256, 0, s->stream, s->d, mu, s->d_Vinv);
       // fp64 tensor-core variant (ba_schur_mma, DMMA m8n8k4 over smem-staged entry rows): correct and
       // parity-tested, tensor pipe 3.3 % active, but 1.78 ms vs 0.47 ms at c4 -- its staging spends
       // ~100 instructions per entry on index arithmetic (profiles/r2i_ba_schur_mma.summary.txt).
@@ -1085,7 +1094,7 @@ int levmar(cosl_ba_solver* s, int itmax, const double opts[5], double info[10], 
   double ginf = 0, maxdiag = 0, dp_L2 = 0;
   if (!finite) stop = 7;
   for (itno = 0; itno < itmax && !stop; ++itno) {
-    COSL_TRY(linearize(s));
+    COSL_TRY(linearize(s, itno == 0, itno > 0 && !fixed_trials));
     // ginf / maxdiag are needed on the host for mu0 (first iteration) and for the eps1 stop test.  After
     // the first iteration the test is evaluated one read-back LATE: the scalars stay in d_sc (nothing
     // below touches SC_GINF / SC_MAXDIAG) and arrive with the read-back of the next trial, which is

@@ -355,15 +355,9 @@ __global__ void __launch_bounds__(256) ba_stats_kernel(BaDev d) {
 // their slice of rhs.  addU: this rank contributes U/ea/mu (rank 0 only in the multi-GPU case, where
 // U/ea are already all-reduced).  Padding rows of a block stay zero (the factorisation treats them
 // as identity).
-__global__ void __launch_bounds__(256)
-ba_tile_init(BaDev d, double mu, int addU, const int* __restrict__ diagBlk,
-             const int* __restrict__ blkCam0, const int* __restrict__ order, int* __restrict__ cnt, int nCnt) {
+__device__ __forceinline__ void ba_tile_init_body(const BaDev& d, double mu, int addU, const int* __restrict__ diagBlk,
+                                                  const int* __restrict__ blkCam0, const int* __restrict__ order) {
   const int t = blockIdx.x;
-  for (int q = blockIdx.x * 256 + threadIdx.x; q < nCnt; q += gridDim.x * 256) cnt[q] = 0;
-  if (blockIdx.x == 0 && threadIdx.x < 6) {
-    const int slot[6] = {SC_DP_L2, SC_DL, SC_P_L2, SC_FAIL, SC_COST, SC_NONFINITE};
-    d.sc[slot[threadIdx.x]] = 0.0;
-  }
   double2* tile = reinterpret_cast<double2*>(d.tiles + (size_t)t * 4096);
   const double2 z = make_double2(0.0, 0.0);
 #pragma unroll
@@ -421,6 +415,62 @@ __device__ __forceinline__ void inv3sym_mu(const double* __restrict__ V, double 
   I[3] = (a * f - c * c) * r;
   I[4] = (b * c - a * e) * r;
   I[5] = (a * d - b * b) * r;
+}
+
+// One launch in front of every Schur contraction ("prep"): blocks [0, nTiles) initialise the tiles
+// (ba_tile_init_body), the following blocks compute the damped inverses V*_i^-1 (one point per thread) and --
+// when a linearisation preceded this trial (doStats) -- the gradient / diagonal statistics |g|_inf and
+// max diag(U, V) that the host needs for the eps1 test (it reads them with the trial's scalars).  Block 0
+// also clears the scalars of the trial and the grid clears the task counters of the solve.
+__global__ void __launch_bounds__(256)
+ba_prep_kernel(BaDev d, double mu, int addU, const int* __restrict__ diagBlk, const int* __restrict__ blkCam0,
+               const int* __restrict__ order, int* __restrict__ cnt, int nCnt, int nTiles,
+               double* __restrict__ Vinv, int doStats) {
+  for (int q = blockIdx.x * 256 + threadIdx.x; q < nCnt; q += gridDim.x * 256) cnt[q] = 0;
+  if (blockIdx.x == 0 && threadIdx.x < 6) {
+    const int slot[6] = {SC_DP_L2, SC_DL, SC_P_L2, SC_FAIL, SC_COST, SC_NONFINITE};
+    d.sc[slot[threadIdx.x]] = 0.0;
+  }
+  if ((int)blockIdx.x < nTiles) {
+    ba_tile_init_body(d, mu, addU, diagBlk, blkCam0, order);
+    return;
+  }
+  const long long t = (long long)(blockIdx.x - nTiles) * 256 + threadIdx.x;
+  double g = 0, dg = 0;
+  if (t < d.n) {
+    double I[6] = {0, 0, 0, 0, 0, 0};
+    if (t >= d.ncon) {
+      const double* V = d.V + 6 * t;
+      inv3sym_mu(V, mu, I);
+      if (doStats) {
+        const double* e = d.eb + 3 * t;
+        g = fmax(fabs(e[0]), fmax(fabs(e[1]), fabs(e[2])));
+        dg = fmax(V[0], fmax(V[3], V[5]));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) Vinv[6 * t + k] = I[k];
+  } else if (doStats && t < (long long)d.n + d.m) {
+    const int j = (int)(t - d.n);
+    if (j >= d.mcon) {
+      const double* U = d.U + 21 * (size_t)j;
+      const double* e = d.ea + 6 * (size_t)j;
+      dg = fmax(fmax(U[0], U[6]), fmax(fmax(U[11], U[15]), fmax(U[18], U[20])));
+#pragma unroll
+      for (int k = 0; k < 6; ++k) g = fmax(g, fabs(e[k]));
+    }
+  }
+  if (doStats) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      g = fmax(g, __shfl_xor_sync(0xffffffffu, g, o));
+      dg = fmax(dg, __shfl_xor_sync(0xffffffffu, dg, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      if (g > 0) atomic_max_nonneg(&d.sc[SC_GINF], g);
+      if (dg > 0) atomic_max_nonneg(&d.sc[SC_MAXDIAG], dg);
+    }
+  }
 }
 
 // Entries carry the point index ({obsA, obsB, point, -}) and the damped inverses V*^-1 are computed
@@ -825,14 +875,6 @@ struct BaRowDst {
   int dst, rOff, cOff, trans;  // as in BaPairItem; dst < 0: cameras (a, a + slot) share no point
 };
 
-__global__ void __launch_bounds__(256) ba_vinv_kernel(BaDev d, double mu, double* __restrict__ Vinv) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= d.n) return;
-  double I[6] = {0, 0, 0, 0, 0, 0};
-  if (i >= d.ncon) inv3sym_mu(d.V + 6 * i, mu, I);
-#pragma unroll
-  for (int k = 0; k < 6; ++k) Vinv[6 * i + k] = I[k];
-}
 
 constexpr int BA_ROWS_WARPS = 4;
 
