@@ -590,7 +590,8 @@ def ba_roofline(tm, trials, prob, st, world, solver):
 
 def run_ba(args, api, synth, BaOptions, torch, dist, rank, world, local, barrier, max_over_ranks):
     prob, truth = synth.make_ba_scene(BA_CAMS, BA_KF, BA_PTS, KLT_W, KLT_H,
-                                      seed=synth.BASE_SEED + 4, m_con=BA_CAMS, n_con=0)
+                                      seed=synth.BASE_SEED + 4, m_con=BA_CAMS, n_con=0,
+                                      sort_by_home=os.environ.get("COSL_BENCH_BA_SORTED", "0") == "1")
     opt = BaOptions.defaults()
     opt.device = local
     comm = None

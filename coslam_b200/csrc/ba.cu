@@ -331,7 +331,25 @@ void free_solver(cosl_ba_solver* s) {
   delete s;
 }
 
+// temporaries of the solver set-up: handed back to the pool on every exit path
+struct TmpDeviceBufs {
+  cudaStream_t st;
+  std::vector<void*> bufs;
+  explicit TmpDeviceBufs(cudaStream_t s) : st(s) {}
+  ~TmpDeviceBufs() {
+    for (void* b : bufs)
+      if (b) cudaFreeAsync(b, st);
+  }
+  template <typename T>
+  int alloc(T** p, size_t count) {
+    const int rc = dev_alloc(st, p, count);
+    if (rc == COSL_OK) bufs.push_back(*p);
+    return rc;
+  }
+};
+
 int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
+  TmpDeviceBufs tmp(s->stream);
   const double tBuild0 = now_s();
   const int m = p->m, n = p->n, mcon = p->m_con, ncon = p->n_con;
   const long long N = p->nobs;
@@ -384,8 +402,8 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   COSL_TRY(dev_alloc(s->stream, &s->d_ccam, (size_t)Nc));
   const size_t nBuckets = (size_t)mf * mf;
   unsigned *d_pcnt = nullptr, *d_poff = nullptr;
-  COSL_TRY(dev_alloc(s->stream, &d_pcnt, nBuckets + 1));
-  COSL_TRY(dev_alloc(s->stream, &d_poff, nBuckets + 1));
+  COSL_TRY(tmp.alloc(&d_pcnt, nBuckets + 1));
+  COSL_TRY(tmp.alloc(&d_poff, nBuckets + 1));
   COSL_CUDA(cudaMemcpyAsync(s->d_cam, cam.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, s->stream));
   COSL_CUDA(cudaMemcpyAsync(s->d_pt, pt.data(), sizeof(int) * (size_t)N, cudaMemcpyHostToDevice, s->stream));
   COSL_CUDA(cudaMemcpyAsync(s->d_ptr, p->ptr, sizeof(long long) * ((size_t)n + 1), cudaMemcpyHostToDevice, s->stream));
@@ -424,13 +442,12 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   (void)run_threads;
   if (s->comm && s->comm->nranks > 1 && mf > 0) {
     uint8_t* d_adj = nullptr;
-    COSL_TRY(dev_alloc(s->stream, &d_adj, adj.size()));
+    COSL_TRY(tmp.alloc(&d_adj, adj.size()));
     COSL_CUDA(cudaMemcpyAsync(d_adj, adj.data(), adj.size(), cudaMemcpyHostToDevice, s->stream));
     const int rc = nccl().AllReduce(d_adj, d_adj, adj.size(), ncclUint8, ncclMax, s->comm->comm, s->stream);
     if (rc != 0) return set_error(COSL_E_NCCL, "ncclAllReduce (co-visibility) failed (%d)", rc);
     COSL_CUDA(cudaMemcpyAsync(adj.data(), d_adj, adj.size(), cudaMemcpyDeviceToHost, s->stream));
     COSL_CUDA(cudaStreamSynchronize(s->stream));
-    COSL_CUDA(cudaFreeAsync(d_adj, s->stream));
   }
   {
     int ndDepth = -1;
@@ -539,16 +556,16 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
       }
     }
     int *d_camBlock = nullptr, *d_camSlot = nullptr;
-    COSL_TRY(dev_alloc(s->stream, &d_camBlock, (size_t)mf));
-    COSL_TRY(dev_alloc(s->stream, &d_camSlot, (size_t)mf));
+    COSL_TRY(tmp.alloc(&d_camBlock, (size_t)mf));
+    COSL_TRY(tmp.alloc(&d_camSlot, (size_t)mf));
     COSL_CUDA(cudaMemcpyAsync(d_camBlock, camBlock.data(), sizeof(int) * mf, cudaMemcpyHostToDevice, s->stream));
     COSL_CUDA(cudaMemcpyAsync(d_camSlot, camSlot.data(), sizeof(int) * mf, cudaMemcpyHostToDevice, s->stream));
     const size_t nBB = (size_t)nB * nB;
     unsigned *d_vcnt = nullptr, *d_voff = nullptr;
     int* d_ovf = nullptr;
-    COSL_TRY(dev_alloc(s->stream, &d_vcnt, nBB + 1));
-    COSL_TRY(dev_alloc(s->stream, &d_voff, nBB + 1));
-    COSL_TRY(dev_alloc(s->stream, &d_ovf, (size_t)1));
+    COSL_TRY(tmp.alloc(&d_vcnt, nBB + 1));
+    COSL_TRY(tmp.alloc(&d_voff, nBB + 1));
+    COSL_TRY(tmp.alloc(&d_ovf, (size_t)1));
     COSL_CUDA(cudaMemsetAsync(d_vcnt, 0, sizeof(unsigned) * (nBB + 1), s->stream));
     COSL_CUDA(cudaMemsetAsync(d_ovf, 0, sizeof(int), s->stream));
     BaDev dv = db;
@@ -614,11 +631,6 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
       }
       nEntries = poff[nBuckets];
     }
-    COSL_CUDA(cudaFreeAsync(d_vcnt, s->stream));
-    COSL_CUDA(cudaFreeAsync(d_voff, s->stream));
-    COSL_CUDA(cudaFreeAsync(d_ovf, s->stream));
-    COSL_CUDA(cudaFreeAsync(d_camBlock, s->stream));
-    COSL_CUDA(cudaFreeAsync(d_camSlot, s->stream));
     if (ba_timing())
       std::fprintf(stderr, "[ba timing] camera-block visits: %d blocks, %lld visits (%.2f pair entries per visit), %d items\n",
                    nB, s->nVisits, s->nVisits ? (double)poff[nBuckets] / (double)s->nVisits : 0.0, s->nBItems);
@@ -655,8 +667,6 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
     if (nEntries)
       COSL_LAUNCH(ba_pairs_build<true>, (unsigned)div_up64(Nc, 256), 256, 0, s->stream, db, d_pcnt, d_poff, s->d_entries);
   }
-  COSL_CUDA(cudaFreeAsync(d_pcnt, s->stream));
-  COSL_CUDA(cudaFreeAsync(d_poff, s->stream));
   s->nEntries = nEntries;
   s->nItems = (int)items.size();
   if (ba_timing())
