@@ -134,6 +134,8 @@ struct cosl_ba_solver {
   long long nEntries = 0;
   double* h_sc = nullptr;  // pinned
   bool smallSolve = true;
+  bool twoSolve = false;  // <= 2 blocks: single-CTA resident solve (ba_tile_two)
+  int two00 = -1, two10 = -1, two11 = -1;
   SectionTimer timer;
   int secLin = 0, secSchur = 0, secSolve = 0, secBack = 0, secCost = 0, secComm = 0;
   // statistics
@@ -844,6 +846,13 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
   // system of the c3 local BA (72 pivots x 3 CTA barriers); the task kernel does the same two
   // blocks in about half of that, so it is the default everywhere.  COSL_BA_SMALL_KERNEL=1 selects
   // the dense kernel.
+  if (P.nb >= 1 && P.nb <= 2 && std::getenv("COSL_BA_NO_TWO_KERNEL") == nullptr) {
+    s->twoSolve = true;
+    s->two00 = P.tileIdx[0];
+    s->two10 = P.nb == 2 ? P.tileIdx[(size_t)1 * P.nb + 0] : -1;
+    s->two11 = P.nb == 2 ? P.tileIdx[(size_t)1 * P.nb + 1] : -1;
+    if (s->two00 < 0 || (P.nb == 2 && s->two11 < 0)) s->twoSolve = false;
+  }
   s->smallSolve = (smallBytes <= 200 * 1024) && s->ns <= 1024 && std::getenv("COSL_BA_SMALL_KERNEL") != nullptr;
   // (the kernel also has ~8 KB of static shared memory, so opt in well below the 48 KB default)
   if (s->smallSolve && smallBytes > 32 * 1024)
@@ -851,6 +860,7 @@ int build_solver(cosl_ba_solver* s, const cosl_ba_problem* p) {
                                    (int)smallBytes));
   COSL_CUDA(cudaFuncSetAttribute(ba_tile_solve, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  BA_TILE_SMEM));
+  COSL_CUDA(cudaFuncSetAttribute(ba_tile_two, cudaFuncAttributeMaxDynamicSharedMemorySize, BA_TILE_SMEM));
   COSL_CUDA(cudaFuncSetAttribute(ba_schur_pairs_st, cudaFuncAttributeMaxDynamicSharedMemorySize, BA_ST_SMEM));
   COSL_CUDA(cudaFuncSetAttribute(ba_schur_blk, cudaFuncAttributeMaxDynamicSharedMemorySize, BA_BLK_SMEM));
   if (s->useRows && s->rowsSmem > 40 * 1024)
@@ -1004,7 +1014,9 @@ int dense_solve(cosl_ba_solver* s) {
   const int ns = s->ns;
   if (ns == 0) return COSL_OK;
   s->timer.begin(s->secSolve, s->stream);
-  if (s->smallSolve) {
+  if (s->twoSolve) {
+    COSL_LAUNCH(ba_tile_two, 1, BA_NTHREADS, BA_TILE_SMEM, s->stream, s->td, s->two00, s->two10, s->two11);
+  } else if (s->smallSolve) {
     COSL_LAUNCH(ba_tile_small, 1, 256, sizeof(double) * (size_t)ns * ns, s->stream, s->td,
                 s->d_tileIdx, s->d_blkRow0, ns);
   } else {

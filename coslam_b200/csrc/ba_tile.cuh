@@ -719,6 +719,113 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Reduced systems of ONE or TWO blocks (<= 20 free cameras: the per-key-frame local BA, c2 / c3): the
+// whole solve in ONE CTA with the tiles resident in shared memory -- POTRF(0), TRSM(1,0), UPD(1,1,0),
+// POTRF(1), BWD(1), BWD(0) with the same tile primitives as the dataflow kernel, but without tickets,
+// polling, publishing and the global round trip of every tile between two tasks (6 tasks x ~3 us).
+// t00 / t10 / t11: tile indices of the lower block triangle (t10 < 0: structurally zero; t11 < 0: one block).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_stage_diag(const double* __restrict__ g, double* __restrict__ sT, int bk, int tid) {
+  double2 v[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) v[u] = __ldcg(reinterpret_cast<const double2*>(g) + tid + BA_NTHREADS * u);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int e = 2 * (tid + BA_NTHREADS * u);
+    const int c = e >> 6, r = e & 63;
+    double2 w = v[u];
+    if (r >= bk || c >= bk) w.x = (r == c) ? 1.0 : 0.0;
+    if (r + 1 >= bk || c >= bk) w.y = (r + 1 == c) ? 1.0 : 0.0;
+    *reinterpret_cast<double2*>(sT + c * BA_LDS + r) = w;
+  }
+}
+
+__global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_two(BaTileDev d, int t00, int t10, int t11) {
+  extern __shared__ double smem[];
+  double* sA = smem;                       // block (0,0) -> L00
+  double* sB = sA + BA_TB * BA_LDS;        // block (1,0) -> L10
+  double* sC = sB + BA_TB * BA_LDS;        // block (1,1) -> L11
+  double* sX = sC + BA_TB * BA_LDS;        // x0 [0..63], x1 [64..127]
+  double* sM = sX + 8 * BA_TB;
+  double* sV = sM + 8 * BA_TB;
+  double* sY = sV + BA_TB;
+  double* sD = sY + BA_TB;
+  __shared__ double sM0[8 * BA_TB], sY0[BA_TB], sR1[BA_TB];
+  __shared__ int s_fail;
+  const int tid = threadIdx.x;
+  const int bk0 = d.blkRows[0];
+  const bool two = t11 >= 0;
+  const int bk1 = two ? d.blkRows[1] : 0;
+  if (tid == 0) s_fail = 0;
+  tile_stage_diag(d.tiles + (size_t)t00 * BA_TILE, sA, bk0, tid);
+  if (tid < 64) sV[tid] = (tid < bk0) ? __ldcg(d.rhs + tid) : 0.0;
+  if (two) {
+    tile_stage_diag(d.tiles + (size_t)t11 * BA_TILE, sC, bk1, tid);
+    if (t10 >= 0) tile_load<BA_LDS>(d.tiles + (size_t)t10 * BA_TILE, sB, tid);
+    if (tid < 64) sR1[tid] = (tid < bk1) ? __ldcg(d.rhs + BA_TB + tid) : 0.0;
+  }
+  __syncthreads();
+  tile_potrf2(sA, sV, sY, sM, sD, tid, &s_fail);  // L00 (sA), y0 (sY), M_b of block 0 (sM)
+  if (two) {
+    if (t10 >= 0) {
+      tile_trsm2(sB, sA, sM, (bk0 + 7) >> 3, tid);  // L10 = A10 L00^-T
+      __syncthreads();
+      TileAcc acc;
+      tile_gemm_dmma(sB, sB, (bk0 + 3) & ~3, tid, acc);  // L10 L10^T
+#pragma unroll
+      for (int mi = 0; mi < 2; ++mi)
+#pragma unroll
+        for (int ni = 0; ni < 4; ++ni)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            int r, c;
+            tile_acc_rc(tid, mi, ni, e, r, c);
+            sC[c * BA_LDS + r] -= acc.c[mi][ni][e];
+          }
+      if (tid < 64) {  // b1 -= L10 y0
+        double sum = 0;
+        for (int p = 0; p < bk0; ++p) sum = __fma_rn(sB[p * BA_LDS + tid], sY[p], sum);
+        sR1[tid] -= sum;
+      }
+    }
+    // keep y0 and the diagonal inverses of block 0 for its backward step
+    sM0[tid] = sM[tid];
+    sM0[tid + BA_NTHREADS] = sM[tid + BA_NTHREADS];
+    if (tid < 64) sY0[tid] = sY[tid];
+    __syncthreads();
+    tile_potrf2(sC, sR1, sY, sM, sD, tid, &s_fail);  // L11 (sC), y1 (sY), M_b of block 1 (sM)
+    if (tid < 64) {
+      sV[tid] = sY[tid];
+      sX[BA_TB + tid] = 0.0;
+      tile_bwd3(sC, sM, sV, sX + BA_TB, (bk1 + 7) >> 3, tid);  // x1 = L11^-T y1
+    }
+    __syncthreads();
+    if (tid < 64) {  // v0 = y0 - L10^T x1
+      double sum = 0;
+      if (t10 >= 0)
+        for (int r = 0; r < bk1; ++r) sum = __fma_rn(sB[tid * BA_LDS + r], sX[BA_TB + r], sum);
+      sV[tid] = sY0[tid] - sum;
+      sX[tid] = 0.0;
+      tile_bwd3(sA, sM0, sV, sX, (bk0 + 7) >> 3, tid);  // x0 = L00^-T v0
+    }
+    __syncthreads();
+    if (tid < 64) {
+      d.x[tid] = (tid < bk0) ? sX[tid] : 0.0;
+      d.x[BA_TB + tid] = (tid < bk1) ? sX[BA_TB + tid] : 0.0;
+    }
+  } else {
+    if (tid < 64) {
+      sV[tid] = sY[tid];
+      sX[tid] = 0.0;
+      tile_bwd3(sA, sM, sV, sX, (bk0 + 7) >> 3, tid);
+    }
+    __syncthreads();
+    if (tid < 64) d.x[tid] = (tid < bk0) ? sX[tid] : 0.0;
+  }
+  if (tid == 0 && s_fail) d.sc[d.scFail] = 1.0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Small systems (local BA: a handful of blocks): everything inside ONE CTA's shared memory,
 // dense column-major lower with leading dimension ns (rows of block k start at 60*k: every block
 // but the last is full when the plan has a single region).
