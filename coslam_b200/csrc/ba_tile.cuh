@@ -212,7 +212,9 @@ __device__ __forceinline__ double ba_rsqrt_pivot(double d) {
 
 __device__ __forceinline__ void tile_potrf2(double* __restrict__ sT, double* __restrict__ sBv,
                                             double* __restrict__ sYv, double* __restrict__ sM,
-                                            double* __restrict__ sD, int tid, int* s_fail) {
+                                            double* __restrict__ sD, int tid, int* s_fail, int nbp = 8) {
+  // nbp = number of 8-column panels that hold real rows ((rows + 7) / 8): the padding of a partial block is
+  // the identity and needs no work (its L columns stay as staged, its y and M_b are never read)
   const bool isP = tid < 64;
   const int r = tid;
   double a[8], x[8];
@@ -223,7 +225,7 @@ __device__ __forceinline__ void tile_potrf2(double* __restrict__ sT, double* __r
     x[q] = 0.0;
   }
 #pragma unroll 1
-  for (int pb = 0; pb < 8; ++pb) {
+  for (int pb = 0; pb < nbp; ++pb) {
     const int c0 = 8 * pb;
     if (isP) {
       if (r >= c0 && r < c0 + 8) {
@@ -283,7 +285,7 @@ __device__ __forceinline__ void tile_potrf2(double* __restrict__ sT, double* __r
     }
     __syncthreads();  // X and y of this panel are visible; the update warps finished the previous panel
     if (isP) {
-      if (pb < 7 && r >= c0 + 8) {  // look-ahead: next panel's columns of this row, kept in registers
+      if (pb + 1 < nbp && r >= c0 + 8) {  // look-ahead: next panel's columns of this row, kept in registers
 #pragma unroll
         for (int qn = 0; qn < 8; ++qn) a[qn] = sT[(c0 + 8 + qn) * BA_LDS + r];
 #pragma unroll
@@ -323,7 +325,7 @@ __device__ __forceinline__ void tile_potrf2(double* __restrict__ sT, double* __r
         const int uw = (tid >> 5) - 2;              // update warp 0..5
         const int lane = tid & 31, g = lane >> 2, kq = lane & 3;
         const int t0 = pb + 2;                      // first 8-row block of the trailing part
-        const int nt = 8 - t0;                      // blocks per side
+        const int nt = nbp - t0;                    // blocks per side (padding blocks need no update)
         const int ntile = nt * (nt + 1) / 2;
         const double* xk0 = sT + (c0 + kq) * BA_LDS;       // X(., c0 + kq)
         const double* xk1 = sT + (c0 + 4 + kq) * BA_LDS;   // X(., c0 + 4 + kq)
@@ -511,7 +513,7 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
       }
       __syncthreads();
       if (d.trace && tid == 0) d.trace[8 * (size_t)ti + 4] = ba_globaltimer();
-      tile_potrf2(sA, sV, sY, sM, sD, tid, &s_fail);
+      tile_potrf2(sA, sV, sY, sM, sD, tid, &s_fail, (bk + 7) >> 3);
       if (d.trace && tid == 0) d.trace[8 * (size_t)ti + 5] = ba_globaltimer();
       {
         double* g = d.tiles + (size_t)t.tC * BA_TILE;  // L in place (lower), zeros above
@@ -765,7 +767,7 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_two(BaTileDev d, int t
     if (tid < 64) sR1[tid] = (tid < bk1) ? __ldcg(d.rhs + BA_TB + tid) : 0.0;
   }
   __syncthreads();
-  tile_potrf2(sA, sV, sY, sM, sD, tid, &s_fail);  // L00 (sA), y0 (sY), M_b of block 0 (sM)
+  tile_potrf2(sA, sV, sY, sM, sD, tid, &s_fail, (bk0 + 7) >> 3);  // L00 (sA), y0 (sY), M_b of block 0 (sM)
   if (two) {
     if (t10 >= 0) {
       tile_trsm2(sB, sA, sM, (bk0 + 7) >> 3, tid);  // L10 = A10 L00^-T
@@ -793,7 +795,7 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_two(BaTileDev d, int t
     sM0[tid + BA_NTHREADS] = sM[tid + BA_NTHREADS];
     if (tid < 64) sY0[tid] = sY[tid];
     __syncthreads();
-    tile_potrf2(sC, sR1, sY, sM, sD, tid, &s_fail);  // L11 (sC), y1 (sY), M_b of block 1 (sM)
+    tile_potrf2(sC, sR1, sY, sM, sD, tid, &s_fail, (bk1 + 7) >> 3);  // L11 (sC), y1 (sY), M_b of block 1 (sM)
     if (tid < 64) {
       sV[tid] = sY[tid];
       sX[BA_TB + tid] = 0.0;
