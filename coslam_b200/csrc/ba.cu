@@ -119,6 +119,7 @@ struct cosl_ba_solver {
   int nSlots = 1;
   size_t rowsSmem = 0;
   bool useRows = false;
+  bool costDone = false;         // solve_trial already evaluated the trial cost (ba_finish_cost)
   bool statsPending = false;     // |g|_inf / max diag of the last linearisation still to be computed (prep kernel)
   unsigned long long scSeq = 0;  // sequence number of the last scalar read-back (ba_publish_sc)
   bool useBlk = false;     // camera-block DMMA contraction (COSL_BA_SCHUR_BLK=1)
@@ -1050,7 +1051,8 @@ int solve_trial(cosl_ba_solver* s, double mu, bool* solved) {
     s->statsPending = false;
     COSL_LAUNCH(ba_prep_kernel, nTilesInit + (unsigned)div_up64((long long)s->n + s->m, 256), 256, 0, s->stream, s->d,
                 mu, r0 ? 1 : 0, s->d_diagBlk, s->d_blkCam0, s->d_order, s->smallSolve ? (int*)nullptr : s->d_cnt,
-                s->smallSolve ? 0 : s->td.nCounters + 2 + s->td.nTasks, nTilesInit, s->d_Vinv, doStats ? 1 : 0);
+                s->smallSolve ? 0 : s->td.nCounters + 2 + s->td.nTasks, nTilesInit, s->d_Vinv, doStats ? 1 : 0,
+                s->d_dpb, 3LL * s->n);
     if (doStats) COSL_TRY(allreduce(s, s->d_sc + SC_NSUM, 2, ncclMax));
     if (fineSchur) {
       s->timer.end(s->stream);
@@ -1084,6 +1086,24 @@ int solve_trial(cosl_ba_solver* s, double mu, bool* solved) {
   // the one exchange of an LM trial: [rhs | Schur-structure tiles] is contiguous, no packing
   if (ns && multi(s)) COSL_TRY(allreduce(s, s->d_S, (size_t)s->reduceCount, ncclSum));
   COSL_TRY(dense_solve(s));
+  s->costDone = false;
+  if (ns) {
+    // back substitution + trial cost in two launches (ba_kernels.cuh): the accumulator d_dpb was zeroed by the
+    // prep kernel, V*^-1 is the one the Schur contraction used
+    const int nCamBlocks = div_up(6 * s->m, 256);
+    s->timer.begin(s->secBack, s->stream);
+    COSL_LAUNCH(ba_back_cams_points, nCamBlocks + (unsigned)div_up64(s->N, 256), 256, 0, s->stream, s->d, s->d_pa,
+                s->d_x, s->d_dpa, s->d_na, mu, r0 ? 1 : 0, nCamBlocks, s->d_dpb);
+    s->timer.end(s->stream);
+    s->timer.begin(s->secCost, s->stream);
+    COSL_LAUNCH(ba_finish_cost, (unsigned)div_up64(s->N + (long long)s->n, 256), 256, 0, s->stream, s->d, s->d_na,
+                s->d_pb, s->d_nb, s->d_dpb, s->d_Vinv, mu);
+    s->timer.end(s->stream);
+    s->costDone = true;
+    COSL_CUDA(cudaGetLastError());
+    *solved = true;
+    return COSL_OK;
+  }
   s->timer.begin(s->secBack, s->stream);
   // (also zeroes the accumulator of the point back-substitution, d_nb)
   COSL_LAUNCH(ba_cam_update, std::max(div_up(6 * s->m, 256), (int)std::min<long long>(148, div_up64(3LL * s->n, 1024))),
@@ -1141,11 +1161,13 @@ int levmar(cosl_ba_solver* s, int itmax, const double opts[5], double info[10], 
       COSL_TRY(solve_trial(s, mu, &solved));
       // trial cost, merged scalar all-reduce
       ++s->nfev;  // (cost / non-finite scalars were cleared by solve_trial)
-      s->timer.begin(s->secCost, s->stream);
-      if (s->N)
-        COSL_LAUNCH(ba_residual_kernel, (unsigned)div_up64(s->N, 256), 256, 0, s->stream, s->d,
-                    s->d_na, s->d_nb, 0, 0.0, nullptr);
-      s->timer.end(s->stream);
+      if (!s->costDone) {
+        s->timer.begin(s->secCost, s->stream);
+        if (s->N)
+          COSL_LAUNCH(ba_residual_kernel, (unsigned)div_up64(s->N, 256), 256, 0, s->stream, s->d,
+                      s->d_na, s->d_nb, 0, 0.0, nullptr);
+        s->timer.end(s->stream);
+      }
       COSL_TRY(allreduce(s, s->d_sc, SC_NSUM, ncclSum));
       COSL_TRY(read_sc(s));
       if (ginfPending) {

@@ -425,8 +425,11 @@ __device__ __forceinline__ void inv3sym_mu(const double* __restrict__ V, double 
 __global__ void __launch_bounds__(256)
 ba_prep_kernel(BaDev d, double mu, int addU, const int* __restrict__ diagBlk, const int* __restrict__ blkCam0,
                const int* __restrict__ order, int* __restrict__ cnt, int nCnt, int nTiles,
-               double* __restrict__ Vinv, int doStats) {
+               double* __restrict__ Vinv, int doStats, double* __restrict__ zeroBuf, long long zeroCount) {
   for (int q = blockIdx.x * 256 + threadIdx.x; q < nCnt; q += gridDim.x * 256) cnt[q] = 0;
+  // accumulator of the point back-substitution (ba_back_cams_points)
+  for (long long q = (long long)blockIdx.x * 256 + threadIdx.x; q < zeroCount; q += (long long)gridDim.x * 256)
+    zeroBuf[q] = 0.0;
   if (blockIdx.x == 0 && threadIdx.x < 6) {
     const int slot[6] = {SC_DP_L2, SC_DL, SC_P_L2, SC_FAIL, SC_COST, SC_NONFINITE};
     d.sc[slot[threadIdx.x]] = 0.0;
@@ -1080,6 +1083,141 @@ ba_cam_update(BaDev d, const double* __restrict__ pa, const double* __restrict__
   if (threadIdx.x == 0 && addSums && s != 0) atomicAdd(&d.sc[SC_DL], s);
   s = block_sum_1(p2, s_red);
   if (threadIdx.x == 0 && addSums && s != 0) atomicAdd(&d.sc[SC_P_L2], s);
+}
+
+// ------------------------------------------------------------------------------------------
+// Back substitution in two launches (instead of cam update | memset | point accumulate | point finish | cost):
+//  ba_back_cams_points: blocks [0, nCamBlocks) form the trial camera parameters na = pa + da and the camera-side
+//    parts of |dp|^2, dL, |p|^2 (ba_cam_update); the other blocks accumulate t_i = sum_j W_ij^T da_j per point
+//    (one observation per thread, segmented shuffles, heads add into acc3, which the prep kernel zeroed),
+//    reading da straight from the solution vector;
+//  ba_finish_cost: one observation per thread: db_i = V*_i^-1 (e_b,i - t_i) recomputed from the point's
+//    accumulator (read-only here; the FIRST observation of a point stores nb_i = pb_i + db_i and adds the
+//    point-side sums), then the weighted squared residual at (na, nb_i) -> cost.  Extra threads finish the
+//    points that have no observation.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+ba_back_cams_points(BaDev d, const double* __restrict__ pa, const double* __restrict__ sol,
+                    double* __restrict__ dpa, double* __restrict__ na, double mu, int addSums, int nCamBlocks,
+                    double* __restrict__ acc3) {
+  __shared__ double s_red[8];
+  if ((int)blockIdx.x < nCamBlocks) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    double dp2 = 0, dl = 0, p2 = 0;
+    if (t < 6 * d.m) {
+      const int j = t / 6, r = t - 6 * j;
+      double dlt = 0;
+      if (j >= d.mcon) {
+        dlt = sol[d.solIdx[j - d.mcon] + r];
+        dp2 = dlt * dlt;
+        dl = dlt * (mu * dlt + d.ea[t]);
+        p2 = pa[t] * pa[t];
+      }
+      dpa[t] = dlt;
+      na[t] = pa[t] + dlt;
+    }
+    double s = block_sum_1(dp2, s_red);
+    if (threadIdx.x == 0 && addSums && s != 0) atomicAdd(&d.sc[SC_DP_L2], s);
+    s = block_sum_1(dl, s_red);
+    if (threadIdx.x == 0 && addSums && s != 0) atomicAdd(&d.sc[SC_DL], s);
+    s = block_sum_1(p2, s_red);
+    if (threadIdx.x == 0 && addSums && s != 0) atomicAdd(&d.sc[SC_P_L2], s);
+    return;
+  }
+  const long long o = (long long)(blockIdx.x - nCamBlocks) * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  double acc[3] = {0, 0, 0};
+  int key = -1 - lane;
+  if (o < d.N) {
+    const int j = d.cam[o], i = d.pt[o];
+    key = i;
+    if (i >= d.ncon && j >= d.mcon) {
+      const double* Wp = d.W + 18 * (size_t)o;
+      const double* da = sol + d.solIdx[j - d.mcon];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        double s = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r) s += Wp[3 * r + c] * da[r];
+        acc[c] = s;
+      }
+    }
+  }
+  seg_reduce<3>(acc, key, lane);
+  const int kprev = __shfl_up_sync(0xffffffffu, key, 1);
+  const bool head = (lane == 0) || (kprev != key);
+  if (head && key >= d.ncon) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) atomicAdd(&acc3[3 * (size_t)key + c], acc[c]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ba_finish_cost(BaDev d, const double* __restrict__ na, const double* __restrict__ pb, double* __restrict__ nb,
+               const double* __restrict__ acc3, const double* __restrict__ Vinv, double mu) {
+  __shared__ double s_red[8];
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double dp2 = 0, dl = 0, p2 = 0, c = 0;
+  long long o = -1;
+  int i = -1;
+  bool store = false;
+  if (t < d.N) {
+    o = t;
+    i = d.pt[o];
+    store = (d.ptr[i] == o);
+  } else if (t < d.N + d.n) {
+    i = (int)(t - d.N);
+    store = (d.ptr[i + 1] == d.ptr[i]);  // a point nobody observes is finished here
+    if (!store) i = -1;
+  }
+  if (i >= 0) {
+    double x[3] = {pb[3 * (size_t)i], pb[3 * (size_t)i + 1], pb[3 * (size_t)i + 2]};
+    double db[3] = {0, 0, 0};
+    if (i >= d.ncon) {
+      const double* Iv = Vinv + 6 * (size_t)i;
+      const double* eb = d.eb + 3 * (size_t)i;
+      const double t0 = eb[0] - acc3[3 * (size_t)i], t1 = eb[1] - acc3[3 * (size_t)i + 1],
+                   t2 = eb[2] - acc3[3 * (size_t)i + 2];
+      db[0] = Iv[0] * t0 + Iv[1] * t1 + Iv[2] * t2;
+      db[1] = Iv[1] * t0 + Iv[3] * t1 + Iv[4] * t2;
+      db[2] = Iv[2] * t0 + Iv[4] * t1 + Iv[5] * t2;
+      if (store) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          dp2 += db[k] * db[k];
+          dl += db[k] * (mu * db[k] + eb[k]);
+          p2 += x[k] * x[k];
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) x[k] += db[k];
+    if (store) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) nb[3 * (size_t)i + k] = x[k];
+    }
+    if (o >= 0) {
+      const int j = d.cam[o];
+      double h[2];
+      ba_project<false, false>(d.camK + 5 * j, d.camR0 + 9 * j, na + 6 * j, x, h, nullptr, nullptr);
+      const double dx = d.xy[2 * o] - h[0], dy = d.xy[2 * o + 1] - h[1];
+      c = d.wgt[o] * (dx * dx + dy * dy);
+    }
+  }
+  double s = block_sum_1(c, s_red);
+  if (threadIdx.x == 0) {
+    if (isfinite(s)) {
+      if (s != 0) atomicAdd(&d.sc[SC_COST], s);
+    } else {
+      d.sc[SC_NONFINITE] = 1.0;
+    }
+  }
+  s = block_sum_1(dp2, s_red);
+  if (threadIdx.x == 0 && s != 0) atomicAdd(&d.sc[SC_DP_L2], s);
+  s = block_sum_1(dl, s_red);
+  if (threadIdx.x == 0 && s != 0) atomicAdd(&d.sc[SC_DL], s);
+  s = block_sum_1(p2, s_red);
+  if (threadIdx.x == 0 && s != 0) atomicAdd(&d.sc[SC_P_L2], s);
 }
 
 }  // namespace coslam
