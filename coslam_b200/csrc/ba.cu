@@ -119,6 +119,7 @@ struct cosl_ba_solver {
   int nSlots = 1;
   size_t rowsSmem = 0;
   bool useRows = false;
+  cudaEvent_t evBlock = nullptr;  // blocking-sync event of the multi-GPU scalar read-back
   bool costDone = false;         // solve_trial already evaluated the trial cost (ba_finish_cost)
   bool statsPending = false;     // |g|_inf / max diag of the last linearisation still to be computed (prep kernel)
   unsigned long long scSeq = 0;  // sequence number of the last scalar read-back (ba_publish_sc)
@@ -329,6 +330,7 @@ void free_solver(cosl_ba_solver* s) {
   for (void* b : bufs)
     if (b) cudaFreeAsync(b, s->stream);
   if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->evBlock) cudaEventDestroy(s->evBlock);
   if (s->h_sc) pinned_slots().put(s->h_sc);
   if (s->stream) cudaStreamDestroy(s->stream);
   delete s;
@@ -926,10 +928,18 @@ __global__ void ba_publish_sc(const double* __restrict__ sc, volatile double* ho
 
 int read_sc(cosl_ba_solver* s) {
   static const bool syncReadback = std::getenv("COSL_BA_SYNC_READBACK") != nullptr;
-  if (syncReadback) {
+  // multi-GPU: N ranks spinning on N host threads compete with NCCL's proxy threads for the cores of a
+  // (possibly small) cgroup; the blocking read-back is used there
+  if (syncReadback || multi(s)) {
     COSL_CUDA(cudaMemcpyAsync(s->h_sc, s->d_sc, sizeof(double) * SC_NTOT, cudaMemcpyDeviceToHost,
                               s->stream));
-    COSL_CUDA(cudaStreamSynchronize(s->stream));
+    if (multi(s)) {  // yield the core while waiting (cudaStreamSynchronize spins)
+      if (!s->evBlock) COSL_CUDA(cudaEventCreateWithFlags(&s->evBlock, cudaEventBlockingSync | cudaEventDisableTiming));
+      COSL_CUDA(cudaEventRecord(s->evBlock, s->stream));
+      COSL_CUDA(cudaEventSynchronize(s->evBlock));
+    } else {
+      COSL_CUDA(cudaStreamSynchronize(s->stream));
+    }
     return COSL_OK;
   }
   const unsigned long long seq = ++s->scSeq;
