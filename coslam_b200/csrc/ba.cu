@@ -928,12 +928,15 @@ __global__ void ba_publish_sc(const double* __restrict__ sc, volatile double* ho
 
 int read_sc(cosl_ba_solver* s) {
   static const bool syncReadback = std::getenv("COSL_BA_SYNC_READBACK") != nullptr;
-  // multi-GPU: N ranks spinning on N host threads compete with NCCL's proxy threads for the cores of a
-  // (possibly small) cgroup; the blocking read-back is used there
-  if (syncReadback || multi(s)) {
+  // multi-GPU on a crowded host (fewer than 3 usable cores per rank, e.g. 8 ranks in a 16-thread cgroup):
+  // N ranks spinning on N host threads compete with NCCL's proxy threads; read back with a blocking,
+  // core-yielding wait there.  Otherwise: zero-copy publish + spin.
+  static const bool forceBlock = std::getenv("COSL_BA_BLOCKING_READBACK") != nullptr;  // test hook
+  const bool crowded = multi(s) && (forceBlock || host_threads_all() < 3 * s->comm->nranks);
+  if (syncReadback || crowded) {
     COSL_CUDA(cudaMemcpyAsync(s->h_sc, s->d_sc, sizeof(double) * SC_NTOT, cudaMemcpyDeviceToHost,
                               s->stream));
-    if (multi(s)) {  // yield the core while waiting (cudaStreamSynchronize spins)
+    if (crowded) {  // yield the core while waiting (cudaStreamSynchronize spins)
       if (!s->evBlock) COSL_CUDA(cudaEventCreateWithFlags(&s->evBlock, cudaEventBlockingSync | cudaEventDisableTiming));
       COSL_CUDA(cudaEventRecord(s->evBlock, s->stream));
       COSL_CUDA(cudaEventSynchronize(s->evBlock));
