@@ -928,15 +928,16 @@ __global__ void ba_publish_sc(const double* __restrict__ sc, volatile double* ho
 
 int read_sc(cosl_ba_solver* s) {
   static const bool syncReadback = std::getenv("COSL_BA_SYNC_READBACK") != nullptr;
-  // multi-GPU on a crowded host (fewer than 3 usable cores per rank, e.g. 8 ranks in a 16-thread cgroup):
-  // N ranks spinning on N host threads compete with NCCL's proxy threads; read back with a blocking,
-  // core-yielding wait there.  Otherwise: zero-copy publish + spin.
-  static const bool forceBlock = std::getenv("COSL_BA_BLOCKING_READBACK") != nullptr;  // test hook
-  const bool crowded = multi(s) && (forceBlock || host_threads_all() < 3 * s->comm->nranks);
-  if (syncReadback || crowded) {
+  // multi-GPU on a crowded host (fewer than 3 usable cores per rank, e.g. 8 ranks in a 16-thread cgroup): the
+  // copy-engine read-back + stream synchronise of round 1 is kept there (measured 0.94 ms / trial at N = 8
+  // against 1.00 with N ranks polling mapped memory next to NCCL's proxy threads; at N = 2 the polling
+  // read-back wins, 0.98 vs 1.03 ms for a blocking wait).  COSL_BA_BLOCKING_READBACK=1: core-yielding wait.
+  static const bool forceBlock = std::getenv("COSL_BA_BLOCKING_READBACK") != nullptr;
+  const bool crowded = multi(s) && host_threads_all() < 3 * s->comm->nranks;
+  if (syncReadback || crowded || (forceBlock && multi(s))) {
     COSL_CUDA(cudaMemcpyAsync(s->h_sc, s->d_sc, sizeof(double) * SC_NTOT, cudaMemcpyDeviceToHost,
                               s->stream));
-    if (crowded) {  // yield the core while waiting (cudaStreamSynchronize spins)
+    if (forceBlock) {
       if (!s->evBlock) COSL_CUDA(cudaEventCreateWithFlags(&s->evBlock, cudaEventBlockingSync | cudaEventDisableTiming));
       COSL_CUDA(cudaEventRecord(s->evBlock, s->stream));
       COSL_CUDA(cudaEventSynchronize(s->evBlock));
