@@ -57,6 +57,8 @@ struct BaTask {  // 64 bytes, read by every thread of the CTA that executes it
 struct BaBwdEntry {
   int blk;   // block row i of struct(k)
   int tile;  // tile index of (i, k)
+  int fin;   // value of the tile's counter when L_ik is final (all updates + its TRSM)
+  int pad;
 };
 
 struct BaSumEntry {
@@ -440,8 +442,12 @@ inline BaPlan ba_make_plan(int mf, const std::vector<uint8_t>& adj, int ndDepthO
     t.l0 = (int)P.bwdList.size();
     const int id = push(t, cBwd);
     preds[id].push_back(potrfTask[k]);
-    for (int i : strct[k]) {
-      P.bwdList.push_back({i, T(i, k)});
+    // oldest solution first: x_i of the LARGEST i was produced first (BWD runs nb-1 .. 0), the smallest i
+    // last -- the kernel polls per chunk of entries, so only the last chunk waits for the predecessor on
+    // the chain while the others (and the tile loads of the last one) overlap with it
+    for (auto it = strct[k].rbegin(); it != strct[k].rend(); ++it) {
+      const int i = *it;
+      P.bwdList.push_back({i, T(i, k), nupd[T(i, k)] + 1, 0});
       preds[id].push_back(bwdTask[i]);
     }
     gen[id].l1 = (int)P.bwdList.size();

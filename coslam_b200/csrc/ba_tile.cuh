@@ -474,9 +474,7 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
         while (ld_acquire(d.cnt + t.w1i) < t.w1v) {}
       if (tid == 2 && t.w2i >= 0)
         while (ld_acquire(d.cnt + t.w2i) < t.w2v) {}
-      if (t.type == BA_T_BWD)
-        for (int e = t.l0 + tid; e < t.l1; e += 32)
-          while (ld_acquire(d.cnt + d.xdoneBase + d.bwd[e].blk) < 1) {}
+      // (BWD polls the x_i it needs chunk by chunk, see below)
       if (t.type == BA_T_SUM)
         for (int e = t.l0 + tid; e < t.l1; e += 32)
           while (ld_acquire(d.cnt + d.sum[e].tile) < d.sum[e].count) {}
@@ -652,29 +650,37 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
       double p[8];
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) p[jj] = 0.0;
-      for (int e0 = t.l0; e0 < t.l1; e0 += 8) {
-        const int ne = min(8, t.l1 - e0);
+      // Entries are ordered oldest solution first (ba_plan.h).  Per chunk of 4: the tile loads are issued, THEN
+      // the chunk's x_i are awaited -- only the last chunk contains the x of the predecessor on the backward
+      // chain, and its tiles are already in flight while that predecessor finishes.
+      for (int e0 = t.l0; e0 < t.l1; e0 += 4) {
+        const int ne = min(4, t.l1 - e0);
+        // L_ik must be final before it is read: TRSM(i, k) is not an ancestor of BWD(k) except through x_i,
+        // which is awaited only after the loads are issued
+        __syncthreads();  // (also: sX of the previous chunk is consumed)
+        if (tid < ne)
+          while (ld_acquire(d.cnt + d.bwd[e0 + tid].tile) < d.bwd[e0 + tid].fin) {}
         __syncthreads();
-        for (int u = tid; u < ne * BA_TB; u += BA_NTHREADS)
-          sX[u] = __ldcg(d.x + (size_t)d.bwd[e0 + (u >> 6)].blk * BA_TB + (u & 63));
+        double2 v[4][8];
+#pragma unroll
+        for (int w4 = 0; w4 < 4; ++w4) {
+          const int e = min(w4, ne - 1);
+          const double2* col = reinterpret_cast<const double2*>(
+              d.tiles + (size_t)d.bwd[e0 + e].tile * BA_TILE + (8 * wq) * BA_TB) + lane;
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) v[w4][jj] = __ldcg(col + jj * (BA_TB / 2));
+        }
+        if (tid < ne)
+          while (ld_acquire(d.cnt + d.xdoneBase + d.bwd[e0 + tid].blk) < 1) {}
         __syncthreads();
-        for (int eb = 0; eb < ne; eb += 4) {
-          double2 v[4][8];
+        if (tid < ne * BA_TB) sX[tid] = __ldcg(d.x + (size_t)d.bwd[e0 + (tid >> 6)].blk * BA_TB + (tid & 63));
+        __syncthreads();
 #pragma unroll
-          for (int w4 = 0; w4 < 4; ++w4) {
-            const int e = min(eb + w4, ne - 1);
-            const double2* col = reinterpret_cast<const double2*>(
-                d.tiles + (size_t)d.bwd[e0 + e].tile * BA_TILE + (8 * wq) * BA_TB) + lane;
+        for (int w4 = 0; w4 < 4; ++w4) {
+          if (w4 < ne) {
+            const double2 xv = *reinterpret_cast<const double2*>(sX + w4 * BA_TB + 2 * lane);
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) v[w4][jj] = __ldcg(col + jj * (BA_TB / 2));
-          }
-#pragma unroll
-          for (int w4 = 0; w4 < 4; ++w4) {
-            if (eb + w4 < ne) {
-              const double2 xv = *reinterpret_cast<const double2*>(sX + (eb + w4) * BA_TB + 2 * lane);
-#pragma unroll
-              for (int jj = 0; jj < 8; ++jj) p[jj] = __fma_rn(v[w4][jj].x, xv.x, __fma_rn(v[w4][jj].y, xv.y, p[jj]));
-            }
+            for (int jj = 0; jj < 8; ++jj) p[jj] = __fma_rn(v[w4][jj].x, xv.x, __fma_rn(v[w4][jj].y, xv.y, p[jj]));
           }
         }
       }
