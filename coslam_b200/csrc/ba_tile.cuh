@@ -403,8 +403,12 @@ __device__ __forceinline__ void ba_upd_body(const BaTileDev& d, const BaTask& t,
         }
   }
   if (!staged) {
-    tile_load2<BA_LDS>(d.tiles + (size_t)t.tA * BA_TILE, sA, d.tiles + (size_t)t.tB * BA_TILE, sB, tid);
+    tile_load<BA_LDS>(d.tiles + (size_t)t.tB * BA_TILE, sB, tid);  // B = L_jk and C: awaited up front
     if ((t.flags & 1) && tid < 64) sY[tid] = __ldcg(d.y + (size_t)t.k * BA_TB + tid);
+    if (tid == 0 && t.w1i >= 0)
+      while (ld_acquire(d.cnt + t.w1i) < t.w1v) {}  // A = L_ik (deferred wait)
+    __syncthreads();
+    tile_load<BA_LDS>(d.tiles + (size_t)t.tA * BA_TILE, sA, tid);
     __syncthreads();
   }
   if (d.trace && tid == 0) d.trace[8 * (size_t)ti + 4] = ba_globaltimer();
@@ -468,9 +472,11 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
         d.trace[8 * (size_t)ti + 1] = ba_globaltimer();
       }
       // the lanes of warp 0 poll different counters concurrently
-      if (tid == 0 && t.w0i >= 0)
+      // TRSM defers the wait for its own tile (w0) and UPD the wait for its A operand (w1) until the other
+      // operands are on their way into shared memory: on the dependency chains those are the late ones
+      if (tid == 0 && t.w0i >= 0 && t.type != BA_T_TRSM)
         while (ld_acquire(d.cnt + t.w0i) < t.w0v) {}
-      if (tid == 1 && t.w1i >= 0)
+      if (tid == 1 && t.w1i >= 0 && t.type != BA_T_UPD)
         while (ld_acquire(d.cnt + t.w1i) < t.w1v) {}
       if (tid == 2 && t.w2i >= 0)
         while (ld_acquire(d.cnt + t.w2i) < t.w2v) {}
@@ -594,9 +600,13 @@ __global__ void __launch_bounds__(BA_NTHREADS, 1) ba_tile_solve(BaTileDev d) {
       // L_ik = A_ik L_kk^-T by blocked substitution (tile_trsm2); every warp owns 8 rows
       double* gC = d.tiles + (size_t)t.tC * BA_TILE;
       const double* gm = d.Linv + (size_t)t.tA * BA_TILE;
-      tile_load2<BA_LDS>(gC, sA, d.tiles + (size_t)t.w1i * BA_TILE, sB, tid);
+      tile_load<BA_LDS>(d.tiles + (size_t)t.w1i * BA_TILE, sB, tid);  // L_kk: awaited up front
       sM[tid] = __ldcg(gm + tid);
       sM[tid + BA_NTHREADS] = __ldcg(gm + tid + BA_NTHREADS);
+      if (tid == 0 && t.w0i >= 0)
+        while (ld_acquire(d.cnt + t.w0i) < t.w0v) {}  // A_ik has received all its updates
+      __syncthreads();
+      tile_load<BA_LDS>(gC, sA, tid);
       __syncthreads();
       if (d.trace && tid == 0) d.trace[8 * (size_t)ti + 4] = ba_globaltimer();
       tile_trsm2(sA, sB, sM, (bk + 7) >> 3, tid);
